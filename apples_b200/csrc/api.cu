@@ -1,0 +1,840 @@
+// C ABI (include/apples_b200.h): context, device buffers, and the per-batch pipeline
+//   H2D -> transpose -> dense representative distances -> selection (+ member distances) -> placement -> D2H
+// that replaces pool.starmap(queryworker.runquery, queries) (run_apples.py:94-102).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+enum Stage { T_H2D = 0, T_TRANSPOSE, T_DENSE, T_SELECT, T_PLACE, T_D2H, T_NSTAGE };
+
+struct TimedSpan {
+    int stage;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct apples_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // tree
+    int M = 0;
+    DevBuf t_parent, t_elen, t_level, t_first;
+    // reference
+    int kind = -1, L = 0, W = 0, Wp = 0, Lp = 0, n_ref = 0, n_rep = 0, rep_pad = 0, ref_pad = 0;
+    DevBuf refs_rm, reps_rm, reps_wm, refs_wm, ref_node, goff, gmem;
+    bool refs_wm_ready = false;
+    // matrix mode
+    int n_cols = 0;
+    DevBuf col_node;
+    // per-batch work buffers
+    DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, Kd, Vd, statusd, zero_edge, pair_counter;
+    DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
+    DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
+    DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
+    // resident queries
+    DevBuf res_q, res_self;
+    int64_t res_nq = 0;
+    bool res_has_self = false;
+    DevBuf res_edge, res_err, res_distal, res_pendant, res_status;
+    // timing
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double t_ms[T_NSTAGE] = {0, 0, 0, 0, 0, 0};
+    double n_launch = 0, n_dense_launch = 0, n_pairs = 0, n_obs = 0, n_valid = 0;
+    size_t scratch_limit = (size_t)6 << 30;  // placement scratch pool upper bound (bytes)
+    int64_t max_subbatch = 32768;
+    int slot_cap = 256;
+};
+
+namespace {
+
+int fail(apples_ctx* c, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                       \
+    } while (0)
+
+int ensure(apples_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return 0;
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = std::max<size_t>(bytes, 256);
+    CK(cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return 0;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+cudaEvent_t get_event(apples_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Span {
+    apples_ctx* ctx;
+    TimedSpan s;
+    Span(apples_ctx* c, int stage) : ctx(c) {
+        s.stage = stage;
+        s.a = get_event(c);
+        s.b = get_event(c);
+        cudaEventRecord(s.a, c->stream);
+    }
+    ~Span() {
+        cudaEventRecord(s.b, ctx->stream);
+        ctx->spans.push_back(s);
+    }
+};
+
+void collect_spans(apples_ctx* ctx) {
+    for (auto& s : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ctx->t_ms[s.stage] += ms;
+        ctx->ev_pool.push_back(s.a);
+        ctx->ev_pool.push_back(s.b);
+    }
+    ctx->spans.clear();
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int next_pow2(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// smallest valid-site count v with NOT (v / L < overlap_frac)  (distance.py:735, IEEE double division)
+int overlap_vmin(int L, double overlap) {
+    int lo = 0, hi = L + 1;  // invariant: lo fails (or is 0), hi passes (or is L+1)
+    while (hi - lo > 1) {
+        int mid = lo + (hi - lo) / 2;
+        if ((double)mid / (double)L < overlap) lo = mid; else hi = mid;
+    }
+    if (hi > L) return L + 1;
+    // v == 0 always fails (`not valid`)
+    return std::max(hi, 1);
+}
+
+NucGate make_gate(int L, double thr, double overlap) {
+    NucGate g;
+    g.L = L;
+    g.vmin = overlap_vmin(L, overlap);
+    g.thr = thr;
+    // dist <= thr  <=>  p <= p*, p* = 0.75 (1 - exp(-4 thr / 3)); +-1e-9 relative guard band, exact evaluation inside it
+    double pstar = 0.75 * (1.0 - std::exp(-4.0 * thr / 3.0));
+    if (!(thr >= 0.0)) pstar = -1.0;
+    g.p_lo = pstar > 0 ? pstar * (1.0 - 1e-9) : -1.0;
+    g.p_hi = pstar > 0 ? pstar * (1.0 + 1e-9) : 0.0;
+    if (pstar >= 0.75 * (1.0 - 1e-9)) {  // threshold so large that every valid pair is near
+        g.p_lo = 2.0;
+        g.p_hi = 3.0;
+    }
+    return g;
+}
+
+TreeDev tree_dev(apples_ctx* ctx) {
+    TreeDev t;
+    t.M = ctx->M;
+    t.parent = (const int*)ctx->t_parent.p;
+    t.elen = (const double*)ctx->t_elen.p;
+    t.level = (const int*)ctx->t_level.p;
+    t.first = (const int*)ctx->t_first.p;
+    return t;
+}
+
+size_t query_row_bytes(const apples_ctx* ctx) {
+    return ctx->kind == APPLES_AA ? (size_t)ctx->Lp : (size_t)3 * ctx->W * 4;
+}
+
+struct BatchIO {
+    // exactly one of these input sources
+    const void* h_queries = nullptr;   // host packed queries
+    const void* d_queries = nullptr;   // device packed queries (resident)
+    const double* h_rows = nullptr;    // host matrix rows
+    const int32_t* h_self = nullptr;
+    const int32_t* d_self = nullptr;
+    // outputs: host pointers or device pointers
+    int32_t* edge = nullptr; double* error = nullptr; double* distal = nullptr; double* pendant = nullptr;
+    int32_t* status = nullptr;
+    bool out_on_device = false;
+    // parity exports
+    int obs_cap = 0; int32_t* obs_count = nullptr; int32_t* obs_node = nullptr; double* obs_dist = nullptr;
+    bool stop_after_select = false;
+    double* dbg_x1 = nullptr; double* dbg_x2 = nullptr; double* dbg_err = nullptr; uint8_t* dbg_valid = nullptr;
+};
+
+int check_params(apples_ctx* ctx, const apples_params* p) {
+    if (!p) return fail(ctx, "params is NULL");
+    if (p->method < 0 || p->method > 3) return fail(ctx, "unknown method %d", p->method);
+    if (p->criterion < 0 || p->criterion > 2) return fail(ctx, "unknown criterion %d", p->criterion);
+    return 0;
+}
+
+// the whole pipeline for nq queries, processed in sub-batches
+int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_params* prm) {
+    if (check_params(ctx, prm)) return -1;
+    if (ctx->M <= 0) return fail(ctx, "apples_set_tree has not been called");
+    const bool matrix = io.h_rows != nullptr;
+    if (matrix && ctx->n_cols <= 0) return fail(ctx, "apples_set_matrix_columns has not been called");
+    if (!matrix && ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
+    if (nq <= 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int sel_kind = matrix ? SEL_MATRIX : (ctx->kind == APPLES_AA ? SEL_AA : SEL_NUC);
+    const int n_units = matrix ? ctx->n_cols : ctx->n_rep;
+    const int64_t ldk = matrix ? ctx->n_cols : ctx->rep_pad;
+    const size_t key_bytes = (sel_kind == SEL_NUC) ? 4 : 8;
+    const int n_leaf_bound = matrix ? ctx->n_cols : ctx->n_ref;
+
+    // sub-batch size: key matrix <= 1 GiB, at most 32768 queries, multiple of the dense tile
+    int64_t qb = ((int64_t)1 << 30) / std::max<int64_t>(1, ldk * (int64_t)key_bytes);
+    qb = std::min<int64_t>(std::max<int64_t>(qb, DT_TQ), std::max<int64_t>(ctx->max_subbatch, DT_TQ));
+    qb = qb / DT_TQ * DT_TQ;
+    qb = std::min<int64_t>(qb, round_up((int)std::min<int64_t>(nq, 1 << 30), DT_TQ));
+    const int QB = (int)qb;
+    int cap = io.obs_cap > 0 ? next_pow2(io.obs_cap) : std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
+
+    const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
+    if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
+    if (!matrix) {
+        if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
+        if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
+    }
+    if (ensure(ctx, ctx->self_node, (size_t)QB * 4)) return -1;
+    if (ensure(ctx, ctx->obs_node, (size_t)QB * cap * 4)) return -1;
+    if (ensure(ctx, ctx->obs_dist, (size_t)QB * cap * 8)) return -1;
+    if (ensure(ctx, ctx->Kd, (size_t)QB * 4) || ensure(ctx, ctx->Vd, (size_t)QB * 4) ||
+        ensure(ctx, ctx->statusd, (size_t)QB * 4) || ensure(ctx, ctx->zero_edge, (size_t)QB * 4))
+        return -1;
+    if (ensure(ctx, ctx->pair_counter, 8)) return -1;
+    if (ensure(ctx, ctx->o_edge, (size_t)QB * 4) || ensure(ctx, ctx->o_err, (size_t)QB * 8) ||
+        ensure(ctx, ctx->o_distal, (size_t)QB * 8) || ensure(ctx, ctx->o_pendant, (size_t)QB * 8) ||
+        ensure(ctx, ctx->o_status, (size_t)QB * 4))
+        return -1;
+    if (ensure(ctx, ctx->rec_off, (size_t)QB * 8) || ensure(ctx, ctx->stack_off, (size_t)QB * 8) ||
+        ensure(ctx, ctx->qlist, (size_t)QB * 4))
+        return -1;
+    CK(cudaMemsetAsync(ctx->pair_counter.p, 0, 8, s));
+    const bool dbg = io.dbg_x1 != nullptr;
+    if (dbg) {
+        if (ensure(ctx, ctx->dbg_x1, (size_t)ctx->M * 8) || ensure(ctx, ctx->dbg_x2, (size_t)ctx->M * 8) ||
+            ensure(ctx, ctx->dbg_err, (size_t)ctx->M * 8) || ensure(ctx, ctx->dbg_valid, (size_t)ctx->M))
+            return -1;
+        CK(cudaMemsetAsync(ctx->dbg_x1.p, 0, (size_t)ctx->M * 8, s));
+        CK(cudaMemsetAsync(ctx->dbg_x2.p, 0, (size_t)ctx->M * 8, s));
+        CK(cudaMemsetAsync(ctx->dbg_err.p, 0, (size_t)ctx->M * 8, s));
+        CK(cudaMemsetAsync(ctx->dbg_valid.p, 0, (size_t)ctx->M, s));
+    }
+
+    std::vector<int> hK(QB), hV(QB), hS(QB);
+    std::vector<long long> h_rec_off(QB), h_stack_off(QB);
+    std::vector<int> h_qlist(QB);
+    const NucGate gate = make_gate(ctx->L, prm->filt_threshold, prm->overlap_frac);
+
+    for (int64_t base = 0; base < nq; base += QB) {
+        const int nb = (int)std::min<int64_t>(QB, nq - base);
+        const int nb_pad = round_up(nb, DT_TQ);
+        // ---------------- inputs ----------------
+        const void* d_q = nullptr;
+        const double* d_rows = nullptr;
+        {
+            Span sp(ctx, T_H2D);
+            if (matrix) {
+                CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)base * ctx->n_cols, (size_t)nb * qrow,
+                                   cudaMemcpyHostToDevice, s));
+                d_rows = (const double*)ctx->keys.p;
+            } else if (io.h_queries) {
+                CK(cudaMemcpyAsync(ctx->q_rm.p, (const char*)io.h_queries + (size_t)base * qrow, (size_t)nb * qrow,
+                                   cudaMemcpyHostToDevice, s));
+                d_q = ctx->q_rm.p;
+            } else {
+                d_q = (const char*)io.d_queries + (size_t)base * qrow;
+            }
+            if (io.h_self)
+                CK(cudaMemcpyAsync(ctx->self_node.p, io.h_self + base, (size_t)nb * 4, cudaMemcpyHostToDevice, s));
+        }
+        const int* d_self = io.h_self ? (const int*)ctx->self_node.p : (io.d_self ? io.d_self + base : nullptr);
+
+        // ---------------- representative distances ----------------
+        if (sel_kind == SEL_NUC) {
+            {
+                Span sp(ctx, T_TRANSPOSE);
+                launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, s);
+                ctx->n_launch += 1;
+            }
+            {
+                Span sp(ctx, T_DENSE);
+                launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, nb_pad, (const uint32_t*)ctx->reps_wm.p, ctx->rep_pad,
+                                      ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
+                ctx->n_launch += 1;
+                ctx->n_dense_launch += 1;
+            }
+            ctx->n_pairs += (double)nb * ctx->n_rep;
+        } else if (sel_kind == SEL_AA) {
+            Span sp(ctx, T_DENSE);
+            launch_dense_aa((const uint8_t*)d_q, nb, (const uint8_t*)ctx->reps_rm.p, ctx->n_rep, ctx->Lp, ctx->L,
+                            prm->overlap_frac, (double*)ctx->keys.p, ldk, nullptr, s);
+            ctx->n_launch += 1;
+            ctx->n_dense_launch += 1;
+            ctx->n_pairs += (double)nb * ctx->n_rep;
+        }
+        CK(cudaGetLastError());
+
+        // ---------------- selection ----------------
+        SelectArgs sa{};
+        sa.n = nb;
+        sa.qlist = nullptr;
+        sa.n_units = n_units;
+        sa.ldk = ldk;
+        sa.keys_nuc = (const uint32_t*)ctx->keys.p;
+        sa.keys_f64 = matrix ? d_rows : (const double*)ctx->keys.p;
+        sa.goff = (const int*)ctx->goff.p;
+        sa.gmem = (const int*)ctx->gmem.p;
+        sa.ref_node = (const int*)ctx->ref_node.p;
+        sa.refs_nuc = (const uint32_t*)ctx->refs_rm.p;
+        sa.q_nuc = (const uint32_t*)d_q;
+        sa.W = ctx->W;
+        sa.refs_aa = (const uint8_t*)ctx->refs_rm.p;
+        sa.q_aa = (const uint8_t*)d_q;
+        sa.Lp = ctx->Lp;
+        sa.L = ctx->L;
+        sa.col_node = (const int*)ctx->col_node.p;
+        sa.self_node = d_self;
+        sa.thr = prm->filt_threshold;
+        sa.baseobs = prm->base_observation_threshold;
+        sa.overlap = prm->overlap_frac;
+        sa.gate = gate;
+        sa.cap = cap;
+        sa.obs_node = (int*)ctx->obs_node.p;
+        sa.obs_dist = (double*)ctx->obs_dist.p;
+        sa.K = (int*)ctx->Kd.p;
+        sa.V = (int*)ctx->Vd.p;
+        sa.status = (int*)ctx->statusd.p;
+        sa.zero_edge = (int*)ctx->zero_edge.p;
+        sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
+        sa.tree = tree_dev(ctx);
+        {
+            Span sp(ctx, T_SELECT);
+            launch_select(sel_kind, sa, s);
+            ctx->n_launch += 1;
+        }
+        CK(cudaGetLastError());
+        {
+            Span sp(ctx, T_D2H);
+            CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+
+        // ---------------- overflow reruns: queries whose observed set exceeds the slot capacity ----------------
+        int n_over = 0, maxK = 0;
+        for (int i = 0; i < nb; ++i)
+            if (hS[i] == ST_OVERFLOW) {
+                h_qlist[n_over++] = i;
+                maxK = std::max(maxK, hK[i]);
+            }
+        int cap2 = 0;
+        if (n_over) {
+            cap2 = next_pow2(maxK);
+            if (ensure(ctx, ctx->obs_node2, (size_t)n_over * cap2 * 4)) return -1;
+            if (ensure(ctx, ctx->obs_dist2, (size_t)n_over * cap2 * 8)) return -1;
+            CK(cudaMemcpyAsync(ctx->qlist.p, h_qlist.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, s));
+            SelectArgs sb = sa;
+            sb.n = n_over;
+            sb.qlist = (const int*)ctx->qlist.p;
+            sb.cap = cap2;
+            sb.obs_node = (int*)ctx->obs_node2.p;
+            sb.obs_dist = (double*)ctx->obs_dist2.p;
+            sb.pair_counter = nullptr;
+            {
+                Span sp(ctx, T_SELECT);
+                launch_select(sel_kind, sb, s);
+                ctx->n_launch += 1;
+            }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        std::vector<char> is_over(nb, 0);
+        for (int i = 0; i < n_over; ++i) is_over[h_qlist[i]] = 1;
+
+        // ---------------- parity export of the observed sets ----------------
+        if (io.obs_count) {
+            for (int i = 0; i < nb; ++i) io.obs_count[base + i] = hK[i];
+            const int ocap = io.obs_cap;
+            std::vector<int> tn((size_t)nb * cap);
+            std::vector<double> td((size_t)nb * cap);
+            CK(cudaMemcpy(tn.data(), ctx->obs_node.p, tn.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(td.data(), ctx->obs_dist.p, td.size() * 8, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < nb; ++i) {
+                if (is_over[i]) continue;
+                const int k = std::min(std::min(hK[i], cap), ocap);
+                memcpy(io.obs_node + (size_t)(base + i) * ocap, &tn[(size_t)i * cap], (size_t)k * 4);
+                memcpy(io.obs_dist + (size_t)(base + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
+            }
+            if (n_over) {
+                std::vector<int> un((size_t)n_over * cap2);
+                std::vector<double> ud((size_t)n_over * cap2);
+                CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
+                for (int j = 0; j < n_over; ++j) {
+                    const int i = h_qlist[j];
+                    const int k = std::min(hK[i], ocap);
+                    memcpy(io.obs_node + (size_t)(base + i) * ocap, &un[(size_t)j * cap2], (size_t)k * 4);
+                    memcpy(io.obs_dist + (size_t)(base + i) * ocap, &ud[(size_t)j * cap2], (size_t)k * 8);
+                }
+            }
+        }
+        for (int i = 0; i < nb; ++i)
+            if (hS[i] == ST_PLACE) {
+                ctx->n_obs += hK[i];
+                ctx->n_valid += hV[i];
+            }
+        if (io.stop_after_select) continue;
+
+        // ---------------- placement: plan scratch, launch in chunks ----------------
+        PlaceArgs pa{};
+        pa.K = (const int*)ctx->Kd.p;
+        pa.status = (const int*)ctx->statusd.p;
+        pa.zero_edge = (const int*)ctx->zero_edge.p;
+        pa.criterion = prm->criterion;
+        pa.negative_branch = prm->negative_branch;
+        pa.tree = tree_dev(ctx);
+        pa.out_edge = (int*)ctx->o_edge.p;
+        pa.out_error = (double*)ctx->o_err.p;
+        pa.out_distal = (double*)ctx->o_distal.p;
+        pa.out_pendant = (double*)ctx->o_pendant.p;
+        pa.out_status = (int*)ctx->o_status.p;
+        pa.dbg_query = dbg ? 0 : -1;
+        pa.dbg_x1 = dbg ? (double*)ctx->dbg_x1.p : nullptr;
+        pa.dbg_x2 = (double*)ctx->dbg_x2.p;
+        pa.dbg_err = (double*)ctx->dbg_err.p;
+        pa.dbg_valid = (unsigned char*)ctx->dbg_valid.p;
+
+        // pass A: the regular slots (identity mapping), chunked by scratch size; pass B: the overflow reruns
+        for (int pass = 0; pass < 2; ++pass) {
+            const int n_items = pass == 0 ? nb : n_over;
+            int i0 = 0;
+            while (i0 < n_items) {
+                long long recs = 0, stk = 0;
+                int i1 = i0;
+                while (i1 < n_items) {
+                    const int qi = pass == 0 ? i1 : h_qlist[i1];
+                    long long v = 0, k = 0;
+                    const bool active = hS[qi] == ST_PLACE && (pass == 1 || !is_over[qi]);
+                    if (active) { v = hV[qi]; k = hK[qi]; }
+                    if (i1 > i0 && (size_t)(recs + v) * sizeof(NodeRec) > ctx->scratch_limit) break;
+                    // -1: a query whose observed set lives in the other pass's buffers (kernel skips it)
+                    h_rec_off[i1 - i0] = (hS[qi] == ST_PLACE && !active) ? -1 : recs;
+                    h_stack_off[i1 - i0] = stk;
+                    recs += v;
+                    stk += k;
+                    ++i1;
+                }
+                if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * sizeof(NodeRec))) return -1;
+                if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * sizeof(StackEnt))) return -1;
+                CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, s));
+                pa.n = i1 - i0;
+                pa.rec_off = (const long long*)ctx->rec_off.p;
+                pa.stack_off = (const long long*)ctx->stack_off.p;
+                pa.recs = (NodeRec*)ctx->recs.p;
+                pa.stacks = (StackEnt*)ctx->stacks.p;
+                if (pass == 0) {
+                    pa.qlist = nullptr;
+                    pa.q_begin = i0;
+                    pa.cap = cap;
+                    pa.obs_node = (const int*)ctx->obs_node.p;
+                    pa.obs_dist = (const double*)ctx->obs_dist.p;
+                } else {
+                    pa.qlist = (const int*)ctx->qlist.p + i0;
+                    pa.q_begin = 0;
+                    pa.cap = cap2;
+                    pa.obs_node = (const int*)ctx->obs_node2.p + (size_t)i0 * cap2;
+                    pa.obs_dist = (const double*)ctx->obs_dist2.p + (size_t)i0 * cap2;
+                }
+                {
+                    Span sp(ctx, T_PLACE);
+                    launch_place(prm->method, pa, s);
+                    ctx->n_launch += 1;
+                }
+                CK(cudaGetLastError());
+                // the offsets live in host vectors that the next chunk overwrites
+                CK(cudaStreamSynchronize(s));
+                i0 = i1;
+            }
+        }
+
+        // ---------------- outputs ----------------
+        {
+            Span sp(ctx, T_D2H);
+            const cudaMemcpyKind kd = io.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+            CK(cudaMemcpyAsync(io.edge + base, ctx->o_edge.p, (size_t)nb * 4, kd, s));
+            CK(cudaMemcpyAsync(io.error + base, ctx->o_err.p, (size_t)nb * 8, kd, s));
+            CK(cudaMemcpyAsync(io.distal + base, ctx->o_distal.p, (size_t)nb * 8, kd, s));
+            CK(cudaMemcpyAsync(io.pendant + base, ctx->o_pendant.p, (size_t)nb * 8, kd, s));
+            CK(cudaMemcpyAsync(io.status + base, ctx->o_status.p, (size_t)nb * 4, kd, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    }
+    if (dbg) {
+        CK(cudaMemcpy(io.dbg_x1, ctx->dbg_x1.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(io.dbg_x2, ctx->dbg_x2.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(io.dbg_err, ctx->dbg_err.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(io.dbg_valid, ctx->dbg_valid.p, (size_t)ctx->M, cudaMemcpyDeviceToHost));
+    }
+    {
+        unsigned long long pc = 0;
+        CK(cudaMemcpy(&pc, ctx->pair_counter.p, 8, cudaMemcpyDeviceToHost));
+        ctx->n_pairs += (double)pc;
+    }
+    collect_spans(ctx);
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+int32_t apples_words_per_row(int32_t L) { return ((L + 31) / 32 + 3) / 4 * 4; }
+int32_t apples_aa_row_bytes(int32_t L) { return (L + 15) / 16 * 16; }
+
+int apples_ctx_create(int device, apples_ctx** out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return -2;
+    if (cudaSetDevice(device) != cudaSuccess) return -3;
+    apples_ctx* ctx = new apples_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return -4;
+    }
+    if (dense_nuc_configure() != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return -5;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void apples_ctx_destroy(apples_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
+                     &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
+                     &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->Kd, &ctx->Vd,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
+                     &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
+                     &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
+                     &ctx->res_pendant, &ctx->res_status};
+    for (DevBuf* b : all) release(*b);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto& sp : ctx->spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* apples_last_error(const apples_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* apples_ctx_stream(apples_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int apples_ctx_set_limits(apples_ctx* ctx, int64_t max_subbatch, int64_t scratch_bytes, int32_t slot_cap) {
+    if (!ctx) return -1;
+    if (max_subbatch > 0) ctx->max_subbatch = max_subbatch;
+    if (scratch_bytes > 0) ctx->scratch_limit = (size_t)scratch_bytes;
+    if (slot_cap > 0) ctx->slot_cap = next_pow2(std::max(4, slot_cap));
+    return 0;
+}
+
+int apples_set_tree(apples_ctx* ctx, int32_t M, const int32_t* parent, const double* edge_length, const int32_t* level,
+                    const int32_t* first) {
+    if (!ctx) return -1;
+    if (M < 2 || !parent || !edge_length || !level || !first) return fail(ctx, "apples_set_tree: bad arguments");
+    for (int u = 0; u < M - 1; ++u)
+        if (parent[u] <= u || parent[u] >= M) return fail(ctx, "apples_set_tree: node ids must be post-order ranks");
+    if (parent[M - 1] != -1) return fail(ctx, "apples_set_tree: last node must be the root");
+    CK(cudaSetDevice(ctx->device));
+    if (ensure(ctx, ctx->t_parent, (size_t)M * 4) || ensure(ctx, ctx->t_elen, (size_t)M * 8) ||
+        ensure(ctx, ctx->t_level, (size_t)M * 4) || ensure(ctx, ctx->t_first, (size_t)M * 4))
+        return -1;
+    CK(cudaMemcpy(ctx->t_parent.p, parent, (size_t)M * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->t_elen.p, edge_length, (size_t)M * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->t_level.p, level, (size_t)M * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->t_first.p, first, (size_t)M * 4, cudaMemcpyHostToDevice));
+    ctx->M = M;
+    return 0;
+}
+
+int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, const void* packed_refs,
+                         const int32_t* ref_node, int32_t n_rep, const void* packed_reps, const int32_t* group_offsets,
+                         const int32_t* group_members) {
+    if (!ctx) return -1;
+    if ((kind != APPLES_NUC && kind != APPLES_AA) || L <= 0 || n_ref <= 0 || n_rep <= 0 || !packed_refs || !ref_node ||
+        !packed_reps || !group_offsets || !group_members)
+        return fail(ctx, "apples_set_reference: bad arguments");
+    if (kind == APPLES_NUC && L > 65535) return fail(ctx, "nucleotide alignments longer than 65535 columns are not supported");
+    for (int i = 0; i < n_rep; ++i)
+        if (group_offsets[i + 1] < group_offsets[i]) return fail(ctx, "apples_set_reference: group_offsets not monotone");
+    const int n_mem = group_offsets[n_rep];
+    for (int i = 0; i < n_mem; ++i)
+        if (group_members[i] < 0 || group_members[i] >= n_ref) return fail(ctx, "apples_set_reference: member out of range");
+    CK(cudaSetDevice(ctx->device));
+    ctx->kind = kind;
+    ctx->L = L;
+    ctx->n_ref = n_ref;
+    ctx->n_rep = n_rep;
+    ctx->W = apples_words_per_row(L);
+    ctx->Wp = round_up(ctx->W, DT_WC);
+    ctx->Lp = apples_aa_row_bytes(L);
+    ctx->rep_pad = round_up(n_rep, DT_TR);
+    ctx->ref_pad = round_up(n_ref, DT_TR);
+    ctx->refs_wm_ready = false;
+    const size_t row = query_row_bytes(ctx);
+    if (ensure(ctx, ctx->refs_rm, (size_t)n_ref * row) || ensure(ctx, ctx->reps_rm, (size_t)n_rep * row) ||
+        ensure(ctx, ctx->ref_node, (size_t)n_ref * 4) || ensure(ctx, ctx->goff, (size_t)(n_rep + 1) * 4) ||
+        ensure(ctx, ctx->gmem, (size_t)std::max(n_mem, 1) * 4))
+        return -1;
+    CK(cudaMemcpy(ctx->refs_rm.p, packed_refs, (size_t)n_ref * row, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->reps_rm.p, packed_reps, (size_t)n_rep * row, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->ref_node.p, ref_node, (size_t)n_ref * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->goff.p, group_offsets, (size_t)(n_rep + 1) * 4, cudaMemcpyHostToDevice));
+    if (n_mem) CK(cudaMemcpy(ctx->gmem.p, group_members, (size_t)n_mem * 4, cudaMemcpyHostToDevice));
+    if (kind == APPLES_NUC) {
+        const size_t wm = (size_t)3 * ctx->Wp * ctx->rep_pad * 4;
+        if (ensure(ctx, ctx->reps_wm, wm)) return -1;
+        CK(cudaMemsetAsync(ctx->reps_wm.p, 0, wm, ctx->stream));
+        launch_transpose_nuc((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_wm.p, ctx->Wp,
+                             ctx->rep_pad, ctx->stream);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int apples_set_matrix_columns(apples_ctx* ctx, int32_t n_cols, const int32_t* col_node) {
+    if (!ctx) return -1;
+    if (n_cols <= 0 || !col_node) return fail(ctx, "apples_set_matrix_columns: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (ensure(ctx, ctx->col_node, (size_t)n_cols * 4)) return -1;
+    CK(cudaMemcpy(ctx->col_node.p, col_node, (size_t)n_cols * 4, cudaMemcpyHostToDevice));
+    ctx->n_cols = n_cols;
+    return 0;
+}
+
+int apples_place_batch(apples_ctx* ctx, int64_t nq, const void* packed_queries, const int32_t* self_node,
+                       const apples_params* params, int32_t* edge, double* error, double* distal, double* pendant,
+                       int32_t* status) {
+    if (!ctx) return -1;
+    if (nq < 0 || (nq > 0 && (!packed_queries || !edge || !error || !distal || !pendant || !status)))
+        return fail(ctx, "apples_place_batch: bad arguments");
+    BatchIO io;
+    io.h_queries = packed_queries;
+    io.h_self = self_node;
+    io.edge = edge; io.error = error; io.distal = distal; io.pendant = pendant; io.status = status;
+    return run_batch(ctx, nq, io, params);
+}
+
+int apples_place_batch_matrix(apples_ctx* ctx, int64_t nq, const double* rows, const int32_t* self_node,
+                              const apples_params* params, int32_t* edge, double* error, double* distal,
+                              double* pendant, int32_t* status) {
+    if (!ctx) return -1;
+    if (nq < 0 || (nq > 0 && (!rows || !edge || !error || !distal || !pendant || !status)))
+        return fail(ctx, "apples_place_batch_matrix: bad arguments");
+    BatchIO io;
+    io.h_rows = rows;
+    io.h_self = self_node;
+    io.edge = edge; io.error = error; io.distal = distal; io.pendant = pendant; io.status = status;
+    return run_batch(ctx, nq, io, params);
+}
+
+int apples_queries_upload(apples_ctx* ctx, int64_t nq, const void* packed_queries, const int32_t* self_node) {
+    if (!ctx) return -1;
+    if (ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
+    if (nq <= 0 || !packed_queries) return fail(ctx, "apples_queries_upload: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t row = query_row_bytes(ctx);
+    if (ensure(ctx, ctx->res_q, (size_t)nq * row)) return -1;
+    CK(cudaMemcpy(ctx->res_q.p, packed_queries, (size_t)nq * row, cudaMemcpyHostToDevice));
+    ctx->res_has_self = self_node != nullptr;
+    if (self_node) {
+        if (ensure(ctx, ctx->res_self, (size_t)nq * 4)) return -1;
+        CK(cudaMemcpy(ctx->res_self.p, self_node, (size_t)nq * 4, cudaMemcpyHostToDevice));
+    }
+    if (ensure(ctx, ctx->res_edge, (size_t)nq * 4) || ensure(ctx, ctx->res_err, (size_t)nq * 8) ||
+        ensure(ctx, ctx->res_distal, (size_t)nq * 8) || ensure(ctx, ctx->res_pendant, (size_t)nq * 8) ||
+        ensure(ctx, ctx->res_status, (size_t)nq * 4))
+        return -1;
+    ctx->res_nq = nq;
+    return 0;
+}
+
+int apples_place_resident(apples_ctx* ctx, const apples_params* params) {
+    if (!ctx) return -1;
+    if (ctx->res_nq <= 0) return fail(ctx, "apples_queries_upload has not been called");
+    BatchIO io;
+    io.d_queries = ctx->res_q.p;
+    io.d_self = ctx->res_has_self ? (const int32_t*)ctx->res_self.p : nullptr;
+    io.edge = (int32_t*)ctx->res_edge.p; io.error = (double*)ctx->res_err.p; io.distal = (double*)ctx->res_distal.p;
+    io.pendant = (double*)ctx->res_pendant.p; io.status = (int32_t*)ctx->res_status.p;
+    io.out_on_device = true;
+    return run_batch(ctx, ctx->res_nq, io, params);
+}
+
+int apples_results_download(apples_ctx* ctx, int32_t* edge, double* error, double* distal, double* pendant,
+                            int32_t* status) {
+    if (!ctx) return -1;
+    if (ctx->res_nq <= 0) return fail(ctx, "no resident results");
+    const size_t n = (size_t)ctx->res_nq;
+    CK(cudaSetDevice(ctx->device));
+    if (edge) CK(cudaMemcpy(edge, ctx->res_edge.p, n * 4, cudaMemcpyDeviceToHost));
+    if (error) CK(cudaMemcpy(error, ctx->res_err.p, n * 8, cudaMemcpyDeviceToHost));
+    if (distal) CK(cudaMemcpy(distal, ctx->res_distal.p, n * 8, cudaMemcpyDeviceToHost));
+    if (pendant) CK(cudaMemcpy(pendant, ctx->res_pendant.p, n * 8, cudaMemcpyDeviceToHost));
+    if (status) CK(cudaMemcpy(status, ctx->res_status.p, n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queries, double overlap_frac, uint32_t* mism,
+                           uint32_t* valid, double* dist) {
+    if (!ctx) return -1;
+    if (ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
+    if (nq <= 0 || !packed_queries || !mism || !valid || !dist) return fail(ctx, "apples_distance_counts: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t row = query_row_bytes(ctx);
+    const size_t n_out = (size_t)nq * ctx->n_ref;
+    DevBuf dq, dm, dv, dd, qwm;
+    int rc = 0;
+    auto cleanup = [&]() { release(dq); release(dm); release(dv); release(dd); release(qwm); };
+    if (ensure(ctx, dq, (size_t)nq * row) || ensure(ctx, dm, n_out * 4) || ensure(ctx, dv, n_out * 4) ||
+        ensure(ctx, dd, n_out * 8)) { cleanup(); return -1; }
+    cudaMemcpyAsync(dq.p, packed_queries, (size_t)nq * row, cudaMemcpyHostToDevice, s);
+    cudaMemsetAsync(dm.p, 0, n_out * 4, s);
+    if (ctx->kind == APPLES_NUC) {
+        if (!ctx->refs_wm_ready) {
+            const size_t wm = (size_t)3 * ctx->Wp * ctx->ref_pad * 4;
+            if (ensure(ctx, ctx->refs_wm, wm)) { cleanup(); return -1; }
+            cudaMemsetAsync(ctx->refs_wm.p, 0, wm, s);
+            launch_transpose_nuc((const uint32_t*)ctx->refs_rm.p, ctx->n_ref, ctx->W, (uint32_t*)ctx->refs_wm.p, ctx->Wp,
+                                 ctx->ref_pad, s);
+            ctx->refs_wm_ready = true;
+        }
+        const int q_pad = round_up((int)nq, DT_TQ);
+        if (ensure(ctx, qwm, (size_t)3 * ctx->Wp * q_pad * 4)) { cleanup(); return -1; }
+        launch_transpose_nuc((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qwm.p, ctx->Wp, q_pad, s);
+        launch_dense_nuc_full((const uint32_t*)qwm.p, q_pad, (int)nq, (const uint32_t*)ctx->refs_wm.p, ctx->ref_pad,
+                              ctx->n_ref, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
+                              (double*)dd.p, ctx->num_sms, s);
+    } else {
+        launch_dense_aa((const uint8_t*)dq.p, (int)nq, (const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, ctx->L,
+                        overlap_frac, (double*)dd.p, ctx->n_ref, (uint32_t*)dv.p, s);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mism, dm.p, n_out * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(valid, dv.p, n_out * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dist, dd.p, n_out * 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(ctx, "apples_distance_counts: %s", cudaGetErrorString(e));
+    cleanup();
+    return rc;
+}
+
+int apples_observed_sets(apples_ctx* ctx, int64_t nq, const void* packed_queries, const double* rows,
+                         const int32_t* self_node, const apples_params* params, int32_t cap, int32_t* count,
+                         int32_t* node, double* dist) {
+    if (!ctx) return -1;
+    if (nq <= 0 || (!packed_queries) == (!rows) || cap <= 0 || !count || !node || !dist)
+        return fail(ctx, "apples_observed_sets: bad arguments");
+    BatchIO io;
+    io.h_queries = packed_queries;
+    io.h_rows = rows;
+    io.h_self = self_node;
+    io.obs_cap = cap;
+    io.obs_count = count;
+    io.obs_node = node;
+    io.obs_dist = dist;
+    io.stop_after_select = true;
+    return run_batch(ctx, nq, io, params);
+}
+
+int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const double* row, int32_t self_node,
+                          const apples_params* params, double* x1, double* x2, double* err, uint8_t* valid) {
+    if (!ctx) return -1;
+    if ((!packed_query) == (!row) || !x1 || !x2 || !err || !valid) return fail(ctx, "apples_edge_solutions: bad arguments");
+    BatchIO io;
+    io.h_queries = packed_query;
+    io.h_rows = row;
+    int32_t selfv = self_node;
+    io.h_self = &selfv;
+    int32_t e = 0, st = 0;
+    double er = 0, di = 0, pe = 0;
+    io.edge = &e; io.error = &er; io.distal = &di; io.pendant = &pe; io.status = &st;
+    io.dbg_x1 = x1; io.dbg_x2 = x2; io.dbg_err = err; io.dbg_valid = valid;
+    return run_batch(ctx, 1, io, params);
+}
+
+int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
+    if (!ctx || !out) return -1;
+    double v[11] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+                    ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid};
+    for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+    if (reset) {
+        for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
+        ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = 0;
+    }
+    return 0;
+}
+
+}  // extern "C"

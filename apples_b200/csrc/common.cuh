@@ -1,0 +1,160 @@
+// Shared declarations for the sm_100a kernels behind include/apples_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/apples_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile shape of the dense query x representative distance kernel (distance.cu)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DT_TQ = 64;       // queries per CTA tile
+constexpr int DT_TR = 64;       // representatives per CTA tile
+constexpr int DT_WC = 16;       // 32-site words per pipeline stage
+constexpr int DT_STAGES = 4;    // TMA pipeline depth
+constexpr int DT_CONSUMERS = 256;
+constexpr int DT_THREADS = DT_CONSUMERS + 32;  // + one producer warp
+constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
+constexpr int DT_STAGE_BYTES = DT_STAGE_WORDS * 4;
+constexpr int DT_SMEM_BYTES = DT_STAGES * DT_STAGE_BYTES + 2 * DT_STAGES * 8 + 16;
+
+// internal per-query status used between the selection and the placement kernel
+constexpr int ST_PLACE = 0;      // observed set ready, go on to placement
+constexpr int ST_ZERO = 1;       // zero-distance shortcut, zero_edge holds the leaf
+constexpr int ST_TOO_FEW = 2;    // <= 2 observed distances
+constexpr int ST_OVERFLOW = 100; // more observed leaves than the slot capacity: rerun with a larger one
+
+struct TreeDev {
+    int M;
+    const int* parent;
+    const double* elen;
+    const int* level;
+    const int* first;
+};
+
+// gates of jc69 (distance.py:735-745) in the integer domain plus the fast near/far classification
+struct NucGate {
+    int L;
+    int vmin;     // smallest valid-site count that passes `valid / L < overlap_frac` (distance.py:735)
+    double p_lo;  // mism <= p_lo * valid  =>  certainly dist <= threshold
+    double p_hi;  // mism >= p_hi * valid  =>  certainly dist >  threshold
+    double thr;
+};
+
+// jc69 from the integer counts: the fp64 operations of distance.py:737-745 in the same order
+__device__ __forceinline__ double jc69_from_counts(uint32_t m, uint32_t v, int vmin) {
+    if (v == 0u || (int)v < vmin) return -1.0;
+    if (m == 0u) return 0.0;  // p - eps < 0  <=>  p == 0 for p = m/v with v <= 65535
+    double p = (double)m / (double)v;
+    double loc = 1.0 - (4.0 * p) / 3.0;
+    if (0.0 >= loc) return -1.0;
+    return -0.75 * log(loc);
+}
+
+// scoredist from the BLOSUM45 sum and the valid count (distance.py:699-712)
+__device__ __forceinline__ double scoredist_from_sum(double tot, uint32_t v, int L, double overlap) {
+    if (v == 0u || (double)v / (double)L < overlap) return -1.0;
+    double x = 1.0 - tot / (double)v;
+    if (0.0 >= x) return -1.0;
+    double cd = -log(x);
+    return cd * 1.3;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// selection (select.cu) and placement (placement.cu) launch arguments
+// ---------------------------------------------------------------------------------------------------------------
+enum { SEL_NUC = 0, SEL_AA = 1, SEL_MATRIX = 2 };
+
+struct SelectArgs {
+    int n;                 // queries in this launch
+    const int* qlist;      // optional: slot -> query index inside the sub-batch (NULL = identity)
+    int n_units;           // representatives (alignment) or matrix columns
+    int64_t ldk;           // row stride of the key matrix
+    const uint32_t* keys_nuc;  // [nq][ldk] packed (mismatch | valid << 16)
+    const double* keys_f64;    // [nq][ldk] distances (protein representatives / matrix rows)
+    const int* goff;       // cluster CSR
+    const int* gmem;
+    const int* ref_node;
+    const uint32_t* refs_nuc;  // row-major [n_ref][3][W]
+    const uint32_t* q_nuc;     // row-major [nq][3][W]
+    int W;
+    const uint8_t* refs_aa;    // [n_ref][Lp]
+    const uint8_t* q_aa;       // [nq][Lp]
+    int Lp;
+    int L;
+    const int* col_node;
+    const int* self_node;  // [nq] or NULL
+    double thr;
+    int baseobs;
+    double overlap;
+    NucGate gate;
+    int cap;               // slot capacity (power of two)
+    int* obs_node;         // [slots][cap]
+    double* obs_dist;      // [slots][cap]
+    int* K;                // [nq] observed leaves (may exceed cap)
+    int* V;                // [nq] valid nodes of the restricted subtree
+    int* status;           // [nq] ST_*
+    int* zero_edge;        // [nq]
+    unsigned long long* pair_counter;  // number of member distances evaluated (statistics)
+    TreeDev tree;
+};
+
+struct alignas(16) NodeRec {
+    double S[6];
+    double R[6];
+    double len;
+    int orig;
+    int fchild;
+    int rsib;
+    int nchild;
+    double pad_;
+};
+static_assert(sizeof(NodeRec) == 128, "NodeRec must be 128 bytes");
+
+struct StackEnt {
+    int A;
+    int first;
+    int last;
+    int n;
+};
+
+struct PlaceArgs {
+    int n;                 // entries in this launch
+    const int* qlist;      // slot -> query index (NULL = identity) for obs buffers
+    int q_begin;           // first query index of the launch when qlist == NULL
+    int cap;
+    const int* obs_node;
+    const double* obs_dist;
+    const int* K;
+    const int* status;
+    const int* zero_edge;
+    const long long* rec_off;    // per launch entry: first NodeRec of the query's scratch
+    const long long* stack_off;  // per launch entry: first StackEnt
+    NodeRec* recs;
+    StackEnt* stacks;
+    int criterion;
+    int negative_branch;
+    TreeDev tree;
+    int* out_edge;
+    double* out_error;
+    double* out_distal;
+    double* out_pendant;
+    int* out_status;
+    // optional per-edge export for one query (index inside the sub-batch), arrays of M
+    int dbg_query;
+    double* dbg_x1;
+    double* dbg_x2;
+    double* dbg_err;
+    unsigned char* dbg_valid;
+};
+
+// kernels / launchers implemented in the .cu files
+void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int Wp, int rows_pad, cudaStream_t s);
+void launch_dense_nuc_keys(const uint32_t* q_wm, int q_pad, const uint32_t* r_wm, int r_pad, int Wp, uint32_t* keys,
+                           int64_t ldk, int num_sms, cudaStream_t s);
+void launch_dense_nuc_full(const uint32_t* q_wm, int q_pad, int nq, const uint32_t* r_wm, int r_pad, int n_ref, int Wp,
+                           int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms, cudaStream_t s);
+void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
+                     int64_t ldd, uint32_t* valid_out, cudaStream_t s);
+void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
+void launch_place(int method, const PlaceArgs& a, cudaStream_t s);
+cudaError_t dense_nuc_configure();

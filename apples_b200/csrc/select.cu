@@ -1,0 +1,374 @@
+// Kernel (c): APPLES-2 query-specific observed-set selection, one warp per query.
+//
+// Alignment mode replaces ReducedReference.get_obs_dist (apples/Reference.py:117-157): the reference pops
+// representatives in ascending (distance, index) order and expands a cluster while
+// `dist <= threshold or obs_num < baseobs`.  Because pops are ascending and obs_num only grows, that is
+//   taken = { clusters with dist <= threshold }  U  { the next clusters in (dist, index) order while obs_num < baseobs }
+// (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters as it meets them, keeps
+// the 32 smallest far clusters in a register-resident sorted list (one entry per lane) and afterwards walks that
+// list in order until obs_num reaches baseobs (re-scanning for the next 32 in the rare case the list runs out).
+// Nucleotide keys are the exact integer pairs (mismatch, valid) from the dense kernel: ordering by the rational
+// mismatch/valid is ordering by jc69 distance (equal rationals give the identical double), so no fp64 is needed
+// for the ~R representatives per query; the corrected fp64 distance is evaluated only for the selected members.
+//
+// Distance-matrix mode replaces valid_dists (apples/PoolQueryWorker.py:44-59): stable ascending order by
+// (value, column), keep while `tx <= baseobs or v <= threshold` -- the same rule with one member per unit.
+//
+// Then, as PoolQueryWorker.runquery:63-98 does: drop the query's own backbone entry, take the zero-distance
+// shortcut (first zero in the reference's dict order), flag `<= 2` observed distances; otherwise sort the observed
+// leaves by node id (= left-to-right order in the DFS layout) and count the valid nodes of the restricted subtree
+// (Subtree.py:23-43) so the host can size the placement scratch.
+#include "common.cuh"
+
+#define FULLMASK 0xffffffffu
+
+template <int KIND>
+struct Key;
+
+template <>
+struct Key<SEL_NUC> {
+    uint32_t m, v;
+    int idx;
+};
+template <>
+struct Key<SEL_AA> {
+    double d;
+    int idx;
+};
+template <>
+struct Key<SEL_MATRIX> {
+    double d;
+    int idx;
+};
+
+__device__ __forceinline__ bool key_less(const Key<SEL_NUC>& a, const Key<SEL_NUC>& b) {
+    const uint32_t x = a.m * b.v, y = b.m * a.v;  // counts <= 65535: products fit 32 bits
+    return x < y || (x == y && a.idx < b.idx);
+}
+__device__ __forceinline__ bool key_less(const Key<SEL_AA>& a, const Key<SEL_AA>& b) {
+    return a.d < b.d || (a.d == b.d && a.idx < b.idx);
+}
+__device__ __forceinline__ bool key_less(const Key<SEL_MATRIX>& a, const Key<SEL_MATRIX>& b) {
+    return a.d < b.d || (a.d == b.d && a.idx < b.idx);
+}
+
+__device__ __forceinline__ Key<SEL_NUC> key_shfl(const Key<SEL_NUC>& k, int src) {
+    Key<SEL_NUC> o;
+    o.m = __shfl_sync(FULLMASK, k.m, src);
+    o.v = __shfl_sync(FULLMASK, k.v, src);
+    o.idx = __shfl_sync(FULLMASK, k.idx, src);
+    return o;
+}
+template <int KIND>
+__device__ __forceinline__ Key<KIND> key_shfl(const Key<KIND>& k, int src) {
+    Key<KIND> o;
+    o.d = __shfl_sync(FULLMASK, k.d, src);
+    o.idx = __shfl_sync(FULLMASK, k.idx, src);
+    return o;
+}
+__device__ __forceinline__ Key<SEL_NUC> key_shfl_up(const Key<SEL_NUC>& k) {
+    Key<SEL_NUC> o;
+    o.m = __shfl_up_sync(FULLMASK, k.m, 1);
+    o.v = __shfl_up_sync(FULLMASK, k.v, 1);
+    o.idx = __shfl_up_sync(FULLMASK, k.idx, 1);
+    return o;
+}
+template <int KIND>
+__device__ __forceinline__ Key<KIND> key_shfl_up(const Key<KIND>& k) {
+    Key<KIND> o;
+    o.d = __shfl_up_sync(FULLMASK, k.d, 1);
+    o.idx = __shfl_up_sync(FULLMASK, k.idx, 1);
+    return o;
+}
+
+// load + classify one unit.  returns 0 = invalid, 1 = near (dist <= threshold), 2 = far
+__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_NUC>& k) {
+    const uint32_t packed = a.keys_nuc[(size_t)q * a.ldk + u];
+    k.m = packed & 0xffffu;
+    k.v = packed >> 16;
+    k.idx = u;
+    // distance.py:735 (no overlap), :741-743 (1 - 4p/3 <= 0  <=>  4 m >= 3 v)
+    if (k.v == 0u || (int)k.v < a.gate.vmin || 4u * k.m >= 3u * k.v) return 0;
+    const double dm = (double)k.m, dv = (double)k.v;
+    if (dm <= a.gate.p_lo * dv) return 1;
+    if (dm >= a.gate.p_hi * dv) return 2;
+    return jc69_from_counts(k.m, k.v, a.gate.vmin) <= a.thr ? 1 : 2;
+}
+__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_AA>& k) {
+    k.d = a.keys_f64[(size_t)q * a.ldk + u];
+    k.idx = u;
+    if (!(k.d >= 0.0)) return 0;  // Reference.py:141
+    return k.d <= a.thr ? 1 : 2;
+}
+__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_MATRIX>& k) {
+    k.d = a.keys_f64[(size_t)q * a.ldk + u];
+    k.idx = u;
+    if (!(k.d >= 0.0) || a.col_node[u] < 0) return 0;  // PoolQueryWorker.py:52
+    return k.d <= a.thr ? 1 : 2;
+}
+
+// ---- member distances (warp-cooperative) ----------------------------------------------------------------------
+__device__ __forceinline__ double member_dist_nuc(const SelectArgs& a, const uint32_t* qrow, int ref_row, int lane) {
+    const uint32_t* r = a.refs_nuc + (size_t)ref_row * 3 * a.W;
+    uint32_t acc = 0;
+    for (int w = 4 * lane; w < a.W; w += 128) {
+        const uint4 ql = *reinterpret_cast<const uint4*>(qrow + w);
+        const uint4 qh = *reinterpret_cast<const uint4*>(qrow + a.W + w);
+        const uint4 qv = *reinterpret_cast<const uint4*>(qrow + 2 * a.W + w);
+        const uint4 rl = *reinterpret_cast<const uint4*>(r + w);
+        const uint4 rh = *reinterpret_cast<const uint4*>(r + a.W + w);
+        const uint4 rv = *reinterpret_cast<const uint4*>(r + 2 * a.W + w);
+        uint32_t v, m;
+        v = qv.x & rv.x; m = ((ql.x ^ rl.x) | (qh.x ^ rh.x)) & v; acc += __popc(m) + (__popc(v) << 16);
+        v = qv.y & rv.y; m = ((ql.y ^ rl.y) | (qh.y ^ rh.y)) & v; acc += __popc(m) + (__popc(v) << 16);
+        v = qv.z & rv.z; m = ((ql.z ^ rl.z) | (qh.z ^ rh.z)) & v; acc += __popc(m) + (__popc(v) << 16);
+        v = qv.w & rv.w; m = ((ql.w ^ rl.w) | (qh.w ^ rh.w)) & v; acc += __popc(m) + (__popc(v) << 16);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+    return jc69_from_counts(acc & 0xffffu, acc >> 16, a.gate.vmin);
+}
+
+__constant__ double c_blosum45_sel[441] = {
+#include "blosum45.inc"
+};
+
+__device__ __forceinline__ double member_dist_aa(const SelectArgs& a, const uint8_t* qrow, int ref_row, int lane) {
+    const uint8_t* r = a.refs_aa + (size_t)ref_row * a.Lp;
+    double sum = 0.0;
+    uint32_t val = 0;
+    for (int x = 4 * lane; x < a.Lp; x += 128) {
+        const uint32_t qw = *reinterpret_cast<const uint32_t*>(qrow + x);
+        const uint32_t rw = *reinterpret_cast<const uint32_t*>(r + x);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t qc = (qw >> (8 * b)) & 0xffu, rc = (rw >> (8 * b)) & 0xffu;
+            sum += c_blosum45_sel[qc * 21 + rc];
+            val += (qc < 20u && rc < 20u) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(FULLMASK, sum, o);
+        val += __shfl_xor_sync(FULLMASK, val, o);
+    }
+    // every lane must hold the identical double: take lane 0's (the xor-butterfly sums are order-dependent per lane)
+    sum = __shfl_sync(FULLMASK, sum, 0);
+    return scoredist_from_sum(sum, val, a.L, a.overlap);
+}
+
+// ---- per-warp selection state ------------------------------------------------------------------------------------
+template <int KIND>
+struct WarpSel {
+    int obs_num;    // valid member distances so far, own entry included (Reference.py:150-152 / PoolQueryWorker.py:54)
+    int kcount;     // entries of the observed dict after removal of the query's own entry
+    bool has_zero;  // a zero distance has been seen
+    Key<KIND> zkey; // unit key of the best zero so far (dict order = unit order, then position in the group)
+    int zpos;
+    int znode;
+};
+
+template <int KIND>
+__device__ __forceinline__ void observe(const SelectArgs& a, WarpSel<KIND>& st, int slot, int self, int node, double d,
+                                        const Key<KIND>& ukey, int pos, int lane) {
+    // called by all lanes with identical arguments
+    st.obs_num++;
+    if (node < 0 || node == self) return;  // own backbone entry is deleted afterwards (PoolQueryWorker.py:63-66)
+    if (d == 0.0) {                          // PoolQueryWorker.py:72-75: first zero in dict order wins
+        bool better = !st.has_zero || key_less(ukey, st.zkey) || (!key_less(st.zkey, ukey) && pos < st.zpos);
+        if (better) {
+            st.has_zero = true;
+            st.zkey = ukey;
+            st.zpos = pos;
+            st.znode = node;
+        }
+    }
+    if (st.kcount < a.cap && lane == 0) {
+        a.obs_node[(size_t)slot * a.cap + st.kcount] = node;
+        a.obs_dist[(size_t)slot * a.cap + st.kcount] = d;
+    }
+    st.kcount++;
+}
+
+template <int KIND>
+__device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& st, int slot, int q, int self,
+                                            const Key<KIND>& ukey, int lane) {
+    if constexpr (KIND == SEL_MATRIX) {
+        observe<KIND>(a, st, slot, self, a.col_node[ukey.idx], ukey.d, ukey, 0, lane);
+    } else {
+        const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
+        for (int x = b; x < e; ++x) {
+            const int row = a.gmem[x];
+            double d;
+            if constexpr (KIND == SEL_NUC)
+                d = member_dist_nuc(a, a.q_nuc + (size_t)q * 3 * a.W, row, lane);
+            else
+                d = member_dist_aa(a, a.q_aa + (size_t)q * a.Lp, row, lane);
+            if (!(d < 0.0)) observe<KIND>(a, st, slot, self, a.ref_node[row], d, ukey, x - b, lane);  // Reference.py:150
+        }
+        if (lane == 0 && a.pair_counter) atomicAdd(a.pair_counter, (unsigned long long)(e - b));
+    }
+}
+
+// warp bitonic sort of the slot's (node, dist) entries by node id; n2 = power of two >= kcount, padding pre-filled
+__device__ void sort_slot(int* node, double* dist, int n2, int lane) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < n2; i += 32) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int ni = node[i], nl = node[l];
+                    const bool up = (i & k) == 0;
+                    if ((ni > nl) == up) {
+                        node[i] = nl;
+                        node[l] = ni;
+                        const double t = dist[i];
+                        dist[i] = dist[l];
+                        dist[l] = t;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= a.n) return;
+    const int q = a.qlist ? a.qlist[slot] : slot;
+    const int self = a.self_node ? a.self_node[q] : -1;
+
+    WarpSel<KIND> st;
+    st.obs_num = 0;
+    st.kcount = 0;
+    st.has_zero = false;
+    st.zpos = 0;
+    st.znode = -1;
+    st.zkey.idx = 0;
+
+    // sorted list of the smallest far units seen so far: lane j holds the j-th smallest, `cnt` entries are live
+    Key<KIND> mine;
+    mine.idx = -1;
+    Key<KIND> last;      // everything <= last has already been handled by an earlier round
+    bool have_last = false;
+    bool first_round = true;
+    bool done = false;
+
+    while (!done) {
+        int cnt = 0;
+        for (int u0 = 0; u0 < a.n_units; u0 += 32) {
+            const int u = u0 + lane;
+            Key<KIND> k;
+            int cls = 0;
+            if (u < a.n_units) cls = load_key(a, q, u, k);
+            if (first_round) {
+                unsigned near = __ballot_sync(FULLMASK, cls == 1);
+                while (near) {
+                    const int src = __ffs(near) - 1;
+                    near &= near - 1;
+                    const Key<KIND> uk = key_shfl(k, src);
+                    expand_unit<KIND>(a, st, slot, q, self, uk, lane);
+                }
+            }
+            bool cand = cls == 2;
+            if (cand && have_last) cand = key_less(last, k);
+            if (cnt == 32) {  // quick reject against the current 32nd smallest (held by lane 31)
+                const Key<KIND> k31 = key_shfl(mine, 31);
+                if (cand) cand = key_less(k, k31);
+            }
+            unsigned far = __ballot_sync(FULLMASK, cand);
+            while (far) {
+                const int src = __ffs(far) - 1;
+                far &= far - 1;
+                const Key<KIND> ck = key_shfl(k, src);
+                // position = number of live entries smaller than the candidate
+                const bool smaller = lane < cnt && key_less(mine, ck);
+                const int pos = __popc(__ballot_sync(FULLMASK, smaller));
+                if (pos >= 32) continue;
+                const Key<KIND> up = key_shfl_up(mine);
+                if (lane > pos) mine = up;
+                if (lane == pos) mine = ck;
+                if (cnt < 32) cnt++;
+            }
+        }
+        first_round = false;
+        // walk the far list in ascending order while obs_num < baseobs (Reference.py:146)
+        int j = 0;
+        for (; j < cnt; ++j) {
+            if (st.obs_num >= a.baseobs) break;
+            const Key<KIND> uk = key_shfl(mine, j);
+            expand_unit<KIND>(a, st, slot, q, self, uk, lane);
+        }
+        if (st.obs_num >= a.baseobs || cnt < 32) {
+            done = true;
+        } else {
+            last = key_shfl(mine, 31);
+            have_last = true;
+        }
+    }
+
+    // ---- PoolQueryWorker.runquery:72-98 ----
+    int status = ST_PLACE;
+    int V = 0;
+    if (st.has_zero) {
+        status = ST_ZERO;
+    } else if (st.kcount <= 2) {
+        status = ST_TOO_FEW;
+    } else if (st.kcount > a.cap) {
+        status = ST_OVERFLOW;
+    } else {
+        int* node = a.obs_node + (size_t)slot * a.cap;
+        double* dist = a.obs_dist + (size_t)slot * a.cap;
+        const int K = st.kcount;
+        int n2 = 1;
+        while (n2 < K) n2 <<= 1;
+        __syncwarp();
+        for (int i = K + lane; i < n2; i += 32) {
+            node[i] = 0x7fffffff;
+            dist[i] = 0.0;
+        }
+        __syncwarp();
+        sort_slot(node, dist, n2, lane);
+        // valid nodes = union of leaf -> MRCA paths, MRCA excluded (Subtree.py:23-43).  With leaves sorted by id the
+        // chain owned by leaf i runs up to (excluding) the first ancestor that also contains leaf i+1; the last
+        // leaf's chain stops below the first ancestor that contains leaf 0 (the MRCA).
+        const int leaf0 = node[0];
+        int c = 0;
+        for (int i = lane; i < K; i += 32) {
+            int u = node[i];
+            const int nxt = (i + 1 < K) ? node[i + 1] : -1;
+            c++;
+            while (true) {
+                const int p = a.tree.parent[u];
+                const bool top = (i + 1 < K) ? (p >= nxt) : (a.tree.first[p] <= leaf0);
+                if (top) break;
+                c++;
+                u = p;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
+        V = c;
+    }
+    if (lane == 0) {
+        a.K[q] = st.kcount;
+        a.V[q] = V;
+        a.status[q] = status;
+        a.zero_edge[q] = st.znode;
+    }
+}
+
+void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
+    const int warps = 4;
+    dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
+    if (a.n <= 0) return;
+    if (kind == SEL_NUC)
+        select_kernel<SEL_NUC><<<grid, block, 0, s>>>(a);
+    else if (kind == SEL_AA)
+        select_kernel<SEL_AA><<<grid, block, 0, s>>>(a);
+    else
+        select_kernel<SEL_MATRIX><<<grid, block, 0, s>>>(a);
+}

@@ -1,0 +1,268 @@
+"""Host side of the hot path: `place_batch` replaces the one call that fans queries out to CPU workers,
+
+    results = pool.starmap(queryworker.runquery, queries)            run_apples.py:94-102
+
+and returns the same list of per-query jplace dicts (PoolQueryWorker.runquery, apples/PoolQueryWorker.py:28-141),
+in the same order, with the same warnings / stderr messages.  All per-query work (distances, observed-set
+selection, restricted subtree, least-squares moments, per-edge solve, criterion selection) runs in CUDA behind
+the C ABI of include/apples_b200.h.  There is no CPU path here.
+"""
+import logging
+import sys
+
+import numpy as np
+
+from . import _lib
+from . import fasta as _fasta
+
+
+def _edge_index_of(v):
+    return int(v.edge_index) if hasattr(v, 'edge_index') else int(v)
+
+
+class GpuPlacer:
+    """One GPU context holding the replicated read-only state (tree, packed reference, clusters) -- the analogue of
+    PoolQueryWorker's fork-inherited class attributes (PoolQueryWorker.py:11-25)."""
+
+    def __init__(self, tree, reference=None, name_to_node_map=None, device=0, matrix_tags=None):
+        self.lib = _lib.load()
+        self.tree = tree
+        self.name_to_node = {k: _edge_index_of(v) for k, v in
+                             (name_to_node_map if name_to_node_map is not None else tree.name_to_node).items()}
+        h = _lib.C.c_void_p()
+        rc = self.lib.apples_ctx_create(int(device), _lib.C.byref(h))
+        if rc != 0:
+            raise RuntimeError('apples_ctx_create(device=%d) failed with code %d (no usable CUDA device?)' % (device, rc))
+        self.h = h
+        self.device = int(device)
+        self._check(self.lib.apples_set_tree(self.h, tree.num_nodes, _lib.ptr(tree.parent), _lib.ptr(tree.edge_length),
+                                             _lib.ptr(tree.level), _lib.ptr(tree.first)))
+        self.reference = None
+        self.kind = None
+        self.L = None
+        self.ref_names = None
+        self.matrix_tags = None
+        if reference is not None:
+            self.set_reference(reference)
+        if matrix_tags is not None:
+            self.set_matrix_tags(matrix_tags)
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError('libapples_b200: ' + self.lib.apples_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, 'h', None) is not None and self.h:
+            self.lib.apples_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_limits(self, max_subbatch=0, scratch_bytes=0, slot_cap=0):
+        self._check(self.lib.apples_ctx_set_limits(self.h, int(max_subbatch), int(scratch_bytes), int(slot_cap)))
+
+    @property
+    def stream(self):
+        return self.lib.apples_ctx_stream(self.h)
+
+    def set_reference(self, reference):
+        d = reference.device_arrays(self.name_to_node)
+        self.set_reference_arrays(**d)
+        self.reference = reference
+
+    def set_reference_arrays(self, kind, L, ref_names, packed_refs, ref_node, packed_reps, group_offsets, group_members):
+        self.kind, self.L, self.ref_names = kind, int(L), ref_names
+        self._keep = (np.ascontiguousarray(packed_refs), np.ascontiguousarray(ref_node, dtype=np.int32),
+                      np.ascontiguousarray(packed_reps), np.ascontiguousarray(group_offsets, dtype=np.int32),
+                      np.ascontiguousarray(group_members, dtype=np.int32))
+        pr, rn, pp, go, gm = self._keep
+        self._check(self.lib.apples_set_reference(self.h, kind, int(L), pr.shape[0], _lib.ptr(pr), _lib.ptr(rn),
+                                                  pp.shape[0], _lib.ptr(pp), _lib.ptr(go), _lib.ptr(gm)))
+        self._keep = None
+
+    def set_matrix_tags(self, tags):
+        self.matrix_tags = list(tags)
+        col = np.array([self.name_to_node.get(t, -1) for t in self.matrix_tags], dtype=np.int32)
+        self._check(self.lib.apples_set_matrix_columns(self.h, len(col), _lib.ptr(col)))
+
+    def pack_queries(self, seqs):
+        """'S1' rows (or a uint8 [n, L] matrix) -> packed device-layout rows."""
+        mat = _fasta.as_byte_matrix(seqs, self.L)
+        if mat.shape[1] != self.L:
+            raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], self.L))
+        return _fasta.pack(mat, self.kind)
+
+    def self_nodes(self, names):
+        return np.array([self.name_to_node.get(n, -1) for n in names], dtype=np.int32)
+
+    @staticmethod
+    def params_from_options(options):
+        return _lib.make_params(options.method_name, options.criterion_name, bool(options.negative_branch),
+                                options.base_observation_threshold, options.filt_threshold,
+                                getattr(options, 'minimum_alignment_overlap', 0.001))
+
+    # ------------------------------------------------------------------------------------------------ hot path
+    def _outputs(self, nq):
+        return (np.empty(nq, np.int32), np.empty(nq, np.float64), np.empty(nq, np.float64), np.empty(nq, np.float64),
+                np.empty(nq, np.int32))
+
+    def place_packed(self, packed, self_node, params):
+        """packed queries (host) -> (edge, error, distal, pendant, status) arrays."""
+        nq = int(packed.shape[0])
+        out = self._outputs(nq)
+        packed = np.ascontiguousarray(packed)
+        self._check(self.lib.apples_place_batch(self.h, nq, _lib.ptr(packed), _lib.ptr(self_node), _lib.C.byref(params),
+                                                *[_lib.ptr(o) for o in out]))
+        return out
+
+    def place_rows(self, rows, self_node, params):
+        """distance-matrix rows float64 [nq, n_cols] -> result arrays."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        nq = int(rows.shape[0])
+        out = self._outputs(nq)
+        self._check(self.lib.apples_place_batch_matrix(self.h, nq, _lib.ptr(rows), _lib.ptr(self_node),
+                                                       _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
+        return out
+
+    def upload_queries(self, packed, self_node=None):
+        packed = np.ascontiguousarray(packed) if isinstance(packed, np.ndarray) else packed
+        self._res_n = int(packed.shape[0])
+        self._check(self.lib.apples_queries_upload(self.h, self._res_n, _lib.ptr(packed), _lib.ptr(self_node)))
+
+    def place_resident(self, params):
+        self._check(self.lib.apples_place_resident(self.h, _lib.C.byref(params)))
+
+    def download_results(self):
+        out = self._outputs(self._res_n)
+        self._check(self.lib.apples_results_download(self.h, *[_lib.ptr(o) for o in out]))
+        return out
+
+    def timings(self, reset=False):
+        v = np.zeros(11, np.float64)
+        self.lib.apples_get_timings(self.h, _lib.ptr(v), 11, 1 if reset else 0)
+        keys = ['h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms', 'launches',
+                'rep_distance_launches', 'pairs', 'observed', 'valid_nodes']
+        return dict(zip(keys, v.tolist()))
+
+    # ------------------------------------------------------------------------------------------------ parity exports
+    def distance_counts(self, packed, overlap_frac=0.001):
+        packed = np.ascontiguousarray(packed)
+        nq, nr = int(packed.shape[0]), len(self.ref_names)
+        mism = np.zeros((nq, nr), np.uint32)
+        valid = np.zeros((nq, nr), np.uint32)
+        dist = np.zeros((nq, nr), np.float64)
+        self._check(self.lib.apples_distance_counts(self.h, nq, _lib.ptr(packed), float(overlap_frac), _lib.ptr(mism),
+                                                    _lib.ptr(valid), _lib.ptr(dist)))
+        return mism, valid, dist
+
+    def observed_sets(self, params, packed=None, rows=None, self_node=None, cap=4096):
+        src = packed if packed is not None else rows
+        src = np.ascontiguousarray(src)
+        nq = int(src.shape[0])
+        count = np.zeros(nq, np.int32)
+        node = np.full((nq, cap), -1, np.int32)
+        dist = np.zeros((nq, cap), np.float64)
+        self._check(self.lib.apples_observed_sets(self.h, nq, _lib.ptr(src) if packed is not None else None,
+                                                  _lib.ptr(src) if packed is None else None, _lib.ptr(self_node),
+                                                  _lib.C.byref(params), cap, _lib.ptr(count), _lib.ptr(node),
+                                                  _lib.ptr(dist)))
+        return count, node, dist
+
+    def edge_solutions(self, params, packed_row=None, row=None, self_node=-1):
+        M = self.tree.num_nodes
+        x1, x2, err = np.zeros(M), np.zeros(M), np.zeros(M)
+        valid = np.zeros(M, np.uint8)
+        src = np.ascontiguousarray(packed_row if packed_row is not None else row)
+        self._check(self.lib.apples_edge_solutions(self.h, _lib.ptr(src) if packed_row is not None else None,
+                                                   _lib.ptr(src) if packed_row is None else None, int(self_node),
+                                                   _lib.C.byref(params), _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(err),
+                                                   _lib.ptr(valid)))
+        return x1, x2, err, valid
+
+
+def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True):
+    """Device result arrays -> the per-query dicts PoolQueryWorker.runquery returns, with its messages."""
+    edge, error, distal, pendant, status = [o.tolist() for o in out]
+    results = []
+    for i, name in enumerate(names):
+        if in_backbone[i]:  # PoolQueryWorker.py:63-70
+            if log:
+                logging.warning('The query named %s exists in the backbone. Changing its name to %s-query.' % (name, name))
+            name = name + '-query'
+        code = status[i] & _lib.STATUS_CODE_MASK
+        if code == _lib.ZERO_DIST_LEAF:  # :72-75
+            p = [edge[i], 0, 1, 0, 0]
+        elif code == _lib.TOO_FEW_DISTANCES:  # :77-98
+            if log:
+                sys.stderr.write('Taxon {} cannot be placed. At least three non-infinity distances '
+                                 'should be observed to place a taxon. '
+                                 'Consequently, this taxon is ignored (no output).\n'.format(name))
+            p = [-1, 0, 1, 0, 0]
+        else:
+            pend = 0 if (status[i] & _lib.FLAG_PENDANT_INT0) else pendant[i]
+            p = [edge[i], error[i], 1, distal[i], pend]
+            if code == _lib.PLACED_MISPLACEMENT_FLAG:  # :121-130
+                ignored = ''
+                if exclude_intplace:
+                    p[0] = -1
+                    ignored = ' Consequently, this sequence is ignored (no output).'
+                if log:
+                    logging.warning('Best placement for query sequence %s has zero pendant edge length and placed at '
+                                    'an internal node with a non-zero least squares error. This is a potential '
+                                    'misplacement.%s' % (name, ignored))
+        results.append({'placements': [{'p': [p], 'n': [name]}]})
+    return results
+
+
+def place_batch(reference, options, name_to_node_map, queries, tree=None, placer=None, device=0):
+    """Drop-in for `pool.starmap(queryworker.runquery, queries)` (run_apples.py:94-102).
+
+    queries yields (query_name, query_seq 'S1' row or None, obs_dist dict or None) exactly as run_apples.py builds
+    them (:43-54 distance matrix, :85-89 alignment).  Returns the list of jplace dicts in input order.
+    `tree` is the BackboneTree the name_to_node_map belongs to (or pass an existing GpuPlacer).
+    """
+    queries = list(queries)
+    if not queries:
+        return []
+    own = placer is None
+    if placer is None:
+        if tree is None:
+            raise ValueError('place_batch needs the BackboneTree (tree=) or a GpuPlacer (placer=)')
+        placer = GpuPlacer(tree, reference, name_to_node_map, device=device)
+    try:
+        params = placer.params_from_options(options)
+        names = [q[0] for q in queries]
+        in_backbone = [n in placer.name_to_node for n in names]
+        self_node = placer.self_nodes(names)
+        if queries[0][2]:
+            # distance-matrix mode: every row is a {tag: float} dict in header order
+            tags = list(queries[0][2].keys())
+            seen = set(tags)
+            for q in queries[1:]:
+                for t in q[2].keys():
+                    if t not in seen:
+                        seen.add(t)
+                        tags.append(t)
+            if placer.matrix_tags != tags:
+                placer.set_matrix_tags(tags)
+            rows = np.full((len(queries), len(tags)), -1.0, dtype=np.float64)
+            col = {t: j for j, t in enumerate(tags)}
+            for i, q in enumerate(queries):
+                if len(q[2]) == len(tags):
+                    rows[i] = np.fromiter(q[2].values(), dtype=np.float64, count=len(tags))
+                else:
+                    for t, v in q[2].items():
+                        rows[i, col[t]] = v
+            out = placer.place_rows(rows, self_node, params)
+        else:
+            packed = placer.pack_queries([q[1] for q in queries])
+            out = placer.place_packed(packed, self_node, params)
+        return results_to_jplace(names, in_backbone, out, getattr(options, 'exclude_intplace', False))
+    finally:
+        if own:
+            placer.close()

@@ -209,6 +209,11 @@ def copy_data():
             shutil.copyfileobj(fi, fo)
 
 
+def save_gz(src_path, name):
+    with open(src_path, 'rb') as fi, gzip.GzipFile(os.path.join(DATA, name + '.gz'), 'wb', mtime=0) as fo:
+        shutil.copyfileobj(fi, fo)
+
+
 def cluster_tsv_for(tree_fp, threshold, out_path):
     bt = BackboneTree.from_newick(tree_fp)
     cl = treecluster.max_diameter_clusters(bt, threshold * 1.2)
@@ -287,6 +292,10 @@ def main():
     stsv = os.path.join(tmp, 'syn300.tsv')
     cluster_tsv_for(tfp, 0.2, stsv)
     sql = [(k, v, None) for k, v in sq.items()]
+    synth.write_fasta(srefs, os.path.join(tmp, 'syn300_ref.fa'))
+    synth.write_fasta(sq, os.path.join(tmp, 'syn300_query.fa'))
+    for fn in ['syn300.nwk', 'syn300.tsv', 'syn300_ref.fa', 'syn300_query.fa']:
+        save_gz(os.path.join(tmp, fn), fn)
     gen = {'generator': {'tree': dict(n_leaves=300, seed=11, polytomy_frac=0.15, zero_frac=0.05, neg_frac=0.03),
                          'L': 600, 'aln_seed': 12, 'n_queries': 40, 'q_seed': 13, 'cluster_threshold': 0.2}}
     for m in ['FM', 'OLS', 'BME', 'BE']:
@@ -306,6 +315,10 @@ def main():
     pgen = {'generator': {'L': 400, 'aln_seed': 21, 'n_queries': 12, 'q_seed': 22, 'cluster_threshold': 0.6}}
     prr = reference_reduced(prefs, True, ptsv, 0.6, 25)
     pql = [(k, v, None) for k, v in pq.items()]
+    synth.write_fasta(prefs, os.path.join(tmp, 'prot_ref.fa'))
+    synth.write_fasta(pq, os.path.join(tmp, 'prot_query.fa'))
+    for fn in ['prot.tsv', 'prot_ref.fa', 'prot_query.fa']:
+        save_gz(os.path.join(tmp, fn), fn)
     # scoredist values for query 0 against the first 64 references (1e-9 parity target, BLAS summation order)
     pn = list(prefs.keys())[:64]
     sd = [hx(ref_distance.scoredist(pql[0][1], prefs[n], 0.001)) for n in pn]

@@ -1,0 +1,284 @@
+"""GPU (-m gpu): the CUDA hot path, called through the C ABI, against the golden vectors of the unmodified
+reference and against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): mismatch / overlap counts bit-exact; distances, branch lengths and LS scores
+within 1e-9 relative in fp64 (scores with a tiny absolute floor because exact fits score ~1e-16 in the reference);
+placement edges identical.  With identical input distances (distance-matrix mode) x_1, x_2, distal and pendant are
+required to be BIT-IDENTICAL; the score may differ in the last bits only because the reference squares with
+pow(x, 2) (DESIGN.md "parity").
+"""
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+ERR_FLOOR = 1e-12
+
+ALL_CASES = util.golden_names()
+
+
+def _placer(ci, tree, ref):
+    from apples_b200.placer import GpuPlacer
+    return GpuPlacer(tree, ref, tree.name_to_node, device=0)
+
+
+def _check_p(case, qname, got, exp, exact_lengths, octx=None, query=None):
+    assert [isinstance(x, int) for x in got] == [isinstance(x, int) for x in exp], (case, qname, got, exp)
+    if got[0] != exp[0]:
+        # documented exception: exact-score ties (BASELINE.json north_star).  Accept only if the oracle scores the two
+        # edges within tolerance of each other.
+        assert octx is not None and query is not None, (case, qname, got, exp)
+        det = {}
+        octx.runquery(*query, detail=det)
+        ea, eb = det['edges'][got[0]][2], det['edges'][exp[0]][2]
+        assert util.close(ea, eb, REL, ERR_FLOOR), ('edge differs and is not a score tie', case, qname, got, exp)
+        return 'tie'
+    assert util.close(got[1], exp[1], REL, ERR_FLOOR), (case, qname, got, exp)
+    if exact_lengths:
+        assert got[3] == exp[3] and got[4] == exp[4], (case, qname, got, exp)
+    else:
+        assert util.close(got[3], exp[3], REL, 1e-15) and util.close(got[4], exp[4], REL, 1e-15), (case, qname, got, exp)
+    return 'ok'
+
+
+@pytest.mark.parametrize('case', ALL_CASES)
+def test_golden_placements(case, workdir):
+    """place_batch (the drop-in for pool.starmap(runquery)) reproduces the reference's per-query results."""
+    from apples_b200.placer import place_batch
+    ci = util.CaseInputs(case, workdir)
+    tree, ref = ci.product_state()
+    res = place_batch(ref, ci.options, tree.name_to_node, ci.queries, tree=tree, device=0)
+    assert len(res) == len(ci.queries)
+    matrix = ci.refs is None
+    octx = None
+    ties = 0
+    for query, rec, r in zip(ci.queries, ci.g['queries'], res):
+        got = r['placements'][0]['p'][0]
+        exp = [util.unhex(x) for x in rec['p']]
+        assert r['placements'][0]['n'] == [rec['out_name']]
+        if got[0] != exp[0] and octx is None:
+            octx = ci.oracle_context()
+        if _check_p(case, query[0], got, exp, matrix, octx, (query[0], query[1], dict(query[2]) if query[2] else None)) == 'tie':
+            ties += 1
+    assert ties <= max(1, len(res) // 10), 'too many tie exceptions: %d' % ties
+    from apples_b200 import jplace
+    import json
+    joined = jplace.join_jplace(json.loads(json.dumps(res)))
+    assert [p['n'][0] for p in joined['placements']] == ci.g['joined_names']
+
+
+def test_counts_bit_exact_and_distances(workdir):
+    """kernel (a): mismatch / valid counts of all 10 x 490 pairs of config 1 are bit-exact; jc69 within 1e-9 of the
+    oracle and within 5e-9 (8-decimal rounding) of the reference's data/dist.mat."""
+    from oracle import apples_oracle as orc
+    ci = util.CaseInputs('c1_align_FM_MLSE', workdir)
+    tree, ref = ci.product_state()
+    pl = _placer(ci, tree, ref)
+    packed = pl.pack_queries([q[1] for q in ci.queries])
+    mism, valid, dist = pl.distance_counts(packed, 0.001)
+    assert pl.ref_names == ci.g['ref_names']
+    exp = np.array(ci.g['counts'], dtype=np.int64)
+    assert (mism == exp[:, :, 0]).all() and (valid == exp[:, :, 1]).all()
+    rows = util.read_dismat(util.gunzip_to('dist.mat', workdir))
+    worst = 0.0
+    for qi, (qname, qseq, _) in enumerate(ci.queries):
+        for ri, rn in enumerate(pl.ref_names):
+            d = orc.jc69(qseq, ci.refs[rn], 0.001)
+            assert util.close(dist[qi, ri], d, REL, 0.0), (qname, rn, dist[qi, ri], d)
+            worst = max(worst, abs(dist[qi, ri] - rows[qi][2][rn]))
+    assert worst <= 5.1e-9
+    # overlap gate (distance.py:735): with a 0.9 overlap requirement many pairs become missing data (-1.0)
+    _, _, dist2 = pl.distance_counts(packed, 0.9)
+    for qi, (qname, qseq, _) in enumerate(ci.queries[:3]):
+        for ri, rn in enumerate(pl.ref_names):
+            d = orc.jc69(qseq, ci.refs[rn], 0.9)
+            assert util.close(dist2[qi, ri], d, REL, 0.0)
+    pl.close()
+
+
+def test_scoredist(workdir):
+    """kernel (a), amino acids: scoredist with FastTree's BLOSUM45 within 1e-9 relative (BLAS summation order)."""
+    from oracle import apples_oracle as orc
+    ci = util.CaseInputs('c3_prot_FM_MLSE', workdir)
+    tree, ref = ci.product_state()
+    pl = _placer(ci, tree, ref)
+    packed = pl.pack_queries([q[1] for q in ci.queries])
+    _, valid, dist = pl.distance_counts(packed, 0.001)
+    sd = ci.g['scoredist_q0']
+    idx = {n: i for i, n in enumerate(pl.ref_names)}
+    for n, d in zip(sd['refs'], sd['d']):
+        assert util.close(dist[0, idx[n]], util.unhex(d), REL, 0.0), (n, dist[0, idx[n]], util.unhex(d))
+    rng = np.random.default_rng(1)
+    for qi in range(len(ci.queries)):
+        for ri in rng.integers(0, len(pl.ref_names), 40):
+            a, b = ci.queries[qi][1], ci.refs[pl.ref_names[ri]]
+            assert util.close(dist[qi, ri], orc.scoredist(a, b, 0.001), REL, 0.0)
+            assert valid[qi, ri] == np.count_nonzero((a != b'-') & (b != b'-'))
+    pl.close()
+
+
+@pytest.mark.parametrize('case', ['c1_align_FM_MLSE', 'c1_align_FM_MLSE_f045_b5', 'c1_align_special', 'c2_matrix_FM_MLSE',
+                                  'c2_matrix_BME_ME_b5', 'c2_matrix_OLS_HYBRID_f100', 'syn300_FM_MLSE_pos',
+                                  'c3_prot_FM_MLSE', 'small_FM_MLSE_pos'])
+def test_observed_sets(case, workdir):
+    """kernel (c): the observed set of every query equals the reference's obs_dist (after the own-entry removal of
+    PoolQueryWorker.py:63-66): same leaves, distances exact (matrix) / 1e-9 (alignment)."""
+    ci = util.CaseInputs(case, workdir)
+    tree, ref = ci.product_state()
+    pl = _placer(ci, tree, ref)
+    params = pl.params_from_options(ci.options)
+    names = [q[0] for q in ci.queries]
+    self_node = pl.self_nodes(names)
+    if ci.refs is None:
+        tags = list(ci.queries[0][2].keys())
+        pl.set_matrix_tags(tags)
+        rows = np.array([[q[2][t] for t in tags] for q in ci.queries], dtype=np.float64)
+        count, node, dist = pl.observed_sets(params, rows=rows, self_node=self_node, cap=2048)
+    else:
+        packed = pl.pack_queries([q[1] for q in ci.queries])
+        count, node, dist = pl.observed_sets(params, packed=packed, self_node=self_node, cap=2048)
+    for qi, rec in enumerate(ci.g['queries']):
+        exp = {tree.name_to_node[k]: util.unhex(v) for k, v in rec['observed'] if k != rec['name']}
+        k = int(count[qi])
+        assert k == len(exp), (case, rec['name'], k, len(exp))
+        if rec['status'] in (1, 2):
+            continue  # zero-distance / too-few: the set is not sorted (no placement follows)
+        got_nodes = node[qi, :k].tolist()
+        assert got_nodes == sorted(exp.keys()), (case, rec['name'])
+        for u, d in zip(got_nodes, dist[qi, :k].tolist()):
+            if ci.refs is None:
+                assert d == exp[u]
+            else:
+                assert util.close(d, exp[u], REL, 0.0)
+    pl.close()
+
+
+@pytest.mark.parametrize('case', [c for c in ALL_CASES if c.startswith(('small_', 'c2_', 'syn300_', 'c1_align_FM', 'c3_prot_FM'))])
+def test_edge_solutions(case, workdir):
+    """kernel (b): x_1, x_2 and the LS error on EVERY edge of the restricted subtree, and the valid-node set."""
+    ci = util.CaseInputs(case, workdir)
+    tree, ref = ci.product_state()
+    pl = _placer(ci, tree, ref)
+    params = pl.params_from_options(ci.options)
+    matrix = ci.refs is None
+    if matrix:
+        tags = list(ci.queries[0][2].keys())
+        pl.set_matrix_tags(tags)
+    n = 0
+    for (qname, qseq, row), rec in zip(ci.queries, ci.g['queries']):
+        if 'edges' not in rec:
+            continue
+        n += 1
+        sn = tree.name_to_node.get(qname, -1)
+        if matrix:
+            x1, x2, err, valid = pl.edge_solutions(params, row=np.array([[row[t] for t in tags]], dtype=np.float64),
+                                                   self_node=sn)
+        else:
+            x1, x2, err, valid = pl.edge_solutions(params, packed_row=pl.pack_queries([qseq]), self_node=sn)
+        exp = {int(k): [util.unhex(x) for x in v] for k, v in rec['edges'].items()}
+        assert sorted(np.nonzero(valid)[0].tolist()) == sorted(exp.keys()), (case, qname)
+        assert int(valid.sum()) == rec['num_nodes']
+        for u, (e1, e2, ee) in exp.items():
+            if matrix:
+                assert x1[u] == e1 and x2[u] == e2, (case, qname, u, x1[u], e1, x2[u], e2)
+            else:
+                scale = max(abs(e1), abs(e2), tree.edge_length[u], 1e-3)
+                assert abs(x1[u] - e1) <= 1e-9 * scale and abs(x2[u] - e2) <= 1e-9 * scale, (case, qname, u)
+            assert util.close(err[u], ee, REL, ERR_FLOOR), (case, qname, u, err[u], ee)
+    assert n > 0
+    pl.close()
+
+
+def _synthetic(n_leaves, L, n_queries, seed, workdir, protein=False, **tree_kw):
+    from apples_b200 import synth
+    from apples_b200.reference import ReducedReference
+    from apples_b200.tree import BackboneTree
+    nwk = synth.random_tree(n_leaves, seed=seed, **tree_kw)
+    tree = BackboneTree.from_newick(nwk)
+    refs, states = synth.evolve_alignment(tree, L, seed=seed + 1, protein=protein)
+    queries, src = synth.make_queries(tree, states, n_queries, seed=seed + 2, protein=protein)
+    ref = ReducedReference(None, protein, None, 0.2, 1, tree=tree, refs=refs)
+    return nwk, tree, refs, ref, queries, src
+
+
+@pytest.mark.parametrize('method,criterion', [('OLS', 'MLSE'), ('BME', 'MLSE'), ('FM', 'HYBRID'), ('BE', 'ME')])
+def test_synthetic_against_oracle(method, criterion, workdir):
+    """config-4-like shapes at a size the oracle finishes in seconds: 2000-leaf backbone, 1500 sites."""
+    import os
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200 import treecluster
+    from apples_b200.placer import place_batch
+    nwk, tree, refs, ref, queries, _ = _synthetic(2000, 1500, 48, 100, workdir)
+    ref.set_baseobs(25)
+    opt = types.SimpleNamespace(method_name=method, criterion_name=criterion, negative_branch=False,
+                                base_observation_threshold=25, filt_threshold=0.2, minimum_alignment_overlap=0.001,
+                                exclude_intplace=False)
+    qlist = [(k, v, None) for k, v in queries.items()]
+    res = place_batch(ref, opt, tree.name_to_node, qlist, tree=tree, device=0)
+    tfp = os.path.join(workdir, 'syn2000.nwk')
+    open(tfp, 'w').write(nwk)
+    otree, onames = orc.load_tree(tfp)
+    octx = orc.OracleContext(otree, onames, refs=refs, representatives=ref.representatives, method=method,
+                             criterion=criterion)
+    ties = 0
+    for q, r in zip(qlist, res):
+        exp, _ = octx.runquery(q[0], q[1], None)
+        if _check_p('syn2000', q[0], r['placements'][0]['p'][0], exp['placements'][0]['p'][0], False, octx, q) == 'tie':
+            ties += 1
+    assert ties <= 2
+
+
+def test_properties_at_scale(workdir):
+    """Size-independent properties on a 20 000-leaf backbone with 5000 sites and 6000 queries (several sub-batches
+    of the dense kernel): determinism, batch-composition independence, resident == host path, and copies of backbone
+    leaves land on a zero-distance leaf whose sequence really is at distance 0."""
+    from apples_b200 import _lib
+    from apples_b200.placer import GpuPlacer
+    nwk, tree, refs, ref, queries, src = _synthetic(20000, 5000, 6000, 200, workdir)
+    pl = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+    pl.set_limits(max_subbatch=2048, scratch_bytes=32 << 20, slot_cap=32)  # force sub-batches, chunks and overflow reruns
+    params = _lib.make_params('FM', 'MLSE')
+    names = list(queries.keys())
+    packed = pl.pack_queries([queries[n] for n in names])
+    # exact copies of 50 leaves, appended
+    leaf_names = [tree.label[u] for u in tree.leaf_ids[:50]]
+    packed = np.concatenate([packed, pl.pack_queries([refs[n] for n in leaf_names])])
+    self_node = np.full(packed.shape[0], -1, np.int32)
+    a = pl.place_packed(packed, self_node, params)
+    b = pl.place_packed(packed, self_node, params)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    pl.set_limits(max_subbatch=32768, scratch_bytes=6 << 30, slot_cap=256)
+    b2 = pl.place_packed(packed, self_node, params)
+    for x, y in zip(a, b2):
+        assert (x == y).all()
+    sub = pl.place_packed(packed[1000:1100], self_node[1000:1100], params)
+    for x, y in zip(a, sub):
+        assert (x[1000:1100] == y).all()
+    pl.upload_queries(packed)
+    pl.place_resident(params)
+    c = pl.download_results()
+    for x, y in zip(a, c):
+        assert (x == y).all()
+    edge, error, distal, pendant, status = a
+    code = status & 0xff
+    assert (code[-50:] == _lib.ZERO_DIST_LEAF).all()
+    mism, valid, dist = pl.distance_counts(packed[-50:], 0.001)
+    row_of = {n: i for i, n in enumerate(pl.ref_names)}
+    node_to_name = {tree.name_to_node[n]: n for n in pl.ref_names}
+    for i in range(50):
+        hit = node_to_name[int(edge[-50 + i])]
+        assert mism[i, row_of[hit]] == 0 and dist[i, row_of[hit]] == 0.0
+    placed = (code == _lib.PLACED) | (code == _lib.PLACED_MISPLACEMENT_FLAG)
+    assert placed[:-50].mean() > 0.95
+    el = tree.edge_length[edge[placed]]
+    assert (distal[placed] >= -1e-12).all() and (distal[placed] <= np.maximum(el, 0) + 1e-12).all()
+    assert (pendant[placed] >= 0).all()
+    # the true source leaf of each query is usually inside the clade the query is placed into / next to
+    t = pl.timings()
+    assert t['rep_distance_launches'] >= 2
+    pl.close()

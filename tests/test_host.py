@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the product (tree layout, FASTA input, packing, clusters, jplace assembly)."""
+import hashlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import util
+from apples_b200 import fasta, jplace, synth, treecluster
+from apples_b200.placer import results_to_jplace
+from apples_b200.reference import ReducedReference, consensus_rows
+from apples_b200.tree import BackboneTree
+
+
+def test_tree_layout_small(workdir):
+    t = BackboneTree.from_newick('((A:0.1,B:0.2):0.25,(C:0.3,(D:0.2,E:0.2):0.2):0.25);')
+    # post-order ranks: A0 B1 (AB)2 C3 D4 E5 (DE)6 (C(DE))7 root8
+    assert t.name_to_node == {'A': 0, 'B': 1, 'C': 3, 'D': 4, 'E': 5}
+    assert t.parent.tolist() == [2, 2, 8, 7, 6, 6, 7, 8, -1]
+    assert t.level.tolist() == [2, 2, 1, 2, 3, 3, 2, 1, 0]
+    assert t.first.tolist() == [0, 1, 0, 3, 4, 5, 4, 3, 0]
+    assert t.children_of(8) == [2, 7] and t.children_of(7) == [3, 6]
+    assert t.extended_newick() == '((A:0.1{0},B:0.2{1}):0.25{2},(C:0.3{3},(D:0.2{4},E:0.2{5}):0.2{6}):0.25{7});'
+
+
+@pytest.mark.parametrize('case,fn', [('c2_matrix_FM_MLSE', 'backbone.nwk'), ('c3_prot_FM_MLSE', 'prot_backbone.nwk'),
+                                     ('syn300_FM_MLSE_pos', 'syn300.nwk')])
+def test_extended_newick_matches_reference(case, fn, workdir):
+    """the reference's extended newick (jutil.py:22-96) of the same file, by hash (oracle/gen_golden.py)"""
+    t = BackboneTree.from_newick(util.gunzip_to(fn, workdir))
+    assert hashlib.sha256(t.extended_newick().encode()).hexdigest() == util.load_golden(case)['extended_newick_sha']
+
+
+def test_fasta2dic(tmp_path):
+    p = tmp_path / 'x.fa'
+    p.write_text('>s1 some description\nACGTnn-x\nRYacgt\n>s2\nAC.T*\n')
+    d = fasta.fasta2dic(str(p), False, False)
+    assert list(d) == ['s1', 's2']
+    assert d['s1'].tobytes() == b'ACGT------ACGT'  # N, X, R, Y -> '-' (fasta2dic.py:61)
+    assert d['s2'].tobytes() == b'AC.T*'           # non-letters survive, like the reference
+    d = fasta.fasta2dic(str(p), False, True)
+    assert d['s1'].tobytes() == b'ACGT' + b'-' * 10  # lower-case masked (fasta2dic.py:52-54); R, Y invalid
+    d = fasta.fasta2dic(str(p), True, False)
+    assert d['s1'].tobytes() == b'ACGTNN--RYACGT'  # protein alphabet: only B J O U X Z become '-' (fasta2dic.py:59)
+    p2 = tmp_path / 'x.fq'
+    p2.write_text('@r1\nACGT\n+\nIIII\n@r2\nGGCC\n+\nIIII\n')
+    d = fasta.fasta2dic(str(p2), False, False)
+    assert {k: v.tobytes() for k, v in d.items()} == {'r1': b'ACGT', 'r2': b'GGCC'}
+
+
+def test_pack_nucleotide_roundtrip():
+    rng = np.random.default_rng(5)
+    L = 1234
+    mat = np.frombuffer(b'ACGT-', dtype=np.uint8)[rng.integers(0, 5, (7, L))]
+    pk = fasta.pack_nucleotide(mat)
+    W = fasta.words_per_row(L)
+    assert pk.shape == (7, 3, W) and W % 4 == 0 and pk.dtype == np.uint32
+    bits = np.unpackbits(pk.view(np.uint8).reshape(7, 3, W * 4), axis=2, bitorder='little')[:, :, :L]
+    code = bits[:, 0] + 2 * bits[:, 1]
+    back = np.where(bits[:, 2] == 1, np.frombuffer(b'ACGT', dtype=np.uint8)[code], ord('-'))
+    assert (back == mat).all()
+    assert (bits[:, 0][bits[:, 2] == 0] == 0).all() and (bits[:, 1][bits[:, 2] == 0] == 0).all()
+    # counts from planes == counts from bytes (distance.py:733-737)
+    a, b = pk[0], pk[1]
+    v = a[2] & b[2]
+    m = ((a[0] ^ b[0]) | (a[1] ^ b[1])) & v
+    pop = lambda x: int(np.unpackbits(x.view(np.uint8)).sum())
+    nd = (mat[0] != ord('-')) & (mat[1] != ord('-'))
+    assert pop(v) == int(nd.sum()) and pop(m) == int(((mat[0] != mat[1]) & nd).sum())
+    with pytest.raises(ValueError):
+        fasta.pack_nucleotide(np.frombuffer(b'AC.T', dtype=np.uint8)[None, :])
+
+
+def test_pack_protein():
+    mat = np.frombuffer(b'ARNDCQEGHILKMFPSTWYV-*a', dtype=np.uint8)[None, :]
+    pk = fasta.pack_protein(mat)
+    assert pk.shape == (1, 32)
+    assert pk[0, :23].tolist() == list(range(20)) + [20, 0, 0]
+    assert (pk[0, 23:] == 20).all()
+
+
+def test_clusters_and_consensus(workdir):
+    from oracle import apples_oracle as orc
+    ci = util.CaseInputs('syn300_FM_MLSE_pos', workdir)
+    tree, ref = ci.product_state()
+    reps = orc.representatives_from_tsv(ci.tsv, ci.refs, False)
+    assert len(reps) == len(ref.representatives)
+    for (c0, g0), (c1, g1) in zip(reps, ref.representatives):
+        assert g0 == g1 and c0.tobytes() == c1.tobytes()
+    # in-repo clustering: a partition of the leaves whose clusters respect the diameter bound
+    cl = treecluster.max_diameter_clusters(tree, 0.24)
+    leaves = sorted(u for c in cl for u in c)
+    assert leaves == tree.leaf_ids.tolist()
+    dev = ref.device_arrays(tree.name_to_node)
+    assert dev['packed_refs'].shape[0] == 300 and dev['group_offsets'][-1] == 300
+    assert sorted(dev['group_members'].tolist()) == list(range(300))
+
+
+def test_cluster_diameter_bound():
+    nwk = synth.random_tree(120, seed=3)
+    t = BackboneTree.from_newick(nwk)
+    cl = treecluster.max_diameter_clusters(t, 0.1)
+    depth = np.zeros(t.num_nodes)
+    for u in range(t.num_nodes - 2, -1, -1):
+        depth[u] = depth[t.parent[u]] + max(t.edge_length[u], 0)
+
+    def dist(a, b):
+        x, y = a, b
+        while x != y:
+            if x < y:
+                x = t.parent[x]
+            else:
+                y = t.parent[y]
+        return depth[a] + depth[b] - 2 * depth[x]
+    for c in cl:
+        for i in range(len(c)):
+            for j in range(i + 1, len(c)):
+                assert dist(c[i], c[j]) <= 0.1 + 1e-12
+
+
+def test_results_to_jplace_and_join():
+    out = (np.array([5, 7, -1, 9], np.int32), np.array([0.5, 0, 0, 0.25]), np.array([0.1, 0, 0, 0.2]),
+           np.array([0.3, 0, 0, 0.0]), np.array([0, 1, 2, 3 | 0x100], np.int32))
+    res = results_to_jplace(['a', 'b', 'c', 'd'], [False, True, False, False], out, log=False)
+    assert res[0] == {'placements': [{'p': [[5, 0.5, 1, 0.1, 0.3]], 'n': ['a']}]}
+    assert res[1] == {'placements': [{'p': [[7, 0, 1, 0, 0]], 'n': ['b-query']}]}
+    assert res[2]['placements'][0]['p'] == [[-1, 0, 1, 0, 0]]
+    assert res[3]['placements'][0]['p'] == [[9, 0.25, 1, 0.2, 0]] and isinstance(res[3]['placements'][0]['p'][0][4], int)
+    ex = results_to_jplace(['d'], [False], tuple(o[3:] for o in out), exclude_intplace=True, log=False)
+    assert ex[0]['placements'][0]['p'][0][0] == -1
+    joined = jplace.join_jplace(json.loads(json.dumps(res)))
+    assert [p['n'][0] for p in joined['placements']] == ['a', 'b-query', 'd']  # jutil.py:11-19
+
+
+def test_synth_determinism():
+    a = synth.random_tree(50, seed=9)
+    assert a == synth.random_tree(50, seed=9) and a != synth.random_tree(50, seed=10)
+    t = BackboneTree.from_newick(a)
+    assert len(t.leaf_ids) == 50 and t.nchild[t.num_nodes - 1] == 3
