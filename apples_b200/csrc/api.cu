@@ -746,6 +746,21 @@ int apples_results_download(apples_ctx* ctx, int32_t* edge, double* error, doubl
     return 0;
 }
 
+int apples_results_to_device(apples_ctx* ctx, void* edge, void* error, void* distal, void* pendant, void* status) {
+    if (!ctx) return -1;
+    if (ctx->res_nq <= 0) return fail(ctx, "no resident results");
+    const size_t n = (size_t)ctx->res_nq;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (edge) CK(cudaMemcpyAsync(edge, ctx->res_edge.p, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (error) CK(cudaMemcpyAsync(error, ctx->res_err.p, n * 8, cudaMemcpyDeviceToDevice, s));
+    if (distal) CK(cudaMemcpyAsync(distal, ctx->res_distal.p, n * 8, cudaMemcpyDeviceToDevice, s));
+    if (pendant) CK(cudaMemcpyAsync(pendant, ctx->res_pendant.p, n * 8, cudaMemcpyDeviceToDevice, s));
+    if (status) CK(cudaMemcpyAsync(status, ctx->res_status.p, n * 4, cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queries, double overlap_frac, uint32_t* mism,
                            uint32_t* valid, double* dist) {
     if (!ctx) return -1;

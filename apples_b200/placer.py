@@ -142,6 +142,10 @@ class GpuPlacer:
         self._check(self.lib.apples_results_download(self.h, *[_lib.ptr(o) for o in out]))
         return out
 
+    def results_to_device(self, edge, error, distal, pendant, status):
+        """copy the resident results into caller-owned device tensors (objects with .data_ptr())"""
+        self._check(self.lib.apples_results_to_device(self.h, *[t.data_ptr() for t in (edge, error, distal, pendant, status)]))
+
     def timings(self, reset=False):
         v = np.zeros(11, np.float64)
         self.lib.apples_get_timings(self.h, _lib.ptr(v), 11, 1 if reset else 0)

@@ -15,8 +15,10 @@ NUC_ALPHABET = np.frombuffer(b'ACGT', dtype=np.uint8)
 AA_ALPHABET = np.frombuffer(b'ARNDCQEGHILKMFPSTWYV', dtype=np.uint8)
 
 
-def random_tree(n_leaves, seed, mean_edge=0.02, polytomy_frac=0.0, zero_frac=0.0, neg_frac=0.0, prefix='L'):
-    """Returns a newick string."""
+def random_tree(n_leaves, seed, mean_edge=0.02, polytomy_frac=0.0, zero_frac=0.0, neg_frac=0.0, prefix='L',
+                model='yule'):
+    """Returns a newick string.  model='yule': every insertion subdivides a uniformly chosen PENDANT edge (depth
+    grows like log N, as in real backbones); model='uniform': a uniformly chosen edge (depth grows like sqrt N)."""
     rng = np.random.default_rng(seed)
     n = int(n_leaves)
     assert n >= 3
@@ -29,9 +31,14 @@ def random_tree(n_leaves, seed, mean_edge=0.02, polytomy_frac=0.0, zero_frac=0.0
     cnt = 4
     picks = rng.random(n)  # one uniform per insertion
     par = parent
+    leaf_list = [1, 2, 3]
     for k in range(3, n):
         # choose a random non-root node e (= the edge above it), subdivide it and hang a new leaf
-        e = 1 + int(picks[k] * (cnt - 1))
+        if model == 'yule':
+            e = leaf_list[int(picks[k] * len(leaf_list))]
+            leaf_list.append(cnt + 1)
+        else:
+            e = 1 + int(picks[k] * (cnt - 1))
         mid = cnt
         leaf = cnt + 1
         cnt += 2

@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py -- queries placed per second on the 200 000-leaf backbone (BASELINE.json metric, config 5).
+
+    python bench.py --gpus N --steps K --warmup W                 (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W  the CPU arm (rank 0 only)
+
+Workload: synthetic 200 000-leaf Yule backbone, 5000-site nucleotide alignment
+evolved under JC69 with gaps, max-diameter clusters at 1.2 x 0.2, FM + MLSE, -f 0.2 -b 25 -V 0.001.  One "step" places
+125 000 queries per GPU (1 M queries at 8 GPUs: weak scaling, queries shard with no data-path collective; the only
+collective is the final NCCL all-gather of the placements, which is inside the timed region).
+
+`value` is measured with the packed queries already resident in HBM (apples_place_resident); `e2e` goes through the
+reference-facing C-ABI call apples_place_batch with pinned HOST buffers, host<->device copies inside the timed region.
+The roofline object describes the dominant kernel (dense query x representative distance kernel); the CPU baseline is
+the oracle port of the reference's Python path (kind "port": the reference itself is Python and cannot travel to the
+GPU box) run through a fork pool on all host cores on a bounded sample of the same queries.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--leaves', type=int, default=200000)
+    ap.add_argument('--sites', type=int, default=5000)
+    ap.add_argument('--queries-per-gpu', type=int, default=125000)
+    ap.add_argument('--method', default='FM')
+    ap.add_argument('--criterion', default='MLSE')
+    ap.add_argument('--cpu-sample', type=int, default=0, help='queries in the CPU-baseline sample (0 = auto)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def build_workload(args, device, rank, want_host_refs):
+    """Synthetic backbone + reference (identical on every rank) and this rank's queries.  Untimed setup."""
+    import torch
+    from apples_b200 import synth, synth_torch, treecluster, fasta
+    from apples_b200.tree import BackboneTree
+    t0 = time.time()
+    nwk = synth.random_tree(args.leaves, seed=2)
+    tree = BackboneTree.from_newick(nwk)
+    ref_bytes, leaf_states = synth_torch.evolve_alignment(tree, args.sites, 5, device)
+    q_bytes, src = synth_torch.make_queries(leaf_states, args.queries_per_gpu, 1000 + rank, device)
+    del leaf_states
+    packed_refs = synth_torch.pack_nucleotide(ref_bytes).cpu().numpy().view(np.uint32)
+    packed_q = synth_torch.pack_nucleotide(q_bytes)
+    ref_host = ref_bytes.cpu().numpy()
+    del ref_bytes
+    # clusters and consensus representatives (Reference.py:85-107 equivalent, build-time)
+    clusters = treecluster.max_diameter_clusters(tree, 0.2 * 1.2)
+    leaf_row = {int(u): i for i, u in enumerate(tree.leaf_ids.tolist())}
+    # the reference orders representatives by the cluster-id STRING with singletons ('-1') first (Reference.py:97)
+    multi = [c for c in clusters if len(c) > 1]
+    single = [c for c in clusters if len(c) == 1]
+    keyed = sorted(((str(i + 1), c) for i, c in enumerate(multi)), key=lambda kc: kc[0])
+    ordered = single + [c for _, c in keyed]
+    from apples_b200.reference import consensus_rows
+    reps = np.empty((len(ordered), args.sites), dtype=np.uint8)
+    offs = np.zeros(len(ordered) + 1, dtype=np.int32)
+    members = []
+    for i, c in enumerate(ordered):
+        rows = [leaf_row[u] for u in c]
+        reps[i] = ref_host[rows[0]] if len(rows) == 1 else consensus_rows(ref_host[rows], False)
+        members.extend(rows)
+        offs[i + 1] = len(members)
+    packed_reps = fasta.pack_nucleotide(reps)
+    arrays = dict(kind=fasta.NUC, L=args.sites, ref_names=[tree.label[u] for u in tree.leaf_ids.tolist()],
+                  packed_refs=packed_refs, ref_node=tree.leaf_ids.astype(np.int32), packed_reps=packed_reps,
+                  group_offsets=offs, group_members=np.asarray(members, dtype=np.int32))
+    info = {'setup_s': round(time.time() - t0, 1), 'n_rep': len(ordered), 'max_level': int(tree.level.max())}
+    host = None
+    if want_host_refs:
+        host = dict(nwk=nwk, ref_host=ref_host, reps=reps, ordered=ordered, leaf_row=leaf_row, q_bytes=q_bytes)
+    return tree, arrays, packed_q, q_bytes, info, host
+
+
+def cpu_context(args, tree, host):
+    """Oracle-side state (the analogue of prepareTree + ReducedReference, built once, untimed like the reference's
+    own setup: its timer brackets only the starmap call, run_apples.py:93-104)."""
+    import tempfile
+    from oracle import apples_oracle as orc
+    tfp = os.path.join(tempfile.mkdtemp(prefix='apples_bench_'), 'backbone.nwk')
+    with open(tfp, 'w') as f:
+        f.write(host['nwk'])
+    otree, onames = orc.load_tree(tfp)
+    names = [tree.label[u] for u in tree.leaf_ids.tolist()]
+    ref_host = host['ref_host']
+    refs = {n: ref_host[i].view('S1') for i, n in enumerate(names)}
+    reps = [(host['reps'][i].view('S1'), [names[host['leaf_row'][u]] for u in c]) for i, c in enumerate(host['ordered'])]
+    return orc.OracleContext(otree, onames, refs=refs, representatives=reps, method=args.method, criterion=args.criterion)
+
+
+def cpu_baseline(ctx, q_host, threads):
+    """The oracle port of the reference's Python path (PoolQueryWorker.runquery under a fork pool,
+    run_apples.py:94-102) on the given queries.  Returns (queries/s, seconds, results)."""
+    from oracle import apples_oracle as orc
+    queries = [('Q%07d' % i, q_host[i].view('S1'), None) for i in range(len(q_host))]
+    t0 = time.time()
+    res = orc.run_pool(ctx, queries, threads)
+    dt = time.time() - t0
+    return len(queries) / dt, dt, res
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    threads = os.cpu_count() or 1
+    workload = ('synthetic %d-leaf Yule backbone, %d-site nucleotide alignment (JC69 + gaps), %d queries per GPU per '
+                'step, APPLES-2 clusters at 1.2x0.2, %s+%s, -f 0.2 -b 25' % (args.leaves, args.sites,
+                                                                           args.queries_per_gpu, args.method,
+                                                                           args.criterion))
+    import torch
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        dev = 'cuda:0' if torch.cuda.is_available() else 'cpu'
+        tree, arrays, packed_q, q_bytes, info, host = build_workload(args, dev, 0, True)
+        n_sample = args.cpu_sample or max(threads * 2, 32)
+        q_host = q_bytes[:n_sample * (args.steps + args.warmup)].cpu().numpy()
+        rates = []
+        octx = cpu_context(args, tree, host)
+        for s in range(args.warmup + args.steps):
+            qs = q_host[s * n_sample:(s + 1) * n_sample]
+            r, dt, _ = cpu_baseline(octx, qs, threads)
+            if s >= args.warmup:
+                rates.append((r, dt))
+        tot_t = sum(dt for _, dt in rates)
+        val = n_sample * len(rates) / tot_t
+        line = {'impl': 'reference', 'metric': 'queries placed/sec', 'value': val, 'unit': 'queries/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / len(rates),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u32 popcount + f64',
+                'data': 'synthetic', 'config': {'workload': workload, 'sample_queries_per_step': n_sample},
+                'cpu_baseline': {'value': val, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
+                                 'sample': '%d queries per step through the oracle port of PoolQueryWorker.runquery, '
+                                           'fork pool of %d processes' % (n_sample, threads)},
+                'e2e': {'value': val, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+    from apples_b200 import _lib
+    from apples_b200.placer import GpuPlacer
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device; the hot path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    device = 'cuda:%d' % local_rank
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    want_host = (rank == 0 and not args.no_cpu_baseline)
+    tree, arrays, packed_q, q_bytes, info, host = build_workload(args, device, rank, want_host)
+    nq = args.queries_per_gpu
+    pl = GpuPlacer(tree, None, tree.name_to_node, device=local_rank)
+    pl.set_reference_arrays(**arrays)
+    params = _lib.make_params(args.method, args.criterion)
+    packed_host = torch.empty(packed_q.shape, dtype=torch.int32).pin_memory()
+    packed_host.copy_(packed_q)
+    del packed_q
+    pl.upload_queries(packed_host)
+    stream = torch.cuda.ExternalStream(pl.stream, device=device)
+    # send / receive buffers of the final gather of placements
+    send = (torch.empty(nq, dtype=torch.int32, device=device), torch.empty(nq, dtype=torch.float64, device=device),
+            torch.empty(nq, dtype=torch.float64, device=device), torch.empty(nq, dtype=torch.float64, device=device),
+            torch.empty(nq, dtype=torch.int32, device=device))
+    recv = [torch.empty(nq * world, dtype=t.dtype, device=device) for t in send] if world > 1 else None
+
+    def step_resident():
+        pl.place_resident(params)
+        if world > 1:
+            pl.results_to_device(*send)
+            for r, t in zip(recv, send):
+                dist.all_gather_into_tensor(r, t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    pl.timings(reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    tm = pl.timings(reset=True)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = nq * world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the C-ABI call with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        self_node = None
+        for _ in range(min(args.warmup, 1)):
+            pl.place_packed(packed_host.numpy(), self_node, params)
+        barrier()
+        e0.record(stream)
+        t0 = time.time()
+        for _ in range(args.steps):
+            out = pl.place_packed(packed_host.numpy(), self_node, params)
+        e1.record(stream)
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e = {'value': nq * world * args.steps / (ems / 1e3), 'unit': 'queries/s',
+               'h2d_bytes_per_step': int(packed_host.numel() * 4), 'd2h_bytes_per_step': int(nq * 36),
+               'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps}
+        pl.timings(reset=True)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (dense representative distances), per launch ----
+    peaks = {}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    n_dense = max(tm['rep_distance_launches'], 1.0)
+    dense_ms = tm['rep_distance_ms'] / n_dense
+    W = _lib.load().apples_words_per_row(args.sites)
+    n_rep = info['n_rep']
+    q_per_launch = nq * args.steps / n_dense
+    alg_bytes = (q_per_launch + n_rep) * 3 * W * 4 + 4.0 * q_per_launch * n_rep
+    ach = alg_bytes / (dense_ms * 1e-3) / 1e9
+    cell_sites = q_per_launch * n_rep * args.sites
+    cs_rate = cell_sites / (dense_ms * 1e-3)
+    sm_max = clocks.get('sm_max_mhz') or float(peaks.get('sm_max_mhz', 1965.0))
+    sm_cur = clocks.get('sm_mhz') or sm_max
+    # integer-pipe ceiling: 2 POPC per 32-site word-pair, POPC issues 16 lanes/clk/SM (profiles/microbench_r01.txt)
+    int_peak_max = 148 * 16 * 16 * sm_max * 1e6
+    int_peak_cur = 148 * 16 * 16 * sm_cur * 1e6
+    roofline = {'kernel': 'dense_nuc_kernel<false> (query x representative mismatch/valid counts)', 'bound': 'hbm',
+                'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None,
+                'peak_source': peak_src, 'avg_launch_ms': dense_ms, 'launches': n_dense,
+                'binding_resource': 'integer pipe (POPC/LOP3), not HBM: see int_pipe',
+                'int_pipe': {'achieved': cs_rate / 1e12, 'unit': 'Tcell-sites/s',
+                             'peak_at_max_clock': int_peak_max / 1e12, 'frac_at_max_clock': cs_rate / int_peak_max,
+                             'peak_at_observed_clock': int_peak_cur / 1e12, 'frac_at_observed_clock': cs_rate / int_peak_cur,
+                             'model': '148 SMs x 16 POPC lanes/clk x 16 sites per POPC (2 POPC per 32-site word pair)'}}
+    step_ms = ms / args.steps
+    stages = {k: tm[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms')}
+    line = {'metric': 'queries placed/sec', 'value': value, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u32 popcount + f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'n_representatives': n_rep, 'queries_per_step': nq * world,
+                       'l2': 'inputs larger than L2 (packed queries %.0f MB + packed reference %.0f MB per GPU)'
+                             % (nq * 3 * W * 4 / 1e6, (args.leaves + n_rep) * 3 * W * 4 / 1e6),
+                       'parallelism': 'queries sharded over %d GPU(s), reference + tree replicated, final NCCL all-gather' % world},
+            'distance_gcell_sites_per_s': (tm['pairs'] / args.steps) * args.sites / (step_ms * 1e-3) / 1e9 * world,
+            'stage_ms_per_step': stages, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
+            'observed_per_query': tm['observed'] / (nq * args.steps), 'valid_nodes_per_query': tm['valid_nodes'] / (nq * args.steps),
+            'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'setup': info}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----
+    if not args.no_cpu_baseline and world == 1:
+        n_sample = args.cpu_sample or max(threads * 2, 32)
+        q_host = q_bytes[:n_sample].cpu().numpy()
+        rate, dt, res = cpu_baseline(cpu_context(args, tree, host), q_host, threads)
+        # parity of the timed GPU results on that sample
+        edge, error, distal, pendant, status = pl.download_results()
+        same = 0
+        for i, r in enumerate(res):
+            p = r[0]['placements'][0]['p'][0]
+            if p[0] == int(edge[i]) and abs(p[1] - error[i]) <= 1e-9 * max(abs(p[1]), 1e-3):
+                same += 1
+        line['cpu_baseline'] = {'value': rate, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
+                                'sample': '%d of this step\'s queries through the oracle port of '
+                                          'PoolQueryWorker.runquery under a fork pool of %d processes (%.1f s)'
+                                          % (n_sample, threads, dt),
+                                'parity_on_sample': '%d/%d identical edge and score within 1e-9' % (same, n_sample)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -107,6 +107,8 @@ int apples_queries_upload(apples_ctx* ctx, int64_t nq, const void* packed_querie
 int apples_place_resident(apples_ctx* ctx, const apples_params* params);
 int apples_results_download(apples_ctx* ctx, int32_t* edge, double* error, double* distal, double* pendant,
                             int32_t* status);
+/* same, into DEVICE buffers of the caller (e.g. the send buffers of the final NCCL gather of placements) */
+int apples_results_to_device(apples_ctx* ctx, void* edge, void* error, void* distal, void* pendant, void* status);
 
 /* ---- parity exports (test-only seams named in SURVEY.md section 8b) ---- */
 
