@@ -59,7 +59,10 @@ struct apples_ctx {
     double t_ms[T_NSTAGE] = {0, 0, 0, 0, 0, 0};
     double n_launch = 0, n_dense_launch = 0, n_pairs = 0, n_obs = 0, n_valid = 0;
     size_t scratch_limit = (size_t)6 << 30;  // placement scratch pool upper bound (bytes)
-    int64_t max_subbatch = 32768;
+    int64_t max_subbatch = 65536;
+    int64_t max_batch = 1 << 20;  // queries per macro-batch (batch-wide observed-list buffers)
+    std::vector<int> hK, hV, hS;
+    std::vector<long long> h_rec_off, h_stack_off;
     int slot_cap = 256;
 };
 
@@ -209,29 +212,28 @@ int check_params(apples_ctx* ctx, const apples_params* p) {
     return 0;
 }
 
-// the whole pipeline for nq queries, processed in sub-batches
-int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_params* prm) {
-    if (check_params(ctx, prm)) return -1;
-    if (ctx->M <= 0) return fail(ctx, "apples_set_tree has not been called");
-    const bool matrix = io.h_rows != nullptr;
-    if (matrix && ctx->n_cols <= 0) return fail(ctx, "apples_set_matrix_columns has not been called");
-    if (!matrix && ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
-    if (nq <= 0) return 0;
-    CK(cudaSetDevice(ctx->device));
+// One macro-batch (at most ctx->max_batch queries) through the pipeline:
+//   phase 1  per sub-batch, no host synchronisation: H2D -> transpose -> dense distances -> selection
+//   phase 2  one D2H of (K, V, status) for the whole batch; overflow reruns (rare)
+//   phase 3  placement of the whole batch in as few launches as the scratch pool allows (one thread per query:
+//            the kernel hides its dependent-load latency only with >= 100k queries in flight)
+//   phase 4  results D2H / D2D
+int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const apples_params* prm) {
     cudaStream_t s = ctx->stream;
+    const bool matrix = io.h_rows != nullptr;
     const int sel_kind = matrix ? SEL_MATRIX : (ctx->kind == APPLES_AA ? SEL_AA : SEL_NUC);
     const int n_units = matrix ? ctx->n_cols : ctx->n_rep;
     const int64_t ldk = matrix ? ctx->n_cols : ctx->rep_pad;
     const size_t key_bytes = (sel_kind == SEL_NUC) ? 4 : 8;
     const int n_leaf_bound = matrix ? ctx->n_cols : ctx->n_ref;
 
-    // sub-batch size: key matrix <= 1 GiB, at most 32768 queries, multiple of the dense tile
-    int64_t qb = ((int64_t)1 << 30) / std::max<int64_t>(1, ldk * (int64_t)key_bytes);
+    // sub-batch size: key matrix <= 2 GiB, multiple of the dense tile
+    int64_t qb = ((int64_t)2 << 30) / std::max<int64_t>(1, ldk * (int64_t)key_bytes);
     qb = std::min<int64_t>(std::max<int64_t>(qb, DT_TQ), std::max<int64_t>(ctx->max_subbatch, DT_TQ));
     qb = qb / DT_TQ * DT_TQ;
-    qb = std::min<int64_t>(qb, round_up((int)std::min<int64_t>(nq, 1 << 30), DT_TQ));
+    qb = std::min<int64_t>(qb, round_up(n, DT_TQ));
     const int QB = (int)qb;
-    int cap = io.obs_cap > 0 ? next_pow2(io.obs_cap) : std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
+    const int cap = io.obs_cap > 0 ? next_pow2(io.obs_cap) : std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
     if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
@@ -239,19 +241,19 @@ int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_param
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
     }
-    if (ensure(ctx, ctx->self_node, (size_t)QB * 4)) return -1;
-    if (ensure(ctx, ctx->obs_node, (size_t)QB * cap * 4)) return -1;
-    if (ensure(ctx, ctx->obs_dist, (size_t)QB * cap * 8)) return -1;
-    if (ensure(ctx, ctx->Kd, (size_t)QB * 4) || ensure(ctx, ctx->Vd, (size_t)QB * 4) ||
-        ensure(ctx, ctx->statusd, (size_t)QB * 4) || ensure(ctx, ctx->zero_edge, (size_t)QB * 4))
+    if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
+    if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
+    if (ensure(ctx, ctx->obs_dist, (size_t)n * cap * 8)) return -1;
+    if (ensure(ctx, ctx->Kd, (size_t)n * 4) || ensure(ctx, ctx->Vd, (size_t)n * 4) ||
+        ensure(ctx, ctx->statusd, (size_t)n * 4) || ensure(ctx, ctx->zero_edge, (size_t)n * 4))
         return -1;
     if (ensure(ctx, ctx->pair_counter, 8)) return -1;
-    if (ensure(ctx, ctx->o_edge, (size_t)QB * 4) || ensure(ctx, ctx->o_err, (size_t)QB * 8) ||
-        ensure(ctx, ctx->o_distal, (size_t)QB * 8) || ensure(ctx, ctx->o_pendant, (size_t)QB * 8) ||
-        ensure(ctx, ctx->o_status, (size_t)QB * 4))
+    if (ensure(ctx, ctx->o_edge, (size_t)n * 4) || ensure(ctx, ctx->o_err, (size_t)n * 8) ||
+        ensure(ctx, ctx->o_distal, (size_t)n * 8) || ensure(ctx, ctx->o_pendant, (size_t)n * 8) ||
+        ensure(ctx, ctx->o_status, (size_t)n * 4))
         return -1;
-    if (ensure(ctx, ctx->rec_off, (size_t)QB * 8) || ensure(ctx, ctx->stack_off, (size_t)QB * 8) ||
-        ensure(ctx, ctx->qlist, (size_t)QB * 4))
+    if (ensure(ctx, ctx->rec_off, (size_t)n * 8) || ensure(ctx, ctx->stack_off, (size_t)n * 8) ||
+        ensure(ctx, ctx->qlist, (size_t)std::max(n, 1) * 4))
         return -1;
     CK(cudaMemsetAsync(ctx->pair_counter.p, 0, 8, s));
     const bool dbg = io.dbg_x1 != nullptr;
@@ -264,37 +266,48 @@ int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_param
         CK(cudaMemsetAsync(ctx->dbg_err.p, 0, (size_t)ctx->M * 8, s));
         CK(cudaMemsetAsync(ctx->dbg_valid.p, 0, (size_t)ctx->M, s));
     }
+    const int* d_self = nullptr;
+    if (io.h_self) {
+        CK(cudaMemcpyAsync(ctx->self_node.p, io.h_self + base0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        d_self = (const int*)ctx->self_node.p;
+    } else if (io.d_self) {
+        d_self = io.d_self + base0;
+    }
 
-    std::vector<int> hK(QB), hV(QB), hS(QB);
-    std::vector<long long> h_rec_off(QB), h_stack_off(QB);
-    std::vector<int> h_qlist(QB);
+    std::vector<int>& hK = ctx->hK; std::vector<int>& hV = ctx->hV; std::vector<int>& hS = ctx->hS;
+    hK.resize(n); hV.resize(n); hS.resize(n);
+    std::vector<long long>& h_rec_off = ctx->h_rec_off; std::vector<long long>& h_stack_off = ctx->h_stack_off;
+    h_rec_off.resize(n); h_stack_off.resize(n);
     const NucGate gate = make_gate(ctx->L, prm->filt_threshold, prm->overlap_frac);
 
-    for (int64_t base = 0; base < nq; base += QB) {
-        const int nb = (int)std::min<int64_t>(QB, nq - base);
-        const int nb_pad = round_up(nb, DT_TQ);
-        // ---------------- inputs ----------------
-        const void* d_q = nullptr;
-        const double* d_rows = nullptr;
-        {
-            Span sp(ctx, T_H2D);
-            if (matrix) {
-                CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)base * ctx->n_cols, (size_t)nb * qrow,
-                                   cudaMemcpyHostToDevice, s));
-                d_rows = (const double*)ctx->keys.p;
-            } else if (io.h_queries) {
-                CK(cudaMemcpyAsync(ctx->q_rm.p, (const char*)io.h_queries + (size_t)base * qrow, (size_t)nb * qrow,
-                                   cudaMemcpyHostToDevice, s));
-                d_q = ctx->q_rm.p;
-            } else {
-                d_q = (const char*)io.d_queries + (size_t)base * qrow;
-            }
-            if (io.h_self)
-                CK(cudaMemcpyAsync(ctx->self_node.p, io.h_self + base, (size_t)nb * 4, cudaMemcpyHostToDevice, s));
-        }
-        const int* d_self = io.h_self ? (const int*)ctx->self_node.p : (io.d_self ? io.d_self + base : nullptr);
+    SelectArgs sa{};
+    sa.n_units = n_units;
+    sa.ldk = ldk;
+    sa.keys_nuc = (const uint32_t*)ctx->keys.p;
+    sa.keys_f64 = (const double*)ctx->keys.p;
+    sa.goff = (const int*)ctx->goff.p;
+    sa.gmem = (const int*)ctx->gmem.p;
+    sa.ref_node = (const int*)ctx->ref_node.p;
+    sa.refs_nuc = (const uint32_t*)ctx->refs_rm.p;
+    sa.W = ctx->W;
+    sa.refs_aa = (const uint8_t*)ctx->refs_rm.p;
+    sa.Lp = ctx->Lp;
+    sa.L = ctx->L;
+    sa.col_node = (const int*)ctx->col_node.p;
+    sa.self_node = d_self;
+    sa.thr = prm->filt_threshold;
+    sa.baseobs = prm->base_observation_threshold;
+    sa.overlap = prm->overlap_frac;
+    sa.gate = gate;
+    sa.K = (int*)ctx->Kd.p;
+    sa.V = (int*)ctx->Vd.p;
+    sa.status = (int*)ctx->statusd.p;
+    sa.zero_edge = (int*)ctx->zero_edge.p;
+    sa.tree = tree_dev(ctx);
 
-        // ---------------- representative distances ----------------
+    // distances + selection of the `nb` queries whose packed rows / matrix rows are at d_q / ctx->keys
+    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a) -> int {
+        const int nb_pad = round_up(nb, DT_TQ);
         if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
@@ -318,207 +331,218 @@ int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_param
             ctx->n_pairs += (double)nb * ctx->n_rep;
         }
         CK(cudaGetLastError());
-
-        // ---------------- selection ----------------
-        SelectArgs sa{};
-        sa.n = nb;
-        sa.qlist = nullptr;
-        sa.n_units = n_units;
-        sa.ldk = ldk;
-        sa.keys_nuc = (const uint32_t*)ctx->keys.p;
-        sa.keys_f64 = matrix ? d_rows : (const double*)ctx->keys.p;
-        sa.goff = (const int*)ctx->goff.p;
-        sa.gmem = (const int*)ctx->gmem.p;
-        sa.ref_node = (const int*)ctx->ref_node.p;
-        sa.refs_nuc = (const uint32_t*)ctx->refs_rm.p;
-        sa.q_nuc = (const uint32_t*)d_q;
-        sa.W = ctx->W;
-        sa.refs_aa = (const uint8_t*)ctx->refs_rm.p;
-        sa.q_aa = (const uint8_t*)d_q;
-        sa.Lp = ctx->Lp;
-        sa.L = ctx->L;
-        sa.col_node = (const int*)ctx->col_node.p;
-        sa.self_node = d_self;
-        sa.thr = prm->filt_threshold;
-        sa.baseobs = prm->base_observation_threshold;
-        sa.overlap = prm->overlap_frac;
-        sa.gate = gate;
-        sa.cap = cap;
-        sa.obs_node = (int*)ctx->obs_node.p;
-        sa.obs_dist = (double*)ctx->obs_dist.p;
-        sa.K = (int*)ctx->Kd.p;
-        sa.V = (int*)ctx->Vd.p;
-        sa.status = (int*)ctx->statusd.p;
-        sa.zero_edge = (int*)ctx->zero_edge.p;
-        sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
-        sa.tree = tree_dev(ctx);
+        a.n = nb;
+        a.q_nuc = (const uint32_t*)d_q;
+        a.q_aa = (const uint8_t*)d_q;
         {
             Span sp(ctx, T_SELECT);
-            launch_select(sel_kind, sa, s);
+            launch_select(sel_kind, a, s);
             ctx->n_launch += 1;
         }
         CK(cudaGetLastError());
-        {
-            Span sp(ctx, T_D2H);
-            CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-        }
-        CK(cudaStreamSynchronize(s));
+        return 0;
+    };
 
-        // ---------------- overflow reruns: queries whose observed set exceeds the slot capacity ----------------
-        int n_over = 0, maxK = 0;
-        for (int i = 0; i < nb; ++i)
-            if (hS[i] == ST_OVERFLOW) {
-                h_qlist[n_over++] = i;
-                maxK = std::max(maxK, hK[i]);
+    // ---------------- phase 1 ----------------
+    sa.out_map = nullptr;
+    sa.cap = cap;
+    sa.obs_node = (int*)ctx->obs_node.p;
+    sa.obs_dist = (double*)ctx->obs_dist.p;
+    sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
+    for (int sb0 = 0; sb0 < n; sb0 += QB) {
+        const int nb = std::min(QB, n - sb0);
+        const void* d_q = nullptr;
+        {
+            Span sp(ctx, T_H2D);
+            if (matrix) {
+                CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)(base0 + sb0) * ctx->n_cols, (size_t)nb * qrow,
+                                   cudaMemcpyHostToDevice, s));
+            } else if (io.h_queries) {
+                CK(cudaMemcpyAsync(ctx->q_rm.p, (const char*)io.h_queries + (size_t)(base0 + sb0) * qrow, (size_t)nb * qrow,
+                                   cudaMemcpyHostToDevice, s));
+                d_q = ctx->q_rm.p;
+            } else {
+                d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
             }
-        int cap2 = 0;
-        if (n_over) {
-            cap2 = next_pow2(maxK);
-            if (ensure(ctx, ctx->obs_node2, (size_t)n_over * cap2 * 4)) return -1;
-            if (ensure(ctx, ctx->obs_dist2, (size_t)n_over * cap2 * 8)) return -1;
-            CK(cudaMemcpyAsync(ctx->qlist.p, h_qlist.data(), (size_t)n_over * 4, cudaMemcpyHostToDevice, s));
-            SelectArgs sb = sa;
-            sb.n = n_over;
-            sb.qlist = (const int*)ctx->qlist.p;
-            sb.cap = cap2;
-            sb.obs_node = (int*)ctx->obs_node2.p;
-            sb.obs_dist = (double*)ctx->obs_dist2.p;
-            sb.pair_counter = nullptr;
+        }
+        sa.q_begin = sb0;
+        if (distances_and_select(d_q, nb, sa)) return -1;
+    }
+
+    // ---------------- phase 2 ----------------
+    auto fetch_counts = [&]() -> int {
+        Span sp(ctx, T_D2H);
+        CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    if (fetch_counts()) return -1;
+    CK(cudaStreamSynchronize(s));
+
+    PlaceArgs pa{};
+    pa.K = (const int*)ctx->Kd.p;
+    pa.status = (const int*)ctx->statusd.p;
+    pa.zero_edge = (const int*)ctx->zero_edge.p;
+    pa.criterion = prm->criterion;
+    pa.negative_branch = prm->negative_branch;
+    pa.tree = tree_dev(ctx);
+    pa.out_edge = (int*)ctx->o_edge.p;
+    pa.out_error = (double*)ctx->o_err.p;
+    pa.out_distal = (double*)ctx->o_distal.p;
+    pa.out_pendant = (double*)ctx->o_pendant.p;
+    pa.out_status = (int*)ctx->o_status.p;
+    pa.dbg_query = dbg ? 0 : -1;
+    pa.dbg_x1 = dbg ? (double*)ctx->dbg_x1.p : nullptr;
+    pa.dbg_x2 = (double*)ctx->dbg_x2.p;
+    pa.dbg_err = (double*)ctx->dbg_err.p;
+    pa.dbg_valid = (unsigned char*)ctx->dbg_valid.p;
+
+    // placement of `cnt` launch entries (entry i -> query id(i)); chunks bounded by the scratch pool
+    auto place_entries = [&](int cnt, auto id, auto active, const int* d_qlist, int capx, const int* on, const double* od) -> int {
+        int i0 = 0;
+        while (i0 < cnt) {
+            long long recs = 0, stk = 0;
+            int i1 = i0;
+            while (i1 < cnt) {
+                const int qi = id(i1);
+                const bool act = hS[qi] == ST_PLACE && active(qi);
+                const long long v = act ? hV[qi] : 0, k = act ? hK[qi] : 0;
+                if (i1 > i0 && (size_t)(recs + v) * sizeof(NodeRec) > ctx->scratch_limit) break;
+                // -1: observed set lives in the other pass's buffers (the kernel skips the entry)
+                h_rec_off[i1] = (hS[qi] == ST_PLACE && !act) ? -1 : recs;
+                h_stack_off[i1] = stk;
+                recs += v;
+                stk += k;
+                ++i1;
+            }
+            if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * sizeof(NodeRec))) return -1;
+            if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * sizeof(StackEnt))) return -1;
+            CK(cudaMemcpyAsync((long long*)ctx->rec_off.p + i0, h_rec_off.data() + i0, (size_t)(i1 - i0) * 8,
+                               cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync((long long*)ctx->stack_off.p + i0, h_stack_off.data() + i0, (size_t)(i1 - i0) * 8,
+                               cudaMemcpyHostToDevice, s));
+            pa.n = i1 - i0;
+            pa.rec_off = (const long long*)ctx->rec_off.p + i0;
+            pa.stack_off = (const long long*)ctx->stack_off.p + i0;
+            pa.recs = (NodeRec*)ctx->recs.p;
+            pa.stacks = (StackEnt*)ctx->stacks.p;
+            pa.cap = capx;
+            if (d_qlist) {
+                pa.qlist = d_qlist + i0;
+                pa.q_begin = 0;
+                pa.obs_node = on + (size_t)i0 * capx;
+                pa.obs_dist = od + (size_t)i0 * capx;
+            } else {
+                pa.qlist = nullptr;
+                pa.q_begin = i0;
+                pa.obs_node = on;
+                pa.obs_dist = od;
+            }
             {
-                Span sp(ctx, T_SELECT);
-                launch_select(sel_kind, sb, s);
+                Span sp(ctx, T_PLACE);
+                launch_place(prm->method, pa, s);
                 ctx->n_launch += 1;
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, s));
+            i0 = i1;
+            if (i0 < cnt) CK(cudaStreamSynchronize(s));  // the scratch pool is reused by the next chunk
+        }
+        return 0;
+    };
+
+    // ---------------- overflow reruns: observed set larger than the slot capacity (rare) ----------------
+    std::vector<int> over;
+    for (int i = 0; i < n; ++i)
+        if (hS[i] == ST_OVERFLOW) over.push_back(i);
+    std::vector<char> is_over(n, 0);
+    for (int g : over) is_over[g] = 1;
+    for (size_t o0 = 0; o0 < over.size(); o0 += QB) {
+        const int ng = (int)std::min<size_t>(QB, over.size() - o0);
+        int maxK = 0;
+        for (int j = 0; j < ng; ++j) maxK = std::max(maxK, hK[over[o0 + j]]);
+        const int cap2 = next_pow2(maxK);
+        if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
+        if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
+        if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
+        CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
+        for (int j = 0; j < ng; ++j) {  // gather the rows of the overflowing queries
+            const size_t g = (size_t)base0 + over[o0 + j];
+            if (matrix)
+                CK(cudaMemcpyAsync((char*)ctx->keys.p + (size_t)j * qrow, io.h_rows + g * ctx->n_cols, qrow, cudaMemcpyHostToDevice, s));
+            else if (io.h_queries)
+                CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.h_queries + g * qrow, qrow, cudaMemcpyHostToDevice, s));
+            else
+                CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.d_queries + g * qrow, qrow, cudaMemcpyDeviceToDevice, s));
+        }
+        SelectArgs sb = sa;
+        sb.out_map = (const int*)ctx->qlist.p;
+        sb.q_begin = 0;
+        sb.cap = cap2;
+        sb.obs_node = (int*)ctx->obs_node2.p;
+        sb.obs_dist = (double*)ctx->obs_dist2.p;
+        sb.pair_counter = nullptr;
+        if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
+        if (fetch_counts()) return -1;
+        CK(cudaStreamSynchronize(s));
+        if (io.obs_count) {
+            std::vector<int> un((size_t)ng * cap2);
+            std::vector<double> ud((size_t)ng * cap2);
+            CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
+            for (int j = 0; j < ng; ++j) {
+                const int i = over[o0 + j];
+                const int k = std::min(hK[i], io.obs_cap);
+                memcpy(io.obs_node + (size_t)(base0 + i) * io.obs_cap, &un[(size_t)j * cap2], (size_t)k * 4);
+                memcpy(io.obs_dist + (size_t)(base0 + i) * io.obs_cap, &ud[(size_t)j * cap2], (size_t)k * 8);
+            }
+        }
+        if (!io.stop_after_select) {
+            const int* ov = over.data() + o0;
+            if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, (const int*)ctx->qlist.p, cap2,
+                              (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p))
+                return -1;
             CK(cudaStreamSynchronize(s));
         }
-        std::vector<char> is_over(nb, 0);
-        for (int i = 0; i < n_over; ++i) is_over[h_qlist[i]] = 1;
+    }
 
-        // ---------------- parity export of the observed sets ----------------
-        if (io.obs_count) {
-            for (int i = 0; i < nb; ++i) io.obs_count[base + i] = hK[i];
-            const int ocap = io.obs_cap;
-            std::vector<int> tn((size_t)nb * cap);
-            std::vector<double> td((size_t)nb * cap);
-            CK(cudaMemcpy(tn.data(), ctx->obs_node.p, tn.size() * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(td.data(), ctx->obs_dist.p, td.size() * 8, cudaMemcpyDeviceToHost));
-            for (int i = 0; i < nb; ++i) {
-                if (is_over[i]) continue;
-                const int k = std::min(std::min(hK[i], cap), ocap);
-                memcpy(io.obs_node + (size_t)(base + i) * ocap, &tn[(size_t)i * cap], (size_t)k * 4);
-                memcpy(io.obs_dist + (size_t)(base + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
-            }
-            if (n_over) {
-                std::vector<int> un((size_t)n_over * cap2);
-                std::vector<double> ud((size_t)n_over * cap2);
-                CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
-                for (int j = 0; j < n_over; ++j) {
-                    const int i = h_qlist[j];
-                    const int k = std::min(hK[i], ocap);
-                    memcpy(io.obs_node + (size_t)(base + i) * ocap, &un[(size_t)j * cap2], (size_t)k * 4);
-                    memcpy(io.obs_dist + (size_t)(base + i) * ocap, &ud[(size_t)j * cap2], (size_t)k * 8);
-                }
-            }
+    // ---------------- parity export of the observed sets ----------------
+    if (io.obs_count) {
+        const int ocap = io.obs_cap;
+        std::vector<int> tn((size_t)n * cap);
+        std::vector<double> td((size_t)n * cap);
+        CK(cudaMemcpy(tn.data(), ctx->obs_node.p, tn.size() * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(td.data(), ctx->obs_dist.p, td.size() * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) {
+            io.obs_count[base0 + i] = hK[i];
+            if (is_over[i]) continue;
+            const int k = std::min(std::min(hK[i], cap), ocap);
+            memcpy(io.obs_node + (size_t)(base0 + i) * ocap, &tn[(size_t)i * cap], (size_t)k * 4);
+            memcpy(io.obs_dist + (size_t)(base0 + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
         }
-        for (int i = 0; i < nb; ++i)
-            if (hS[i] == ST_PLACE) {
-                ctx->n_obs += hK[i];
-                ctx->n_valid += hV[i];
-            }
-        if (io.stop_after_select) continue;
-
-        // ---------------- placement: plan scratch, launch in chunks ----------------
-        PlaceArgs pa{};
-        pa.K = (const int*)ctx->Kd.p;
-        pa.status = (const int*)ctx->statusd.p;
-        pa.zero_edge = (const int*)ctx->zero_edge.p;
-        pa.criterion = prm->criterion;
-        pa.negative_branch = prm->negative_branch;
-        pa.tree = tree_dev(ctx);
-        pa.out_edge = (int*)ctx->o_edge.p;
-        pa.out_error = (double*)ctx->o_err.p;
-        pa.out_distal = (double*)ctx->o_distal.p;
-        pa.out_pendant = (double*)ctx->o_pendant.p;
-        pa.out_status = (int*)ctx->o_status.p;
-        pa.dbg_query = dbg ? 0 : -1;
-        pa.dbg_x1 = dbg ? (double*)ctx->dbg_x1.p : nullptr;
-        pa.dbg_x2 = (double*)ctx->dbg_x2.p;
-        pa.dbg_err = (double*)ctx->dbg_err.p;
-        pa.dbg_valid = (unsigned char*)ctx->dbg_valid.p;
-
-        // pass A: the regular slots (identity mapping), chunked by scratch size; pass B: the overflow reruns
-        for (int pass = 0; pass < 2; ++pass) {
-            const int n_items = pass == 0 ? nb : n_over;
-            int i0 = 0;
-            while (i0 < n_items) {
-                long long recs = 0, stk = 0;
-                int i1 = i0;
-                while (i1 < n_items) {
-                    const int qi = pass == 0 ? i1 : h_qlist[i1];
-                    long long v = 0, k = 0;
-                    const bool active = hS[qi] == ST_PLACE && (pass == 1 || !is_over[qi]);
-                    if (active) { v = hV[qi]; k = hK[qi]; }
-                    if (i1 > i0 && (size_t)(recs + v) * sizeof(NodeRec) > ctx->scratch_limit) break;
-                    // -1: a query whose observed set lives in the other pass's buffers (kernel skips it)
-                    h_rec_off[i1 - i0] = (hS[qi] == ST_PLACE && !active) ? -1 : recs;
-                    h_stack_off[i1 - i0] = stk;
-                    recs += v;
-                    stk += k;
-                    ++i1;
-                }
-                if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * sizeof(NodeRec))) return -1;
-                if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * sizeof(StackEnt))) return -1;
-                CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, s));
-                CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0) * 8, cudaMemcpyHostToDevice, s));
-                pa.n = i1 - i0;
-                pa.rec_off = (const long long*)ctx->rec_off.p;
-                pa.stack_off = (const long long*)ctx->stack_off.p;
-                pa.recs = (NodeRec*)ctx->recs.p;
-                pa.stacks = (StackEnt*)ctx->stacks.p;
-                if (pass == 0) {
-                    pa.qlist = nullptr;
-                    pa.q_begin = i0;
-                    pa.cap = cap;
-                    pa.obs_node = (const int*)ctx->obs_node.p;
-                    pa.obs_dist = (const double*)ctx->obs_dist.p;
-                } else {
-                    pa.qlist = (const int*)ctx->qlist.p + i0;
-                    pa.q_begin = 0;
-                    pa.cap = cap2;
-                    pa.obs_node = (const int*)ctx->obs_node2.p + (size_t)i0 * cap2;
-                    pa.obs_dist = (const double*)ctx->obs_dist2.p + (size_t)i0 * cap2;
-                }
-                {
-                    Span sp(ctx, T_PLACE);
-                    launch_place(prm->method, pa, s);
-                    ctx->n_launch += 1;
-                }
-                CK(cudaGetLastError());
-                // the offsets live in host vectors that the next chunk overwrites
-                CK(cudaStreamSynchronize(s));
-                i0 = i1;
-            }
+    }
+    for (int i = 0; i < n; ++i)
+        if (hS[i] == ST_PLACE) {
+            ctx->n_obs += hK[i];
+            ctx->n_valid += hV[i];
         }
-
-        // ---------------- outputs ----------------
+    if (!io.stop_after_select) {
+        // ---------------- phase 3 ----------------
+        if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, nullptr, cap,
+                          (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p))
+            return -1;
+        // ---------------- phase 4 ----------------
         {
             Span sp(ctx, T_D2H);
             const cudaMemcpyKind kd = io.out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-            CK(cudaMemcpyAsync(io.edge + base, ctx->o_edge.p, (size_t)nb * 4, kd, s));
-            CK(cudaMemcpyAsync(io.error + base, ctx->o_err.p, (size_t)nb * 8, kd, s));
-            CK(cudaMemcpyAsync(io.distal + base, ctx->o_distal.p, (size_t)nb * 8, kd, s));
-            CK(cudaMemcpyAsync(io.pendant + base, ctx->o_pendant.p, (size_t)nb * 8, kd, s));
-            CK(cudaMemcpyAsync(io.status + base, ctx->o_status.p, (size_t)nb * 4, kd, s));
+            CK(cudaMemcpyAsync(io.edge + base0, ctx->o_edge.p, (size_t)n * 4, kd, s));
+            CK(cudaMemcpyAsync(io.error + base0, ctx->o_err.p, (size_t)n * 8, kd, s));
+            CK(cudaMemcpyAsync(io.distal + base0, ctx->o_distal.p, (size_t)n * 8, kd, s));
+            CK(cudaMemcpyAsync(io.pendant + base0, ctx->o_pendant.p, (size_t)n * 8, kd, s));
+            CK(cudaMemcpyAsync(io.status + base0, ctx->o_status.p, (size_t)n * 4, kd, s));
         }
-        CK(cudaStreamSynchronize(s));
     }
+    CK(cudaStreamSynchronize(s));
     if (dbg) {
         CK(cudaMemcpy(io.dbg_x1, ctx->dbg_x1.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(io.dbg_x2, ctx->dbg_x2.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
@@ -531,6 +555,22 @@ int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_param
         ctx->n_pairs += (double)pc;
     }
     collect_spans(ctx);
+    return 0;
+}
+
+// the whole pipeline for nq queries
+int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_params* prm) {
+    if (check_params(ctx, prm)) return -1;
+    if (ctx->M <= 0) return fail(ctx, "apples_set_tree has not been called");
+    const bool matrix = io.h_rows != nullptr;
+    if (matrix && ctx->n_cols <= 0) return fail(ctx, "apples_set_matrix_columns has not been called");
+    if (!matrix && ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
+    if (nq <= 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    for (int64_t b0 = 0; b0 < nq; b0 += ctx->max_batch) {
+        const int n = (int)std::min<int64_t>(ctx->max_batch, nq - b0);
+        if (run_macro(ctx, b0, n, io, prm)) return -1;
+    }
     return 0;
 }
 

@@ -65,8 +65,10 @@ __device__ __forceinline__ double scoredist_from_sum(double tot, uint32_t v, int
 enum { SEL_NUC = 0, SEL_AA = 1, SEL_MATRIX = 2 };
 
 struct SelectArgs {
-    int n;                 // queries in this launch
-    const int* qlist;      // optional: slot -> query index inside the sub-batch (NULL = identity)
+    int n;                 // queries in this launch; their key / query rows are rows 0..n-1 of keys_* / q_*
+    const int* out_map;    // optional: row -> query index inside the batch (NULL: q_begin + row).  With a map the
+                           // observed lists go to row `row` of obs_*, otherwise to row `query index`
+    int q_begin;
     int n_units;           // representatives (alignment) or matrix columns
     int64_t ldk;           // row stride of the key matrix
     const uint32_t* keys_nuc;  // [nq][ldk] packed (mismatch | valid << 16)
@@ -75,14 +77,14 @@ struct SelectArgs {
     const int* gmem;
     const int* ref_node;
     const uint32_t* refs_nuc;  // row-major [n_ref][3][W]
-    const uint32_t* q_nuc;     // row-major [nq][3][W]
+    const uint32_t* q_nuc;     // row-major [n][3][W]
     int W;
     const uint8_t* refs_aa;    // [n_ref][Lp]
-    const uint8_t* q_aa;       // [nq][Lp]
+    const uint8_t* q_aa;       // [n][Lp]
     int Lp;
     int L;
     const int* col_node;
-    const int* self_node;  // [nq] or NULL
+    const int* self_node;  // [batch] or NULL
     double thr;
     int baseobs;
     double overlap;

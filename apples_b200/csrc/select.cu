@@ -236,10 +236,11 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
 template <int KIND>
 __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     if (slot >= a.n) return;
-    const int q = a.qlist ? a.qlist[slot] : slot;
-    const int self = a.self_node ? a.self_node[q] : -1;
+    const int gid = a.out_map ? a.out_map[slot] : a.q_begin + slot;       // query index inside the batch
+    const int oslot = a.out_map ? slot : gid;                             // row of the observed-list buffers
+    const int self = a.self_node ? a.self_node[gid] : -1;
 
     WarpSel<KIND> st;
     st.obs_num = 0;
@@ -256,51 +257,61 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
     bool have_last = false;
     bool first_round = true;
     bool done = false;
+    constexpr int U = 8;  // independent key loads in flight per lane (the scan is latency-bound otherwise)
 
     while (!done) {
         int cnt = 0;
-        for (int u0 = 0; u0 < a.n_units; u0 += 32) {
-            const int u = u0 + lane;
-            Key<KIND> k;
-            int cls = 0;
-            if (u < a.n_units) cls = load_key(a, q, u, k);
+        for (int u0 = 0; u0 < a.n_units; u0 += 32 * U) {
+            Key<KIND> k[U];
+            int cls[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int u = u0 + j * 32 + lane;
+                cls[j] = 0;
+                if (u < a.n_units) cls[j] = load_key(a, slot, u, k[j]);
+            }
             if (first_round) {
-                unsigned near = __ballot_sync(FULLMASK, cls == 1);
-                while (near) {
-                    const int src = __ffs(near) - 1;
-                    near &= near - 1;
-                    const Key<KIND> uk = key_shfl(k, src);
-                    expand_unit<KIND>(a, st, slot, q, self, uk, lane);
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    unsigned near = __ballot_sync(FULLMASK, cls[j] == 1);
+                    while (near) {
+                        const int src = __ffs(near) - 1;
+                        near &= near - 1;
+                        const Key<KIND> uk = key_shfl(k[j], src);
+                        expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
+                    }
                 }
             }
-            bool cand = cls == 2;
-            if (cand && have_last) cand = key_less(last, k);
-            if (cnt == 32) {  // quick reject against the current 32nd smallest (held by lane 31)
-                const Key<KIND> k31 = key_shfl(mine, 31);
-                if (cand) cand = key_less(k, k31);
-            }
-            unsigned far = __ballot_sync(FULLMASK, cand);
-            while (far) {
-                const int src = __ffs(far) - 1;
-                far &= far - 1;
-                const Key<KIND> ck = key_shfl(k, src);
-                // position = number of live entries smaller than the candidate
-                const bool smaller = lane < cnt && key_less(mine, ck);
-                const int pos = __popc(__ballot_sync(FULLMASK, smaller));
-                if (pos >= 32) continue;
-                const Key<KIND> up = key_shfl_up(mine);
-                if (lane > pos) mine = up;
-                if (lane == pos) mine = ck;
-                if (cnt < 32) cnt++;
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                bool cand = cls[j] == 2;
+                if (cand && have_last) cand = key_less(last, k[j]);
+                if (cnt == 32) {  // quick reject against the current 32nd smallest (held by lane 31)
+                    const Key<KIND> k31 = key_shfl(mine, 31);
+                    if (cand) cand = key_less(k[j], k31);
+                }
+                unsigned far = __ballot_sync(FULLMASK, cand);
+                while (far) {
+                    const int src = __ffs(far) - 1;
+                    far &= far - 1;
+                    const Key<KIND> ck = key_shfl(k[j], src);
+                    // position = number of live entries smaller than the candidate
+                    const bool smaller = lane < cnt && key_less(mine, ck);
+                    const int pos = __popc(__ballot_sync(FULLMASK, smaller));
+                    if (pos >= 32) continue;
+                    const Key<KIND> up = key_shfl_up(mine);
+                    if (lane > pos) mine = up;
+                    if (lane == pos) mine = ck;
+                    if (cnt < 32) cnt++;
+                }
             }
         }
         first_round = false;
         // walk the far list in ascending order while obs_num < baseobs (Reference.py:146)
-        int j = 0;
-        for (; j < cnt; ++j) {
+        for (int j = 0; j < cnt; ++j) {
             if (st.obs_num >= a.baseobs) break;
             const Key<KIND> uk = key_shfl(mine, j);
-            expand_unit<KIND>(a, st, slot, q, self, uk, lane);
+            expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
         }
         if (st.obs_num >= a.baseobs || cnt < 32) {
             done = true;
@@ -320,8 +331,8 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
     } else if (st.kcount > a.cap) {
         status = ST_OVERFLOW;
     } else {
-        int* node = a.obs_node + (size_t)slot * a.cap;
-        double* dist = a.obs_dist + (size_t)slot * a.cap;
+        int* node = a.obs_node + (size_t)oslot * a.cap;
+        double* dist = a.obs_dist + (size_t)oslot * a.cap;
         const int K = st.kcount;
         int n2 = 1;
         while (n2 < K) n2 <<= 1;
@@ -354,10 +365,10 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
         V = c;
     }
     if (lane == 0) {
-        a.K[q] = st.kcount;
-        a.V[q] = V;
-        a.status[q] = status;
-        a.zero_edge[q] = st.znode;
+        a.K[gid] = st.kcount;
+        a.V[gid] = V;
+        a.status[gid] = status;
+        a.zero_edge[gid] = st.znode;
     }
 }
 
