@@ -57,7 +57,7 @@ struct apples_ctx {
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> ev_pool;
     double t_ms[T_NSTAGE] = {0, 0, 0, 0, 0, 0};
-    double n_launch = 0, n_dense_launch = 0, n_pairs = 0, n_obs = 0, n_valid = 0;
+    double n_launch = 0, n_dense_launch = 0, n_pairs = 0, n_obs = 0, n_valid = 0, n_over = 0, max_K = 0, max_V = 0;
     size_t scratch_limit = (size_t)6 << 30;  // placement scratch pool upper bound (bytes)
     int64_t max_subbatch = 65536;
     int64_t max_batch = 1 << 20;  // queries per macro-batch (batch-wide observed-list buffers)
@@ -162,15 +162,19 @@ NucGate make_gate(int L, double thr, double overlap) {
     g.L = L;
     g.vmin = overlap_vmin(L, overlap);
     g.thr = thr;
-    // dist <= thr  <=>  p <= p*, p* = 0.75 (1 - exp(-4 thr / 3)); +-1e-9 relative guard band, exact evaluation inside it
-    double pstar = 0.75 * (1.0 - std::exp(-4.0 * thr / 3.0));
-    if (!(thr >= 0.0)) pstar = -1.0;
-    g.p_lo = pstar > 0 ? pstar * (1.0 - 1e-9) : -1.0;
-    g.p_hi = pstar > 0 ? pstar * (1.0 + 1e-9) : 0.0;
-    if (pstar >= 0.75 * (1.0 - 1e-9)) {  // threshold so large that every valid pair is near
-        g.p_lo = 2.0;
-        g.p_hi = 3.0;
+    // dist <= thr  <=>  p <= p*, p* = 0.75 (1 - exp(-4 thr / 3)).  Fixed-point (16.16) guard band around p*: below
+    // P_lo certainly near, above P_hi certainly far, in between the kernel evaluates the fp64 distance itself.
+    if (!(thr >= 0.0)) {          // nothing is near (a zero distance still is not <= a negative threshold)
+        g.P_lo = 0;
+        g.P_hi = 0;               // lhs >= 0 always: everything valid is far
+        return g;
     }
+    const double pstar = 0.75 * (1.0 - std::exp(-4.0 * thr / 3.0));
+    const double lo = std::floor(pstar * (1.0 - 1e-9) * 65536.0) - 1.0;
+    const double hi = std::ceil(pstar * (1.0 + 1e-9) * 65536.0) + 1.0;
+    g.P_lo = (uint32_t)std::max(0.0, std::min(lo, 49152.0));
+    g.P_hi = (uint32_t)std::max(1.0, std::min(hi, 49153.0));
+    if (g.P_lo >= 49151u) g.P_lo = 49152u;  // threshold so large that every valid pair (4 m < 3 v) is near
     return g;
 }
 
@@ -521,10 +525,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             memcpy(io.obs_dist + (size_t)(base0 + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
         }
     }
+    ctx->n_over += (double)over.size();
     for (int i = 0; i < n; ++i)
         if (hS[i] == ST_PLACE) {
             ctx->n_obs += hK[i];
             ctx->n_valid += hV[i];
+            ctx->max_K = std::max(ctx->max_K, (double)hK[i]);
+            ctx->max_V = std::max(ctx->max_V, (double)hV[i]);
         }
     if (!io.stop_after_select) {
         // ---------------- phase 3 ----------------
@@ -882,12 +889,13 @@ int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const doubl
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
     if (!ctx || !out) return -1;
-    double v[11] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
-                    ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid};
-    for (int i = 0; i < n && i < 11; ++i) out[i] = v[i];
+    double v[14] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+                    ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid,
+                    ctx->n_over, ctx->max_K, ctx->max_V};
+    for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
     if (reset) {
         for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
-        ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = 0;
+        ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = ctx->n_over = ctx->max_K = ctx->max_V = 0;
     }
     return 0;
 }

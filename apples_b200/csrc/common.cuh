@@ -35,8 +35,8 @@ struct TreeDev {
 struct NucGate {
     int L;
     int vmin;     // smallest valid-site count that passes `valid / L < overlap_frac` (distance.py:735)
-    double p_lo;  // mism <= p_lo * valid  =>  certainly dist <= threshold
-    double p_hi;  // mism >= p_hi * valid  =>  certainly dist >  threshold
+    uint32_t P_lo;  // (mism << 16) <= P_lo * valid  =>  certainly dist <= threshold
+    uint32_t P_hi;  // (mism << 16) >= P_hi * valid  =>  certainly dist >  threshold
     double thr;
 };
 

@@ -81,52 +81,94 @@ __device__ __forceinline__ Key<KIND> key_shfl_up(const Key<KIND>& k) {
     return o;
 }
 
-// load + classify one unit.  returns 0 = invalid, 1 = near (dist <= threshold), 2 = far
-__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_NUC>& k) {
-    const uint32_t packed = a.keys_nuc[(size_t)q * a.ldk + u];
-    k.m = packed & 0xffffu;
-    k.v = packed >> 16;
-    k.idx = u;
+// raw key of one unit as stored in the key matrix (kept in registers during the scan; the Key is rebuilt on demand)
+template <int KIND>
+struct RawT {
+    using T = double;
+};
+template <>
+struct RawT<SEL_NUC> {
+    using T = uint32_t;
+};
+__device__ __forceinline__ Key<SEL_NUC> make_key_nuc(uint32_t raw, int idx) {
+    Key<SEL_NUC> k;
+    k.m = raw & 0xffffu;
+    k.v = raw >> 16;
+    k.idx = idx;
+    return k;
+}
+template <int KIND>
+__device__ __forceinline__ Key<KIND> make_key(typename RawT<KIND>::T raw, int idx) {
+    if constexpr (KIND == SEL_NUC) {
+        return make_key_nuc(raw, idx);
+    } else {
+        Key<KIND> k;
+        k.d = raw;
+        k.idx = idx;
+        return k;
+    }
+}
+template <int KIND>
+__device__ __forceinline__ typename RawT<KIND>::T load_raw(const SelectArgs& a, int row, int u) {
+    if constexpr (KIND == SEL_NUC)
+        return a.keys_nuc[(size_t)row * a.ldk + u];
+    else
+        return a.keys_f64[(size_t)row * a.ldk + u];
+}
+
+// classify one unit.  returns 0 = invalid, 1 = near (dist <= threshold), 2 = far
+__device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_NUC>& k) {
     // distance.py:735 (no overlap), :741-743 (1 - 4p/3 <= 0  <=>  4 m >= 3 v)
     if (k.v == 0u || (int)k.v < a.gate.vmin || 4u * k.m >= 3u * k.v) return 0;
-    const double dm = (double)k.m, dv = (double)k.v;
-    if (dm <= a.gate.p_lo * dv) return 1;
-    if (dm >= a.gate.p_hi * dv) return 2;
+    // dist <= threshold  <=>  m / v <= p*: decided in 16.16 fixed point with a guard band (counts <= 65535 and
+    // P < 49154, so every product fits 32 bits); only the sliver inside the band evaluates the fp64 distance
+    const uint32_t lhs = k.m << 16;
+    if (a.gate.P_hi == 0u) return 2;  // negative threshold: nothing is near
+    if (lhs <= a.gate.P_lo * k.v) return 1;
+    if (lhs >= a.gate.P_hi * k.v) return 2;
     return jc69_from_counts(k.m, k.v, a.gate.vmin) <= a.thr ? 1 : 2;
 }
-__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_AA>& k) {
-    k.d = a.keys_f64[(size_t)q * a.ldk + u];
-    k.idx = u;
+__device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_AA>& k) {
     if (!(k.d >= 0.0)) return 0;  // Reference.py:141
     return k.d <= a.thr ? 1 : 2;
 }
-__device__ __forceinline__ int load_key(const SelectArgs& a, int q, int u, Key<SEL_MATRIX>& k) {
-    k.d = a.keys_f64[(size_t)q * a.ldk + u];
-    k.idx = u;
-    if (!(k.d >= 0.0) || a.col_node[u] < 0) return 0;  // PoolQueryWorker.py:52
+__device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_MATRIX>& k) {
+    if (!(k.d >= 0.0) || a.col_node[k.idx] < 0) return 0;  // PoolQueryWorker.py:52
     return k.d <= a.thr ? 1 : 2;
 }
 
 // ---- member distances (warp-cooperative) ----------------------------------------------------------------------
-__device__ __forceinline__ double member_dist_nuc(const SelectArgs& a, const uint32_t* qrow, int ref_row, int lane) {
-    const uint32_t* r = a.refs_nuc + (size_t)ref_row * 3 * a.W;
-    uint32_t acc = 0;
+// packed (mismatch | valid << 16) counts of the query against TWO reference rows at once (independent loads in
+// flight); every lane returns the same totals
+__device__ __forceinline__ void member_counts_nuc2(const SelectArgs& a, const uint32_t* __restrict__ qrow, int row0,
+                                                   int row1, int lane, uint32_t& c0, uint32_t& c1) {
+    const uint32_t* __restrict__ r0 = a.refs_nuc + (size_t)row0 * 3 * a.W;
+    const uint32_t* __restrict__ r1 = a.refs_nuc + (size_t)row1 * 3 * a.W;
+    uint32_t acc0 = 0, acc1 = 0;
     for (int w = 4 * lane; w < a.W; w += 128) {
         const uint4 ql = *reinterpret_cast<const uint4*>(qrow + w);
         const uint4 qh = *reinterpret_cast<const uint4*>(qrow + a.W + w);
         const uint4 qv = *reinterpret_cast<const uint4*>(qrow + 2 * a.W + w);
-        const uint4 rl = *reinterpret_cast<const uint4*>(r + w);
-        const uint4 rh = *reinterpret_cast<const uint4*>(r + a.W + w);
-        const uint4 rv = *reinterpret_cast<const uint4*>(r + 2 * a.W + w);
+        const uint4 al = *reinterpret_cast<const uint4*>(r0 + w);
+        const uint4 ah = *reinterpret_cast<const uint4*>(r0 + a.W + w);
+        const uint4 av = *reinterpret_cast<const uint4*>(r0 + 2 * a.W + w);
+        const uint4 bl = *reinterpret_cast<const uint4*>(r1 + w);
+        const uint4 bh = *reinterpret_cast<const uint4*>(r1 + a.W + w);
+        const uint4 bv = *reinterpret_cast<const uint4*>(r1 + 2 * a.W + w);
         uint32_t v, m;
-        v = qv.x & rv.x; m = ((ql.x ^ rl.x) | (qh.x ^ rh.x)) & v; acc += __popc(m) + (__popc(v) << 16);
-        v = qv.y & rv.y; m = ((ql.y ^ rl.y) | (qh.y ^ rh.y)) & v; acc += __popc(m) + (__popc(v) << 16);
-        v = qv.z & rv.z; m = ((ql.z ^ rl.z) | (qh.z ^ rh.z)) & v; acc += __popc(m) + (__popc(v) << 16);
-        v = qv.w & rv.w; m = ((ql.w ^ rl.w) | (qh.w ^ rh.w)) & v; acc += __popc(m) + (__popc(v) << 16);
+#define APPLES_ACC(acc, L_, H_, V_, c)                                                  \
+        v = qv.c & V_.c; m = ((ql.c ^ L_.c) | (qh.c ^ H_.c)) & v; acc += __popc(m) + (__popc(v) << 16);
+        APPLES_ACC(acc0, al, ah, av, x) APPLES_ACC(acc0, al, ah, av, y) APPLES_ACC(acc0, al, ah, av, z) APPLES_ACC(acc0, al, ah, av, w)
+        APPLES_ACC(acc1, bl, bh, bv, x) APPLES_ACC(acc1, bl, bh, bv, y) APPLES_ACC(acc1, bl, bh, bv, z) APPLES_ACC(acc1, bl, bh, bv, w)
+#undef APPLES_ACC
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
-    return jc69_from_counts(acc & 0xffffu, acc >> 16, a.gate.vmin);
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(FULLMASK, acc0, o);
+        acc1 += __shfl_xor_sync(FULLMASK, acc1, o);
+    }
+    c0 = acc0;
+    c1 = acc1;
 }
 
 __constant__ double c_blosum45_sel[441] = {
@@ -170,11 +212,11 @@ struct WarpSel {
 
 template <int KIND>
 __device__ __forceinline__ void observe(const SelectArgs& a, WarpSel<KIND>& st, int slot, int self, int node, double d,
-                                        const Key<KIND>& ukey, int pos, int lane) {
+                                        bool is_zero, const Key<KIND>& ukey, int pos, int lane) {
     // called by all lanes with identical arguments
     st.obs_num++;
     if (node < 0 || node == self) return;  // own backbone entry is deleted afterwards (PoolQueryWorker.py:63-66)
-    if (d == 0.0) {                          // PoolQueryWorker.py:72-75: first zero in dict order wins
+    if (is_zero) {                           // PoolQueryWorker.py:72-75: first zero in dict order wins
         bool better = !st.has_zero || key_less(ukey, st.zkey) || (!key_less(st.zkey, ukey) && pos < st.zpos);
         if (better) {
             st.has_zero = true;
@@ -190,21 +232,38 @@ __device__ __forceinline__ void observe(const SelectArgs& a, WarpSel<KIND>& st, 
     st.kcount++;
 }
 
+// nucleotide members are stored as their integer counts first (bit pattern in the double slot); the fp64 jc69
+// correction is applied afterwards for all observed leaves in parallel (finish_distances)
+__device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<SEL_NUC>& st, int slot, int self, int row,
+                                                   uint32_t c, const Key<SEL_NUC>& ukey, int pos, int lane) {
+    const uint32_t m = c & 0xffffu, v = c >> 16;
+    if (v == 0u || (int)v < a.gate.vmin || 4u * m >= 3u * v) return;  // distance < 0: not stored (Reference.py:150)
+    observe<SEL_NUC>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
+}
+
 template <int KIND>
 __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& st, int slot, int q, int self,
                                             const Key<KIND>& ukey, int lane) {
     if constexpr (KIND == SEL_MATRIX) {
-        observe<KIND>(a, st, slot, self, a.col_node[ukey.idx], ukey.d, ukey, 0, lane);
+        observe<KIND>(a, st, slot, self, a.col_node[ukey.idx], ukey.d, ukey.d == 0.0, ukey, 0, lane);
     } else {
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
-        for (int x = b; x < e; ++x) {
-            const int row = a.gmem[x];
-            double d;
-            if constexpr (KIND == SEL_NUC)
-                d = member_dist_nuc(a, a.q_nuc + (size_t)q * 3 * a.W, row, lane);
-            else
-                d = member_dist_aa(a, a.q_aa + (size_t)q * a.Lp, row, lane);
-            if (!(d < 0.0)) observe<KIND>(a, st, slot, self, a.ref_node[row], d, ukey, x - b, lane);  // Reference.py:150
+        if constexpr (KIND == SEL_NUC) {
+            const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
+            for (int x = b; x < e; x += 2) {
+                const int row0 = a.gmem[x];
+                const int row1 = (x + 1 < e) ? a.gmem[x + 1] : row0;
+                uint32_t c0, c1;
+                member_counts_nuc2(a, qrow, row0, row1, lane, c0, c1);
+                observe_nuc_counts(a, st, slot, self, row0, c0, ukey, x - b, lane);
+                if (x + 1 < e) observe_nuc_counts(a, st, slot, self, row1, c1, ukey, x + 1 - b, lane);
+            }
+        } else {
+            for (int x = b; x < e; ++x) {
+                const int row = a.gmem[x];
+                const double d = member_dist_aa(a, a.q_aa + (size_t)q * a.Lp, row, lane);
+                if (!(d < 0.0)) observe<KIND>(a, st, slot, self, a.ref_node[row], d, d == 0.0, ukey, x - b, lane);  // Reference.py:150
+            }
         }
         if (lane == 0 && a.pair_counter) atomicAdd(a.pair_counter, (unsigned long long)(e - b));
     }
@@ -234,7 +293,7 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     if (slot >= a.n) return;
@@ -259,25 +318,52 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
     bool done = false;
     constexpr int U = 8;  // independent key loads in flight per lane (the scan is latency-bound otherwise)
 
+    Key<KIND> k31;  // copy of the list's largest entry once the list is full
+    k31.idx = -1;
     while (!done) {
         int cnt = 0;
         for (int u0 = 0; u0 < a.n_units; u0 += 32 * U) {
-            Key<KIND> k[U];
+            typename RawT<KIND>::T raw[U];
             int cls[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 const int u = u0 + j * 32 + lane;
-                cls[j] = 0;
-                if (u < a.n_units) cls[j] = load_key(a, slot, u, k[j]);
+                raw[j] = 0;
+                if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int u = u0 + j * 32 + lane;
+                cls[j] = (u < a.n_units) ? classify(a, make_key<KIND>(raw[j], u)) : 0;
             }
             if (first_round) {
+                // near units: queued (lane t holds the t-th pending key) and expanded from ONE loop so that the
+                // member-distance code is instantiated once
+                unsigned nearm[U];
+                bool any = false;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    unsigned near = __ballot_sync(FULLMASK, cls[j] == 1);
-                    while (near) {
-                        const int src = __ffs(near) - 1;
-                        near &= near - 1;
-                        const Key<KIND> uk = key_shfl(k[j], src);
+                    nearm[j] = __ballot_sync(FULLMASK, cls[j] == 1);
+                    any |= nearm[j] != 0u;
+                }
+                while (any) {
+                    int qn = 0;
+                    Key<KIND> qkey;
+                    qkey.idx = -1;
+                    any = false;
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        while (nearm[j] && qn < 32) {
+                            const int src = __ffs(nearm[j]) - 1;
+                            nearm[j] &= nearm[j] - 1;
+                            const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
+                            if (lane == qn) qkey = uk;
+                            ++qn;
+                        }
+                        any |= nearm[j] != 0u;
+                    }
+                    for (int t = 0; t < qn; ++t) {
+                        const Key<KIND> uk = key_shfl(qkey, t);
                         expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
                     }
                 }
@@ -285,16 +371,14 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
 #pragma unroll
             for (int j = 0; j < U; ++j) {
                 bool cand = cls[j] == 2;
-                if (cand && have_last) cand = key_less(last, k[j]);
-                if (cnt == 32) {  // quick reject against the current 32nd smallest (held by lane 31)
-                    const Key<KIND> k31 = key_shfl(mine, 31);
-                    if (cand) cand = key_less(k[j], k31);
-                }
+                const Key<KIND> kj = make_key<KIND>(raw[j], u0 + j * 32 + lane);
+                if (cand && have_last) cand = key_less(last, kj);
+                if (cand && cnt == 32) cand = key_less(kj, k31);  // quick reject against the 32nd smallest
                 unsigned far = __ballot_sync(FULLMASK, cand);
                 while (far) {
                     const int src = __ffs(far) - 1;
                     far &= far - 1;
-                    const Key<KIND> ck = key_shfl(k[j], src);
+                    const Key<KIND> ck = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
                     // position = number of live entries smaller than the candidate
                     const bool smaller = lane < cnt && key_less(mine, ck);
                     const int pos = __popc(__ballot_sync(FULLMASK, smaller));
@@ -303,6 +387,7 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
                     if (lane > pos) mine = up;
                     if (lane == pos) mine = ck;
                     if (cnt < 32) cnt++;
+                    if (cnt == 32) k31 = key_shfl(mine, 31);
                 }
             }
         }
@@ -337,6 +422,12 @@ __global__ void __launch_bounds__(128) select_kernel(const SelectArgs a) {
         int n2 = 1;
         while (n2 < K) n2 <<= 1;
         __syncwarp();
+        if constexpr (KIND == SEL_NUC) {  // jc69 correction of the observed leaves, one per lane
+            for (int i = lane; i < K; i += 32) {
+                const uint32_t c = (uint32_t)__double_as_longlong(dist[i]);
+                dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+            }
+        }
         for (int i = K + lane; i < n2; i += 32) {
             node[i] = 0x7fffffff;
             dist[i] = 0.0;

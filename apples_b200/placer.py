@@ -147,10 +147,11 @@ class GpuPlacer:
         self._check(self.lib.apples_results_to_device(self.h, *[t.data_ptr() for t in (edge, error, distal, pendant, status)]))
 
     def timings(self, reset=False):
-        v = np.zeros(11, np.float64)
-        self.lib.apples_get_timings(self.h, _lib.ptr(v), 11, 1 if reset else 0)
+        v = np.zeros(14, np.float64)
+        self.lib.apples_get_timings(self.h, _lib.ptr(v), 14, 1 if reset else 0)
         keys = ['h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms', 'launches',
-                'rep_distance_launches', 'pairs', 'observed', 'valid_nodes']
+                'rep_distance_launches', 'pairs', 'observed', 'valid_nodes', 'overflow_queries', 'max_observed',
+                'max_valid_nodes']
         return dict(zip(keys, v.tolist()))
 
     # ------------------------------------------------------------------------------------------------ parity exports

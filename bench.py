@@ -334,7 +334,8 @@ def main():
             'distance_gcell_sites_per_s': (tm['pairs'] / args.steps) * args.sites / (step_ms * 1e-3) / 1e9 * world,
             'stage_ms_per_step': stages, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
             'observed_per_query': tm['observed'] / (nq * args.steps), 'valid_nodes_per_query': tm['valid_nodes'] / (nq * args.steps),
-            'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'setup': info}
+            'overflow_queries_per_step': tm['overflow_queries'] / args.steps, 'max_observed': tm['max_observed'],
+            'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'setup': info}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----
     if not args.no_cpu_baseline and world == 1:
