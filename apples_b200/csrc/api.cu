@@ -44,7 +44,7 @@ struct apples_ctx {
     int n_cols = 0;
     DevBuf col_node;
     // per-batch work buffers
-    DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, Kd, Vd, statusd, zero_edge, pair_counter;
+    DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
@@ -248,6 +248,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
     if (ensure(ctx, ctx->obs_dist, (size_t)n * cap * 8)) return -1;
+    if (ensure(ctx, ctx->obs_len, (size_t)n * cap * 4)) return -1;
     if (ensure(ctx, ctx->Kd, (size_t)n * 4) || ensure(ctx, ctx->Vd, (size_t)n * 4) ||
         ensure(ctx, ctx->statusd, (size_t)n * 4) || ensure(ctx, ctx->zero_edge, (size_t)n * 4))
         return -1;
@@ -352,6 +353,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.cap = cap;
     sa.obs_node = (int*)ctx->obs_node.p;
     sa.obs_dist = (double*)ctx->obs_dist.p;
+    sa.obs_len = (int*)ctx->obs_len.p;
     sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
     for (int sb0 = 0; sb0 < n; sb0 += QB) {
         const int nb = std::min(QB, n - sb0);
@@ -403,7 +405,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     pa.dbg_valid = (unsigned char*)ctx->dbg_valid.p;
 
     // placement of `cnt` launch entries (entry i -> query id(i)); chunks bounded by the scratch pool
-    auto place_entries = [&](int cnt, auto id, auto active, const int* d_qlist, int capx, const int* on, const double* od) -> int {
+    auto place_entries = [&](int cnt, auto id, auto active, const int* d_qlist, int capx, const int* on, const double* od,
+                             const int* ol) -> int {
         int i0 = 0;
         while (i0 < cnt) {
             long long recs = 0, stk = 0;
@@ -411,7 +414,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             while (i1 < cnt) {
                 const int qi = id(i1);
                 const bool act = hS[qi] == ST_PLACE && active(qi);
-                const long long v = act ? hV[qi] : 0, k = act ? hK[qi] : 0;
+                const long long v = act ? hV[qi] + 1 : 0, k = act ? hK[qi] : 0;  // + 1: pseudo record of the subtree root
                 if (i1 > i0 && (size_t)(recs + v) * sizeof(NodeRec) > ctx->scratch_limit) break;
                 // -1: observed set lives in the other pass's buffers (the kernel skips the entry)
                 h_rec_off[i1] = (hS[qi] == ST_PLACE && !act) ? -1 : recs;
@@ -437,11 +440,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 pa.q_begin = 0;
                 pa.obs_node = on + (size_t)i0 * capx;
                 pa.obs_dist = od + (size_t)i0 * capx;
+                pa.obs_len = ol + (size_t)i0 * capx;
             } else {
                 pa.qlist = nullptr;
                 pa.q_begin = i0;
                 pa.obs_node = on;
                 pa.obs_dist = od;
+                pa.obs_len = ol;
             }
             {
                 Span sp(ctx, T_PLACE);
@@ -468,6 +473,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         const int cap2 = next_pow2(maxK);
         if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
         if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
+        if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
         if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
         for (int j = 0; j < ng; ++j) {  // gather the rows of the overflowing queries
@@ -485,6 +491,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         sb.cap = cap2;
         sb.obs_node = (int*)ctx->obs_node2.p;
         sb.obs_dist = (double*)ctx->obs_dist2.p;
+        sb.obs_len = (int*)ctx->obs_len2.p;
         sb.pair_counter = nullptr;
         if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
         if (fetch_counts()) return -1;
@@ -504,7 +511,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (!io.stop_after_select) {
             const int* ov = over.data() + o0;
             if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, (const int*)ctx->qlist.p, cap2,
-                              (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p))
+                              (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
                 return -1;
             CK(cudaStreamSynchronize(s));
         }
@@ -536,7 +543,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     if (!io.stop_after_select) {
         // ---------------- phase 3 ----------------
         if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, nullptr, cap,
-                          (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p))
+                          (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p, (const int*)ctx->obs_len.p))
             return -1;
         // ---------------- phase 4 ----------------
         {
@@ -618,7 +625,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
-                     &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->Kd, &ctx->Vd,
+                     &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,

@@ -90,8 +90,9 @@ struct SelectArgs {
     double overlap;
     NucGate gate;
     int cap;               // slot capacity (power of two)
-    int* obs_node;         // [slots][cap]
+    int* obs_node;         // [slots][cap] observed leaves, sorted by node id
     double* obs_dist;      // [slots][cap]
+    int* obs_len;          // [slots][cap] length of the chain each observed leaf owns (placement.cu)
     int* K;                // [nq] observed leaves (may exceed cap)
     int* V;                // [nq] valid nodes of the restricted subtree
     int* status;           // [nq] ST_*
@@ -108,7 +109,8 @@ struct alignas(16) NodeRec {
     int fchild;
     int rsib;
     int nchild;
-    double pad_;
+    int par;   // compact index of the parent (V = the subtree root)
+    int pad_;
 };
 static_assert(sizeof(NodeRec) == 128, "NodeRec must be 128 bytes");
 
@@ -126,6 +128,7 @@ struct PlaceArgs {
     int cap;
     const int* obs_node;
     const double* obs_dist;
+    const int* obs_len;
     const int* K;
     const int* status;
     const int* zero_edge;

@@ -1,24 +1,30 @@
-// Kernel (b): least-squares placement over every edge of the query's restricted backbone, one query per thread.
+// Kernel (b): least-squares placement over every edge of the query's restricted backbone, one WARP per query.
 //
 // Replaces, per query: Subtree (apples/Subtree.py:23-70), Algorithm.dp_frag (apples/Algorithm.py:16-21) with
 // FM/OLS/BME/BE all_S_values + all_R_values (FM.py:6-76, OLS.py:12-80, BME.py:6-60, BE.py:6-57),
 // placement_per_edge + util.solve2_2 (FM.py:79-93, util.py:6-54), error_per_edge (FM.py:97-124) and
 // Algorithm.placement (Algorithm.py:62-101).
 //
-// Layout: node id = post-order rank (= edge_index).  The observed leaves arrive sorted by id, i.e. left to right.
-// Walking leaf i upwards until the first ancestor that also contains leaf i+1 enumerates the valid nodes of the
-// restricted subtree in post-order with O(1) state; a small stack of "pending attach nodes" links siblings in
-// left-to-right order.  The S moments are accumulated during that same walk, the R moments in one reverse sweep,
-// then every edge is solved in closed form and the criterion argmin is taken in post-order (first minimum wins,
-// like Python's min()).
+// Layout: node id = post-order (DFS) rank = edge_index.  The observed leaves arrive sorted by id, i.e. left to
+// right.  "Chain i" = leaf i and its ancestors up to (excluding) the first ancestor that also contains leaf i+1
+// (the last chain stops below the MRCA).  Concatenating the chains enumerates the valid nodes of the restricted
+// subtree (Subtree.py:23-43) in post-order, so a prefix sum over the chain lengths gives every valid node a compact
+// index, and the attach level of a chain (level of the node above its top) describes the whole topology:
+//   * the node a chain hangs from lives on the next chain to the right with a strictly smaller attach level,
+//   * chains hanging from the same node are consecutive "next smaller-or-equal" neighbours, in child order.
+// Lanes work on chains / nodes in parallel: chain discovery and linking, then the S moments level by level from the
+// deepest level up, the R moments level by level down, then every edge is solved in closed form and the criterion
+// argmin is a warp-shuffle reduction (first minimum in post-order wins, like Python's min()).
 //
 // One template for the four weightings: moment vector m[6] = sums over leaves of
 //   [w, w d, w d^2, w D, w D d, w D^2]      d = path length, D = observed distance,
 //   w = 1 (OLS, BME), 1/D^2 (FM), 1/D (BE); BME averages over valid children (BME.py:19,36-37).
-// Mapping onto the reference's names is in DESIGN.md.  fp64 operations are written in the reference's order and
-// this file is compiled with -fmad=false, so S/R moments, x_1, x_2 are bit-identical to the reference's for
-// identical observed distances (the error differs only through Python's pow(x, 2), see DESIGN.md "parity").
+// Children are always summed in child order and fp64 operations are written in the reference's order; the file is
+// compiled with -fmad=false, so S/R moments, x_1, x_2 are bit-identical to the reference's for identical observed
+// distances (the error differs only through Python's pow(x, 2), see DESIGN.md "parity").
 #include "common.cuh"
+
+#define FULLMASK 0xffffffffu
 
 __device__ __forceinline__ void leaf_moments(int method, double D, double* m) {
     m[1] = 0.0; m[2] = 0.0; m[4] = 0.0;
@@ -100,16 +106,28 @@ __device__ __forceinline__ EdgeSol solve_edge(const double* S, const double* R, 
     return e;
 }
 
+// lexicographic (value, index) minimum over the warp; lanes without a candidate pass idx = INT_MAX
+__device__ __forceinline__ void warp_argmin(double& val, int& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULLMASK, val, o);
+        const int oi = __shfl_xor_sync(FULLMASK, idx, o);
+        const bool take = (oi != 0x7fffffff) && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx));
+        if (take) { val = ov; idx = oi; }
+    }
+}
+
 template <int METHOD>
-__global__ void __launch_bounds__(64) place_kernel(const PlaceArgs a) {
+__global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a) {
     constexpr bool BME = METHOD == APPLES_BME;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= a.n) return;
     const int q = a.qlist ? a.qlist[t] : a.q_begin + t;
     const int slot = a.qlist ? t : q;
     const int st = a.status[q];
     if (st != ST_PLACE) {
-        if (st == ST_OVERFLOW) return;  // handled by a later launch
+        if (st == ST_OVERFLOW || lane != 0) return;  // overflow: handled by a later launch
         a.out_edge[q] = (st == ST_ZERO) ? a.zero_edge[q] : -1;
         a.out_error[q] = 0.0;
         a.out_distal[q] = 0.0;
@@ -121,105 +139,132 @@ __global__ void __launch_bounds__(64) place_kernel(const PlaceArgs a) {
     const int K = a.K[q];
     const int* __restrict__ onode = a.obs_node + (size_t)slot * a.cap;
     const double* __restrict__ odist = a.obs_dist + (size_t)slot * a.cap;
-    NodeRec* __restrict__ rec = a.recs + a.rec_off[t];
-    StackEnt* __restrict__ stk = a.stacks + a.stack_off[t];
+    const int* __restrict__ olen = a.obs_len + (size_t)slot * a.cap;
+    NodeRec* rec = a.recs + a.rec_off[t];       // V valid nodes + 1 pseudo record for the subtree root (the MRCA)
+    StackEnt* ch = a.stacks + a.stack_off[t];   // K chains: A = attach level, first = compact offset, last = leaf level
     const int* __restrict__ parent = a.tree.parent;
-    const int* __restrict__ first = a.tree.first;
+    const int* __restrict__ level = a.tree.level;
     const double* __restrict__ elen = a.tree.elen;
 
-    // ---------------- pass 1: enumerate valid nodes in post-order, link children, accumulate S ----------------
-    int p = 0, sp = 0;
-    const int leaf0 = onode[0];
-    for (int i = 0; i < K; ++i) {
+    // ---------------- chains: attach level, leaf level, compact offsets (prefix sum over chain lengths) ----------------
+    int carry = 0, maxlev = 0;
+    for (int i0 = 0; i0 < K; i0 += 32) {
+        const int i = i0 + lane;
+        int len = 0, ll = 0;
+        if (i < K) {
+            len = olen[i];
+            ll = level[onode[i]];
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULLMASK, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (i < K) {
+            ch[i].A = ll - len;
+            ch[i].first = carry + incl - len;
+            ch[i].last = ll;
+        }
+        carry += __shfl_sync(FULLMASK, incl, 31);
+        maxlev = max(maxlev, ll);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlev = max(maxlev, __shfl_xor_sync(FULLMASK, maxlev, o));
+    const int V = carry;
+    __syncwarp();
+    const int rootlev = ch[K - 1].A;  // the last chain stops below the MRCA
+
+    // ---------------- node records: one lane walks one chain ----------------
+    for (int i = lane; i < K; i += 32) {
         int u = onode[i];
-        const int nxt = (i + 1 < K) ? onode[i + 1] : -1;
-        {
-            NodeRec& r = rec[p];
-            leaf_moments(METHOD, odist[i], r.S);
+        const int off = ch[i].first, len = ch[i].last - ch[i].A;
+        for (int s = 0; s < len; ++s) {
+            NodeRec& r = rec[off + s];
             r.len = elen[u];
             r.orig = u;
-            r.fchild = -1;
+            r.fchild = s ? off + s - 1 : -1;
             r.rsib = -1;
-            r.nchild = 0;
-        }
-        int prev = p++;
-        while (true) {
-            const int par = parent[u];
-            const bool top = (i + 1 < K) ? (par >= nxt) : (first[par] <= leaf0);
-            const bool pending = sp > 0 && stk[sp - 1].A == par;
-            if (top) {
-                // `prev` is a non-last child of `par`, which a later chain (or the MRCA) owns
-                if (pending) {
-                    StackEnt& e = stk[sp - 1];
-                    rec[e.last].rsib = prev;
-                    e.last = prev;
-                    e.n++;
-                } else {
-                    StackEnt& e = stk[sp++];
-                    e.A = par; e.first = prev; e.last = prev; e.n = 1;
-                }
-                break;
-            }
-            int fc = prev, n = 1;
-            if (pending) {
-                const StackEnt e = stk[--sp];
-                rec[e.last].rsib = prev;
-                fc = e.first;
-                n = e.n + 1;
-            }
-            NodeRec& r = rec[p];
-            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            const double coef = BME ? 1.0 / (double)n : 1.0;   // BME.py:19
-            for (int c = fc; c >= 0; c = rec[c].rsib) accumulate<BME>(acc, rec[c].S, rec[c].len, coef);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) r.S[k] = acc[k];
-            r.len = elen[par];
-            r.orig = par;
-            r.fchild = fc;
-            r.rsib = -1;
-            r.nchild = n;
-            prev = p++;
-            u = par;
+            r.nchild = s ? 1 : 0;
+            r.par = off + s + 1;  // the top of the chain is re-linked below
+            if (s == 0) leaf_moments(METHOD, odist[i], r.S);
+            u = parent[u];
         }
     }
-    const int Vn = p;
-    // exactly one pending entry is left: the children of the MRCA (the subtree root, not a valid node)
-    const int root_first = stk[0].first;
-    const int root_n = stk[0].n;
+    if (lane == 0) {
+        rec[V].fchild = -1;
+        rec[V].nchild = 0;
+    }
+    __syncwarp();
 
-    // ---------------- pass 2: R moments, parents before children (reverse post-order) ----------------
+    // ---------------- link every chain top to the node it hangs from ----------------
+    for (int j = lane; j < K; j += 32) {
+        const int alj = ch[j].A;
+        const int top = ch[j].first + (ch[j].last - alj) - 1;
+        // next chain to the right with attach level <= mine (next sibling or my owner), then < mine (my owner)
+        int nse = j + 1;
+        while (nse < K && ch[nse].A > alj) ++nse;
+        int own = nse;
+        while (own < K && ch[own].A >= alj) ++own;
+        const int P = (own < K) ? ch[own].first + (ch[own].last - alj) : V;   // compact index of the node I hang from
+        rec[top].par = P;
+        if (nse < K && ch[nse].A == alj)
+            rec[top].rsib = ch[nse].first + (ch[nse].last - alj) - 1;          // next attached chain of the same node
+        else if (own < K)
+            rec[top].rsib = P - 1;                                            // the owner chain's own child comes last
+        // am I the first child?  (no chain to the left hangs from the same node)
+        int pse = j - 1;
+        while (pse >= 0 && ch[pse].A > alj) --pse;
+        if (pse < 0 || ch[pse].A < alj) rec[P].fchild = top;
+        atomicAdd(&rec[P].nchild, 1);
+    }
+    __syncwarp();
+
+    // ---------------- S moments: level by level from the deepest level up (children before parents) ----------------
+    for (int lv = maxlev - 1; lv > rootlev; --lv) {
+        for (int i = lane; i < K; i += 32) {
+            const int al = ch[i].A, ll = ch[i].last;
+            if (al < lv && lv < ll) {
+                NodeRec& r = rec[ch[i].first + (ll - lv)];
+                const double coef = BME ? 1.0 / (double)r.nchild : 1.0;   // BME.py:19
+                double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                for (int c = r.fchild; c >= 0; c = rec[c].rsib) accumulate<BME>(acc, rec[c].S, rec[c].len, coef);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) r.S[k] = acc[k];
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- R moments: level by level down (parents before children) ----------------
     // all_R_values: siblings in child order, then the parent's R shifted by the parent's edge unless the parent is
     // the subtree root (FM.py:53-76); BME: coefficient 1 / (nonroot + #valid siblings) (BME.py:36-37)
-    for (int pp = Vn; pp >= 0; --pp) {
-        int fc, n;
-        const bool nonroot = pp < Vn;
-        if (!nonroot) { fc = root_first; n = root_n; }
-        else { fc = rec[pp].fchild; n = rec[pp].nchild; if (fc < 0) continue; }
-        const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + n - 1) : 1.0;
-        for (int c = fc; c >= 0; c = rec[c].rsib) {
-            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int s = fc; s >= 0; s = rec[s].rsib)
-                if (s != c) accumulate<BME>(acc, rec[s].S, rec[s].len, coef);
-            if (nonroot) accumulate<BME>(acc, rec[pp].R, rec[pp].len, coef);
+    for (int lv = rootlev + 1; lv <= maxlev; ++lv) {
+        for (int i = lane; i < K; i += 32) {
+            const int al = ch[i].A, ll = ch[i].last;
+            if (al < lv && lv <= ll) {
+                const int p = ch[i].first + (ll - lv);
+                NodeRec& r = rec[p];
+                const int P = r.par;
+                const bool nonroot = P < V;
+                const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + rec[P].nchild - 1) : 1.0;
+                double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                for (int s = rec[P].fchild; s >= 0; s = rec[s].rsib)
+                    if (s != p) accumulate<BME>(acc, rec[s].S, rec[s].len, coef);
+                if (nonroot) accumulate<BME>(acc, rec[P].R, rec[P].len, coef);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) rec[c].R[k] = acc[k];
+                for (int k = 0; k < 6; ++k) r.R[k] = acc[k];
+            }
         }
+        __syncwarp();
     }
 
-    // ---------------- pass 3: per-edge closed-form solve + criterion selection in post-order ----------------
+    // ---------------- per-edge closed-form solve + criterion selection (first minimum in post-order) ----------------
     const bool dbg = a.dbg_x1 != nullptr && q == a.dbg_query;
-    int best = -1;
-    EdgeSol bs;
-    bs.x1 = bs.x2 = bs.err = 0.0;
-    bs.int0 = false;
-    // HYBRID: the floor(log2 V) smallest errors in (error, order) order (heapq.nsmallest, Algorithm.py:77-79)
-    constexpr int HMAX = 32;
-    double h_err[HMAX], h_x1[HMAX];
-    int h_p[HMAX];
-    int hn = 0;
-    const int hcap = (a.criterion == APPLES_HYBRID) ? (31 - __clz(Vn)) : 0;
-    for (int pp = 0; pp < Vn; ++pp) {
-        const NodeRec& r = rec[pp];
+    double bval = 0.0;
+    int bidx = 0x7fffffff;
+    for (int p = lane; p < V; p += 32) {
+        NodeRec& r = rec[p];
         const EdgeSol e = solve_edge(r.S, r.R, r.len, a.negative_branch);
         if (dbg) {
             a.dbg_x1[r.orig] = e.x1;
@@ -227,44 +272,53 @@ __global__ void __launch_bounds__(64) place_kernel(const PlaceArgs a) {
             a.dbg_err[r.orig] = e.err;
             a.dbg_valid[r.orig] = 1;
         }
-        if (a.criterion == APPLES_MLSE) {
-            if (best < 0 || e.err < bs.err) { best = pp; bs = e; }
-        } else if (a.criterion == APPLES_ME) {
-            if (best < 0 || e.x1 < bs.x1) { best = pp; bs = e; }
-        } else {
-            if (hn < hcap || e.err < h_err[hn - 1]) {
-                int pos = (hn < hcap) ? hn : hn - 1;
-                while (pos > 0 && h_err[pos - 1] > e.err) {
-                    h_err[pos] = h_err[pos - 1]; h_x1[pos] = h_x1[pos - 1]; h_p[pos] = h_p[pos - 1];
-                    --pos;
-                }
-                h_err[pos] = e.err; h_x1[pos] = e.x1; h_p[pos] = pp;
-                if (hn < hcap) ++hn;
+        const double key = (a.criterion == APPLES_ME) ? e.x1 : e.err;
+        if (bidx == 0x7fffffff || key < bval) { bval = key; bidx = p; }  // ascending p per lane: first minimum kept
+    }
+    warp_argmin(bval, bidx);
+    int best = bidx;
+    if (a.criterion == APPLES_HYBRID) {
+        // heapq.nsmallest(floor(log2 V), key=error) in (error, order) order, then the first minimum of x_1 among
+        // them (Algorithm.py:77-82): floor(log2 V) rounds of "next smallest (error, index)"
+        const int rounds = 31 - __clz(V);
+        double last_e = 0.0, best_x1 = 0.0;
+        int last_p = -1;
+        best = -1;
+        for (int rd = 0; rd < rounds; ++rd) {
+            double v = 0.0;
+            int ix = 0x7fffffff;
+            for (int p = lane; p < V; p += 32) {
+                const NodeRec& r = rec[p];
+                const double e = solve_edge(r.S, r.R, r.len, a.negative_branch).err;
+                const bool after = last_p < 0 || e > last_e || (e == last_e && p > last_p);
+                if (after && (ix == 0x7fffffff || e < v)) { v = e; ix = p; }
             }
+            warp_argmin(v, ix);
+            if (ix == 0x7fffffff) break;
+            const NodeRec& r = rec[ix];
+            const double x1 = solve_edge(r.S, r.R, r.len, a.negative_branch).x1;
+            if (best < 0 || x1 < best_x1) { best = ix; best_x1 = x1; }
+            last_e = v;
+            last_p = ix;
         }
     }
-    if (a.criterion == APPLES_HYBRID) {
-        int bi = 0;
-        for (int i = 1; i < hn; ++i)
-            if (h_x1[i] < h_x1[bi]) bi = i;
-        best = h_p[bi];
-        const NodeRec& r = rec[best];
-        bs = solve_edge(r.S, r.R, r.len, a.negative_branch);
+    if (lane == 0) {
+        const NodeRec& rb = rec[best];
+        const EdgeSol bs = solve_edge(rb.S, rb.R, rb.len, a.negative_branch);
+        // Algorithm.py:93-99
+        const bool flag = bs.x1 == 0.0 && bs.err > 0.0 && (bs.x2 == 0.0 || bs.x2 == rb.len);
+        a.out_edge[q] = rb.orig;
+        a.out_error[q] = bs.err;
+        a.out_distal[q] = rb.len - bs.x2;
+        a.out_pendant[q] = bs.x1;
+        a.out_status[q] = (flag ? APPLES_PLACED_MISPLACEMENT_FLAG : APPLES_PLACED) | (bs.int0 ? APPLES_FLAG_PENDANT_INT0 : 0);
     }
-    const NodeRec& rb = rec[best];
-    // Algorithm.py:93-99
-    const bool flag = bs.x1 == 0.0 && bs.err > 0.0 && (bs.x2 == 0.0 || bs.x2 == rb.len);
-    a.out_edge[q] = rb.orig;
-    a.out_error[q] = bs.err;
-    a.out_distal[q] = rb.len - bs.x2;
-    a.out_pendant[q] = bs.x1;
-    a.out_status[q] = (flag ? APPLES_PLACED_MISPLACEMENT_FLAG : APPLES_PLACED) | (bs.int0 ? APPLES_FLAG_PENDANT_INT0 : 0);
 }
 
 void launch_place(int method, const PlaceArgs& a, cudaStream_t s) {
     if (a.n <= 0) return;
-    const int threads = 64;
-    dim3 grid((a.n + threads - 1) / threads), block(threads);
+    const int warps = 4;
+    dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
     switch (method) {
         case APPLES_FM: place_kernel<APPLES_FM><<<grid, block, 0, s>>>(a); break;
         case APPLES_BME: place_kernel<APPLES_BME><<<grid, block, 0, s>>>(a); break;

@@ -442,14 +442,16 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
         for (int i = lane; i < K; i += 32) {
             int u = node[i];
             const int nxt = (i + 1 < K) ? node[i + 1] : -1;
-            c++;
+            int len = 1;
             while (true) {
                 const int p = a.tree.parent[u];
                 const bool top = (i + 1 < K) ? (p >= nxt) : (a.tree.first[p] <= leaf0);
                 if (top) break;
-                c++;
+                len++;
                 u = p;
             }
+            a.obs_len[(size_t)oslot * a.cap + i] = len;
+            c += len;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
