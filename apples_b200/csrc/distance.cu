@@ -139,11 +139,15 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNuc
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int qt = tile / n_rt, rt = tile % n_rt;
-        uint32_t accM[4][4], accV[4][4];
+        // per pair: acc = mismatch count (low 16 bits) | valid count (high 16 bits); `ones` is the weight-1 plane of a
+        // carry-save counter over the valid words: two valid words are folded with one full adder (2 LOP3) and only
+        // the carry (weight 2) is popcounted, which takes a third of the POPC work off the XU pipe -- the kernel's
+        // binding unit (DESIGN.md "rooflines")
+        uint32_t acc[4][4], ones[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) accM[i][j] = accV[i][j] = 0u;
+            for (int j = 0; j < 4; ++j) acc[i][j] = ones[i][j] = 0u;
 
         for (int c = 0; c < n_chunks; ++c, ++it) {
             const int s = it % DT_STAGES;
@@ -151,31 +155,50 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNuc
             mbar_wait(&full_bar[s], ph);
             const uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
             const uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
-#pragma unroll 2
-            for (int w = 0; w < DT_WC; ++w) {
-                const uint4 ql = *reinterpret_cast<const uint4*>(sq + (0 * DT_WC + w) * DT_TQ + 4 * tq);
-                const uint4 qh = *reinterpret_cast<const uint4*>(sq + (1 * DT_WC + w) * DT_TQ + 4 * tq);
-                const uint4 qv = *reinterpret_cast<const uint4*>(sq + (2 * DT_WC + w) * DT_TQ + 4 * tq);
-                const uint4 rl = *reinterpret_cast<const uint4*>(sr + (0 * DT_WC + w) * DT_TR + 4 * tr);
-                const uint4 rh = *reinterpret_cast<const uint4*>(sr + (1 * DT_WC + w) * DT_TR + 4 * tr);
-                const uint4 rv = *reinterpret_cast<const uint4*>(sr + (2 * DT_WC + w) * DT_TR + 4 * tr);
-                const uint32_t qlo[4] = {ql.x, ql.y, ql.z, ql.w}, qhi[4] = {qh.x, qh.y, qh.z, qh.w},
-                               qva[4] = {qv.x, qv.y, qv.z, qv.w};
-                const uint32_t rlo[4] = {rl.x, rl.y, rl.z, rl.w}, rhi[4] = {rh.x, rh.y, rh.z, rh.w},
-                               rva[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll 1
+            for (int w = 0; w < DT_WC; w += 2) {
+                uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 ql = *reinterpret_cast<const uint4*>(sq + (0 * DT_WC + w + h) * DT_TQ + 4 * tq);
+                    const uint4 qh = *reinterpret_cast<const uint4*>(sq + (1 * DT_WC + w + h) * DT_TQ + 4 * tq);
+                    const uint4 qv = *reinterpret_cast<const uint4*>(sq + (2 * DT_WC + w + h) * DT_TQ + 4 * tq);
+                    const uint4 rl = *reinterpret_cast<const uint4*>(sr + (0 * DT_WC + w + h) * DT_TR + 4 * tr);
+                    const uint4 rh = *reinterpret_cast<const uint4*>(sr + (1 * DT_WC + w + h) * DT_TR + 4 * tr);
+                    const uint4 rv = *reinterpret_cast<const uint4*>(sr + (2 * DT_WC + w + h) * DT_TR + 4 * tr);
+                    qlo[h][0] = ql.x; qlo[h][1] = ql.y; qlo[h][2] = ql.z; qlo[h][3] = ql.w;
+                    qhi[h][0] = qh.x; qhi[h][1] = qh.y; qhi[h][2] = qh.z; qhi[h][3] = qh.w;
+                    qva[h][0] = qv.x; qva[h][1] = qv.y; qva[h][2] = qv.z; qva[h][3] = qv.w;
+                    rlo[h][0] = rl.x; rlo[h][1] = rl.y; rlo[h][2] = rl.z; rlo[h][3] = rl.w;
+                    rhi[h][0] = rh.x; rhi[h][1] = rh.y; rhi[h][2] = rh.z; rhi[h][3] = rh.w;
+                    rva[h][0] = rv.x; rva[h][1] = rv.y; rva[h][2] = rv.z; rva[h][3] = rv.w;
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t v = qva[i] & rva[j];
-                        const uint32_t m = ((qlo[i] ^ rlo[j]) | (qhi[i] ^ rhi[j])) & v;
-                        accM[i][j] += __popc(m);
-                        accV[i][j] += __popc(v);
+                        const uint32_t v0 = qva[0][i] & rva[0][j];
+                        const uint32_t v1 = qva[1][i] & rva[1][j];
+                        const uint32_t m0 = ((qlo[0][i] ^ rlo[0][j]) | (qhi[0][i] ^ rhi[0][j])) & v0;
+                        const uint32_t m1 = ((qlo[1][i] ^ rlo[1][j]) | (qhi[1][i] ^ rhi[1][j])) & v1;
+                        const uint32_t o = ones[i][j];
+                        const uint32_t carry = (o & v0) | (o & v1) | (v0 & v1);  // full adder: one LOP3 each
+                        ones[i][j] = o ^ v0 ^ v1;
+                        acc[i][j] += __popc(m0) + __popc(m1) + (__popc(carry) << 17);
                     }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
+        uint32_t accM[4][4], accV[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16);
+                accM[i][j] = a2 & 0xffffu;
+                accV[i][j] = a2 >> 16;
+            }
 
         // ---- epilogue ----
         const int q0 = qt * DT_TQ + 4 * tq, r0 = rt * DT_TR + 4 * tr;
