@@ -81,6 +81,7 @@ struct DenseNucArgs {
     // keys epilogue
     uint32_t* keys;
     int64_t ldk;
+    uint32_t k_one, k_two17;  // 1 and 1 << 17 (see the consumer loop)
     // full epilogue (parity export)
     int nq, n_ref, vmin;
     uint32_t* mism;
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNuc
     // ===== consumers: thread (tq, tr) owns queries 4*tq..+3 and representatives 4*tr..+3 of the tile =====
     const int tq = tid & 15, tr = tid >> 4;
     uint32_t it = 0;
+    const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int qt = tile / n_rt, rt = tile % n_rt;
         // per pair: acc = mismatch count (low 16 bits) | valid count (high 16 bits); `ones` is the weight-1 plane of a
@@ -184,7 +186,11 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNuc
                         const uint32_t o = ones[i][j];
                         const uint32_t carry = (o & v0) | (o & v1) | (v0 & v1);  // full adder: one LOP3 each
                         ones[i][j] = o ^ v0 ^ v1;
-                        acc[i][j] += __popc(m0) + __popc(m1) + (__popc(carry) << 17);
+                        // the three accumulations go to the (idle) FMA pipe as IMADs: the multipliers are opaque
+                        // registers so that ptxas cannot turn them back into ALU-pipe adds / shifts
+                        acc[i][j] = __popc(m0) * k_one + acc[i][j];
+                        acc[i][j] = __popc(m1) * k_one + acc[i][j];
+                        acc[i][j] = __popc(carry) * k_two17 + acc[i][j];
                     }
             }
             __syncwarp();
@@ -245,6 +251,7 @@ void launch_dense_nuc_keys(const uint32_t* q_wm, int q_pad, const uint32_t* r_wm
                            int64_t ldk, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
     a.q_wm = q_wm; a.r_wm = r_wm; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
+    a.k_one = 1u; a.k_two17 = 1u << 17;
     dense_nuc_kernel<false><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);
 }
 
@@ -252,6 +259,7 @@ void launch_dense_nuc_full(const uint32_t* q_wm, int q_pad, int nq, const uint32
                            int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
     a.q_wm = q_wm; a.r_wm = r_wm; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp;
+    a.k_one = 1u; a.k_two17 = 1u << 17;
     a.nq = nq; a.n_ref = n_ref; a.vmin = vmin; a.mism = mism; a.valid = valid; a.dist = dist;
     dense_nuc_kernel<true><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);
 }
