@@ -10,7 +10,13 @@
 constexpr int DT_TQ = 64;       // queries per CTA tile
 constexpr int DT_TR = 64;       // representatives per CTA tile
 constexpr int DT_WC = 16;       // 32-site words per pipeline stage
-constexpr int DT_STAGES = 4;    // TMA pipeline depth
+#ifndef DT_STAGES_V
+#define DT_STAGES_V 4
+#endif
+#ifndef DT_MINBLOCKS
+#define DT_MINBLOCKS 2
+#endif
+constexpr int DT_STAGES = DT_STAGES_V;    // TMA pipeline depth
 constexpr int DT_CONSUMERS = 256;
 constexpr int DT_THREADS = DT_CONSUMERS + 32;  // + one producer warp
 constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);

@@ -47,6 +47,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 
+// three-input logic op with an explicit truth table (a = 0xf0, b = 0xcc, c = 0xaa)
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // row-major [rows][3][W]  ->  word-major [3][Wp][rows_pad]   (padding must be pre-zeroed by the caller)
 // ---------------------------------------------------------------------------------------------------------------
@@ -90,7 +98,7 @@ struct DenseNucArgs {
 };
 
 template <bool FULL>
-__global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNucArgs a) {
+__global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(const DenseNucArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* stage_base = reinterpret_cast<uint32_t*>(smem_raw);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw + DT_STAGES * DT_STAGE_BYTES);
@@ -179,13 +187,19 @@ __global__ void __launch_bounds__(DT_THREADS, 2) dense_nuc_kernel(const DenseNuc
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t v0 = qva[0][i] & rva[0][j];
-                        const uint32_t v1 = qva[1][i] & rva[1][j];
-                        const uint32_t m0 = ((qlo[0][i] ^ rlo[0][j]) | (qhi[0][i] ^ rhi[0][j])) & v0;
-                        const uint32_t m1 = ((qlo[1][i] ^ rlo[1][j]) | (qhi[1][i] ^ rhi[1][j])) & v1;
+                        // 10 LOP3 per pair per two words, pinned with explicit LUTs (left to itself ptxas re-fuses the
+                        // AND into the adder and spends 12)
+                        const uint32_t v0 = lop3<0xc0>(qva[0][i], rva[0][j], 0u);            // qv & rv
+                        const uint32_t v1 = lop3<0xc0>(qva[1][i], rva[1][j], 0u);
+                        const uint32_t x0 = lop3<0x3c>(qlo[0][i], rlo[0][j], 0u);            // qlo ^ rlo
+                        const uint32_t x1 = lop3<0x3c>(qlo[1][i], rlo[1][j], 0u);
+                        const uint32_t t0 = lop3<0xbe>(qhi[0][i], rhi[0][j], x0);            // (qhi ^ rhi) | x
+                        const uint32_t t1 = lop3<0xbe>(qhi[1][i], rhi[1][j], x1);
+                        const uint32_t m0 = lop3<0xc0>(t0, v0, 0u);                          // mismatching valid sites
+                        const uint32_t m1 = lop3<0xc0>(t1, v1, 0u);
                         const uint32_t o = ones[i][j];
-                        const uint32_t carry = (o & v0) | (o & v1) | (v0 & v1);  // full adder: one LOP3 each
-                        ones[i][j] = o ^ v0 ^ v1;
+                        const uint32_t carry = lop3<0xe8>(o, v0, v1);                        // full adder: majority
+                        ones[i][j] = lop3<0x96>(o, v0, v1);                                  //             parity
                         // the three accumulations go to the (idle) FMA pipe as IMADs: the multipliers are opaque
                         // registers so that ptxas cannot turn them back into ALU-pipe adds / shifts
                         acc[i][j] = __popc(m0) * k_one + acc[i][j];
@@ -243,7 +257,7 @@ cudaError_t dense_nuc_configure() {
 
 static int dense_grid(int q_pad, int r_pad, int num_sms) {
     int tiles = (q_pad / DT_TQ) * (r_pad / DT_TR);
-    int g = 2 * num_sms;  // two resident CTAs per SM, persistent over tiles
+    int g = DT_MINBLOCKS * num_sms;  // resident CTAs per SM, persistent over tiles
     return tiles < g ? tiles : g;
 }
 
