@@ -4,9 +4,9 @@
 // representatives in ascending (distance, index) order and expands a cluster while
 // `dist <= threshold or obs_num < baseobs`.  Because pops are ascending and obs_num only grows, that is
 //   taken = { clusters with dist <= threshold }  U  { the next clusters in (dist, index) order while obs_num < baseobs }
-// (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters as it meets them, keeps
-// the 32 smallest far clusters in a register-resident sorted list (one entry per lane) and afterwards walks that
-// list in order until obs_num reaches baseobs (re-scanning for the next 32 in the rare case the list runs out).
+// (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters as it meets them and keeps,
+// per lane, only the smallest far key of its residue class; afterwards the far clusters are extracted in ascending
+// order (warp-wide minimum of the lane minima, then a re-scan of one residue class) until obs_num reaches baseobs.
 // Nucleotide keys are the exact integer pairs (mismatch, valid) from the dense kernel: ordering by the rational
 // mismatch/valid is ordering by jc69 distance (equal rationals give the identical double), so no fp64 is needed
 // for the ~R representatives per query; the corrected fp64 distance is evaluated only for the selected members.
@@ -79,6 +79,21 @@ __device__ __forceinline__ Key<KIND> key_shfl_up(const Key<KIND>& k) {
     o.d = __shfl_up_sync(FULLMASK, k.d, 1);
     o.idx = __shfl_up_sync(FULLMASK, k.idx, 1);
     return o;
+}
+
+__device__ __forceinline__ Key<SEL_NUC> key_shfl_xor(const Key<SEL_NUC>& k, int o) {
+    Key<SEL_NUC> r;
+    r.m = __shfl_xor_sync(FULLMASK, k.m, o);
+    r.v = __shfl_xor_sync(FULLMASK, k.v, o);
+    r.idx = __shfl_xor_sync(FULLMASK, k.idx, o);
+    return r;
+}
+template <int KIND>
+__device__ __forceinline__ Key<KIND> key_shfl_xor(const Key<KIND>& k, int o) {
+    Key<KIND> r;
+    r.d = __shfl_xor_sync(FULLMASK, k.d, o);
+    r.idx = __shfl_xor_sync(FULLMASK, k.idx, o);
+    return r;
 }
 
 // raw key of one unit as stored in the key matrix (kept in registers during the scan; the Key is rebuilt on demand)
@@ -309,100 +324,107 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
     st.znode = -1;
     st.zkey.idx = 0;
 
-    // sorted list of the smallest far units seen so far: lane j holds the j-th smallest, `cnt` entries are live
-    Key<KIND> mine;
-    mine.idx = -1;
-    Key<KIND> last;      // everything <= last has already been handled by an earlier round
-    bool have_last = false;
-    bool first_round = true;
-    bool done = false;
+    // ---- one scan of the key row.  Near units (dist <= threshold) are expanded as they are met (rare: a handful per
+    // query, handled after a warp vote).  Far units only update a lane-local minimum -- registers only, no warp
+    // traffic -- because the far set is needed only while obs_num < baseobs, and then only its few smallest members:
+    // they are extracted afterwards, one at a time, as the warp-wide minimum of the 32 lane minima; the lane that
+    // owned it gets its next-smallest key by a cooperative re-scan of just its residue class (R / 32 keys). ----
     constexpr int U = 8;  // independent key loads in flight per lane (the scan is latency-bound otherwise)
-
-    Key<KIND> k31;  // copy of the list's largest entry once the list is full
-    k31.idx = -1;
-    while (!done) {
-        int cnt = 0;
-        for (int u0 = 0; u0 < a.n_units; u0 += 32 * U) {
-            typename RawT<KIND>::T raw[U];
-            int cls[U];
+    Key<KIND> lmin;       // smallest far key among the units u with u % 32 == lane
+    bool have_lmin = false;
+    for (int u0 = 0; u0 < a.n_units; u0 += 32 * U) {
+        typename RawT<KIND>::T raw[U];
+        int cls[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = u0 + j * 32 + lane;
+            raw[j] = 0;
+            if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
+        }
+        bool any_near = false;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int u = u0 + j * 32 + lane;
+            const Key<KIND> kj = make_key<KIND>(raw[j], u);
+            cls[j] = (u < a.n_units) ? classify(a, kj) : 0;
+            any_near |= cls[j] == 1;
+            if (cls[j] == 2 && (!have_lmin || key_less(kj, lmin))) {
+                lmin = kj;
+                have_lmin = true;
+            }
+        }
+        if (__any_sync(FULLMASK, any_near)) {
+            // queued (lane t holds the t-th pending key) and expanded from ONE loop so that the member-distance code
+            // is instantiated once
+            unsigned nearm[U];
+            bool any = false;
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                const int u = u0 + j * 32 + lane;
-                raw[j] = 0;
-                if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
+                nearm[j] = __ballot_sync(FULLMASK, cls[j] == 1);
+                any |= nearm[j] != 0u;
             }
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                const int u = u0 + j * 32 + lane;
-                cls[j] = (u < a.n_units) ? classify(a, make_key<KIND>(raw[j], u)) : 0;
-            }
-            if (first_round) {
-                // near units: queued (lane t holds the t-th pending key) and expanded from ONE loop so that the
-                // member-distance code is instantiated once
-                unsigned nearm[U];
-                bool any = false;
+            while (any) {
+                int qn = 0;
+                Key<KIND> qkey;
+                qkey.idx = -1;
+                any = false;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
-                    nearm[j] = __ballot_sync(FULLMASK, cls[j] == 1);
+                    while (nearm[j] && qn < 32) {
+                        const int src = __ffs(nearm[j]) - 1;
+                        nearm[j] &= nearm[j] - 1;
+                        const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
+                        if (lane == qn) qkey = uk;
+                        ++qn;
+                    }
                     any |= nearm[j] != 0u;
                 }
-                while (any) {
-                    int qn = 0;
-                    Key<KIND> qkey;
-                    qkey.idx = -1;
-                    any = false;
-#pragma unroll
-                    for (int j = 0; j < U; ++j) {
-                        while (nearm[j] && qn < 32) {
-                            const int src = __ffs(nearm[j]) - 1;
-                            nearm[j] &= nearm[j] - 1;
-                            const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
-                            if (lane == qn) qkey = uk;
-                            ++qn;
-                        }
-                        any |= nearm[j] != 0u;
-                    }
-                    for (int t = 0; t < qn; ++t) {
-                        const Key<KIND> uk = key_shfl(qkey, t);
-                        expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                bool cand = cls[j] == 2;
-                const Key<KIND> kj = make_key<KIND>(raw[j], u0 + j * 32 + lane);
-                if (cand && have_last) cand = key_less(last, kj);
-                if (cand && cnt == 32) cand = key_less(kj, k31);  // quick reject against the 32nd smallest
-                unsigned far = __ballot_sync(FULLMASK, cand);
-                while (far) {
-                    const int src = __ffs(far) - 1;
-                    far &= far - 1;
-                    const Key<KIND> ck = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
-                    // position = number of live entries smaller than the candidate
-                    const bool smaller = lane < cnt && key_less(mine, ck);
-                    const int pos = __popc(__ballot_sync(FULLMASK, smaller));
-                    if (pos >= 32) continue;
-                    const Key<KIND> up = key_shfl_up(mine);
-                    if (lane > pos) mine = up;
-                    if (lane == pos) mine = ck;
-                    if (cnt < 32) cnt++;
-                    if (cnt == 32) k31 = key_shfl(mine, 31);
+                for (int t = 0; t < qn; ++t) {
+                    const Key<KIND> uk = key_shfl(qkey, t);
+                    expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
                 }
             }
         }
-        first_round = false;
-        // walk the far list in ascending order while obs_num < baseobs (Reference.py:146)
-        for (int j = 0; j < cnt; ++j) {
-            if (st.obs_num >= a.baseobs) break;
-            const Key<KIND> uk = key_shfl(mine, j);
-            expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
+    }
+    // ---- far units in ascending (distance, index) order while obs_num < baseobs (Reference.py:146) ----
+    while (st.obs_num < a.baseobs) {
+        // warp-wide minimum of the lane minima
+        Key<KIND> g = lmin;
+        int owner = have_lmin ? lane : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const Key<KIND> og = key_shfl_xor(g, o);
+            const int oo = __shfl_xor_sync(FULLMASK, owner, o);
+            if (oo >= 0 && (owner < 0 || key_less(og, g))) {
+                g = og;
+                owner = oo;
+            }
         }
-        if (st.obs_num >= a.baseobs || cnt < 32) {
-            done = true;
-        } else {
-            last = key_shfl(mine, 31);
-            have_last = true;
+        if (owner < 0) break;  // no far unit left
+        expand_unit<KIND>(a, st, oslot, slot, self, g, lane);
+        // next-smallest key of the owner's residue class: units owner + 32 k, k split over the lanes
+        Key<KIND> nb;
+        bool have_nb = false;
+        for (int u = owner + 32 * lane; u < a.n_units; u += 32 * 32) {
+            const Key<KIND> kj = make_key<KIND>(load_raw<KIND>(a, slot, u), u);
+            if (classify(a, kj) == 2 && key_less(g, kj) && (!have_nb || key_less(kj, nb))) {
+                nb = kj;
+                have_nb = true;
+            }
+        }
+        int who = have_nb ? lane : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const Key<KIND> ob = key_shfl_xor(nb, o);
+            const int ow = __shfl_xor_sync(FULLMASK, who, o);
+            if (ow >= 0 && (who < 0 || key_less(ob, nb))) {
+                nb = ob;
+                who = ow;
+            }
+        }
+        if (lane == owner) {
+            lmin = nb;
+            have_lmin = who >= 0;
         }
     }
 
