@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libapples_b200.so')
+LIB_PATH = os.environ.get('APPLES_B200_LIB') or os.path.join(_HERE, 'libapples_b200.so')  # env: tuning experiments only
 
 NUC, AA = 0, 1
 FM, OLS, BME, BE = 0, 1, 2, 3

@@ -9,7 +9,10 @@
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int DT_TQ = 64;       // queries per CTA tile
 constexpr int DT_TR = 64;       // representatives per CTA tile
-constexpr int DT_WC = 16;       // 32-site words per pipeline stage
+#ifndef DT_WC_V
+#define DT_WC_V 16
+#endif
+constexpr int DT_WC = DT_WC_V;  // 32-site words per pipeline stage
 #ifndef DT_STAGES_V
 #define DT_STAGES_V 4
 #endif

@@ -7,6 +7,8 @@ placement edges identical.  With identical input distances (distance-matrix mode
 required to be BIT-IDENTICAL; the score may differ in the last bits only because the reference squares with
 pow(x, 2) (DESIGN.md "parity").
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -282,3 +284,105 @@ def test_properties_at_scale(workdir):
     t = pl.timings()
     assert t['rep_distance_launches'] >= 2
     pl.close()
+
+
+def test_error_behaviour_and_ragged_inputs(workdir):
+    """C-ABI error returns (no exceptions cross the boundary, no fallback) and ragged / degenerate inputs."""
+    import ctypes as C
+    from apples_b200 import _lib
+    from apples_b200.placer import GpuPlacer
+    from apples_b200.tree import BackboneTree
+    lib = _lib.load()
+    ci = util.CaseInputs('c1_align_FM_MLSE', workdir)
+    tree, ref = ci.product_state()
+    params = _lib.make_params()
+    # placing before a reference is set is an error with a message
+    pl = GpuPlacer(tree, None, tree.name_to_node, device=0)
+    out = pl._outputs(1)
+    dummy = np.zeros((1, 3, 52), np.uint32)
+    rc = lib.apples_place_batch(pl.h, 1, _lib.ptr(dummy), None, C.byref(params), *[_lib.ptr(o) for o in out])
+    assert rc != 0 and b'apples_set_reference' in lib.apples_last_error(pl.h)
+    # unknown method / criterion
+    bad = _lib.Params(9, 0, 0, 25, 0.2, 0.001)
+    pl.set_reference(ref)
+    rc = lib.apples_place_batch(pl.h, 1, _lib.ptr(dummy), None, C.byref(bad), *[_lib.ptr(o) for o in out])
+    assert rc != 0 and b'method' in lib.apples_last_error(pl.h)
+    # zero queries is fine and touches nothing
+    assert lib.apples_place_batch(pl.h, 0, None, None, C.byref(params), None, None, None, None, None) == 0
+    # a tree whose ids are not post-order ranks is rejected
+    par = tree.parent.copy()
+    par[0], par[1] = par[1], par[0] if par[0] != par[1] else 0
+    par[3] = 1
+    assert lib.apples_set_tree(pl.h, tree.num_nodes, _lib.ptr(par), _lib.ptr(tree.edge_length), _lib.ptr(tree.level),
+                               _lib.ptr(tree.first)) != 0
+    # ragged query alignment / wrong width / bytes outside the alphabet are host-side errors
+    seqs = [q[1] for q in ci.queries]
+    with pytest.raises(ValueError):
+        pl.pack_queries([seqs[0], seqs[1][:-3]])
+    with pytest.raises(ValueError):
+        pl.pack_queries([s[:100] for s in seqs])
+    bad_seq = seqs[0].copy()
+    bad_seq[5] = b'.'
+    with pytest.raises(ValueError):
+        pl.pack_queries([bad_seq])
+    # 1, 63, 64 and 65 queries (tile edges of the dense kernel) give the same answers as the full batch
+    full = pl.place_packed(pl.pack_queries(seqs * 7), None, params)
+    for n in (1, 63, 64, 65):
+        part = pl.place_packed(pl.pack_queries((seqs * 7)[:n]), None, params)
+        for x, y in zip(full, part):
+            assert (x[:n] == y).all()
+    pl.close()
+    # nucleotide alignments longer than 65535 columns are refused (16-bit counts)
+    t2 = BackboneTree.from_newick('((A:1,B:1):1,C:1,D:1);')
+    pl2 = GpuPlacer(t2, None, t2.name_to_node, device=0)
+    W = lib.apples_words_per_row(70000)
+    z = np.zeros((4, 3, W), np.uint32)
+    rn = np.array([0, 1, 3, 4], np.int32)
+    go = np.arange(5, dtype=np.int32)
+    gm = np.arange(4, dtype=np.int32)
+    rc = lib.apples_set_reference(pl2.h, 0, 70000, 4, _lib.ptr(z), _lib.ptr(rn), 4, _lib.ptr(z), _lib.ptr(go), _lib.ptr(gm))
+    assert rc != 0 and b'65535' in lib.apples_last_error(pl2.h)
+    pl2.close()
+
+
+def test_tiny_tree_and_all_singletons(workdir):
+    """4-leaf backbone, every reference its own cluster (fewer representatives than one dense tile), -b larger than
+    the reference: the selection takes everything, like the reference does."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200.placer import place_batch
+    from apples_b200.reference import ReducedReference
+    from apples_b200.tree import BackboneTree
+    nwk = '((A:0.05,B:0.07):0.02,(C:0.04,D:0.03):0.05,E:0.1);'
+    tfp = os.path.join(workdir, 'tiny.nwk')
+    open(tfp, 'w').write(nwk)
+    tree = BackboneTree.from_newick(tfp)
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 4, 300)
+    alpha = np.frombuffer(b'ACGT', dtype=np.uint8)
+    refs, qs = {}, []
+    for n in 'ABCDE':
+        s = base.copy()
+        hit = rng.random(300) < 0.08
+        s[hit] = (s[hit] + 1) % 4
+        refs[n] = alpha[s].view('S1')
+    for i in range(5):
+        s = base.copy()
+        hit = rng.random(300) < 0.1
+        s[hit] = (s[hit] + 2) % 4
+        qs.append(('q%d' % i, alpha[s].view('S1'), None))
+    tsv = os.path.join(workdir, 'tiny.tsv')
+    with open(tsv, 'w') as f:
+        f.write('SequenceName\tClusterNumber\n' + ''.join('%s\t-1\n' % n for n in 'ABCDE'))
+    ref = ReducedReference(None, False, tfp, 0.2, 1, cluster_tsv=tsv, tree=tree, refs=refs)
+    for method, crit, b in [('FM', 'MLSE', 25), ('OLS', 'ME', 2), ('BME', 'HYBRID', 100)]:
+        opt = types.SimpleNamespace(method_name=method, criterion_name=crit, negative_branch=False,
+                                    base_observation_threshold=b, filt_threshold=0.01, minimum_alignment_overlap=0.001,
+                                    exclude_intplace=False)
+        res = place_batch(ref, opt, tree.name_to_node, qs, tree=tree, device=0)
+        otree, onames = orc.load_tree(tfp)
+        octx = orc.OracleContext(otree, onames, refs=refs, representatives=orc.representatives_from_tsv(tsv, refs, False),
+                                 method=method, criterion=crit, filt_threshold=0.01, baseobs=b)
+        for q, r in zip(qs, res):
+            exp, _ = octx.runquery(q[0], q[1], None)
+            _check_p('tiny', q[0], r['placements'][0]['p'][0], exp['placements'][0]['p'][0], False, octx, q)

@@ -139,3 +139,16 @@ def test_synth_determinism():
     assert a == synth.random_tree(50, seed=9) and a != synth.random_tree(50, seed=10)
     t = BackboneTree.from_newick(a)
     assert len(t.leaf_ids) == 50 and t.nchild[t.num_nodes - 1] == 3
+
+
+def test_option_validation():
+    from apples_b200.options import options_config_run
+    with pytest.raises(ValueError):
+        options_config_run(['-d', 'x.mat', '-s', 'ref.fa', '-t', 't.nwk'])   # OptionsRun.py:90-91
+    with pytest.raises(ValueError):
+        options_config_run(['-q', 'q.fa'])                                     # OptionsRun.py:106-107
+    with pytest.raises(ValueError):
+        options_config_run(['-t', 't.nwk', '-q', 'q.fa', '-x', 'e.fa'])       # OptionsRun.py:108-109
+    o, _ = options_config_run(['-t', 't.nwk', '-q', 'q.fa', '-s', 'r.fa'])
+    assert (o.method_name, o.criterion_name, o.base_observation_threshold, o.filt_threshold,
+            o.minimum_alignment_overlap) == ('FM', 'MLSE', 25, 0.2, 0.001)
