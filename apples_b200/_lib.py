@@ -22,7 +22,7 @@ FLAG_PENDANT_INT0 = 0x100
 SYMBOLS = [
     'apples_words_per_row', 'apples_aa_row_bytes', 'apples_ctx_create', 'apples_ctx_destroy', 'apples_last_error',
     'apples_ctx_stream', 'apples_ctx_set_limits', 'apples_set_tree', 'apples_set_reference', 'apples_set_matrix_columns', 'apples_place_batch',
-    'apples_place_batch_matrix', 'apples_queries_upload', 'apples_place_resident', 'apples_results_download', 'apples_results_to_device',
+    'apples_place_batch_matrix', 'apples_set_reference_bytes', 'apples_place_batch_bytes', 'apples_queries_upload', 'apples_place_resident', 'apples_results_download', 'apples_results_to_device',
     'apples_distance_counts', 'apples_observed_sets', 'apples_edge_solutions', 'apples_get_timings',
 ]
 
@@ -63,6 +63,8 @@ def load():
     lib.apples_set_matrix_columns.argtypes = [vp, i32, vp]
     lib.apples_place_batch.argtypes = [vp, i64, vp, vp, C.POINTER(Params), vp, vp, vp, vp, vp]
     lib.apples_place_batch_matrix.argtypes = [vp, i64, vp, vp, C.POINTER(Params), vp, vp, vp, vp, vp]
+    lib.apples_set_reference_bytes.argtypes = [vp, C.c_int, i32, i32, vp, i64, vp, i32, vp, vp]
+    lib.apples_place_batch_bytes.argtypes = [vp, i64, vp, i64, vp, C.POINTER(Params), vp, vp, vp, vp, vp]
     lib.apples_queries_upload.argtypes = [vp, i64, vp, vp]
     lib.apples_place_resident.argtypes = [vp, C.POINTER(Params)]
     lib.apples_results_download.argtypes = [vp, vp, vp, vp, vp, vp]

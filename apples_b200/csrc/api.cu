@@ -45,6 +45,7 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
+    DevBuf q_bytes, bad_flag;
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
@@ -197,6 +198,8 @@ struct BatchIO {
     const void* h_queries = nullptr;   // host packed queries
     const void* d_queries = nullptr;   // device packed queries (resident)
     const double* h_rows = nullptr;    // host matrix rows
+    const uint8_t* h_bytes = nullptr;  // host alignment bytes (packed on the device)
+    int64_t byte_stride = 0;
     const int32_t* h_self = nullptr;
     const int32_t* d_self = nullptr;
     // outputs: host pointers or device pointers
@@ -241,6 +244,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
     if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
+    if (io.h_bytes) {
+        if (ensure(ctx, ctx->q_bytes, (size_t)QB * io.byte_stride) || ensure(ctx, ctx->bad_flag, 4)) return -1;
+        CK(cudaMemsetAsync(ctx->bad_flag.p, 0, 4, s));
+    }
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
@@ -367,6 +374,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 CK(cudaMemcpyAsync(ctx->q_rm.p, (const char*)io.h_queries + (size_t)(base0 + sb0) * qrow, (size_t)nb * qrow,
                                    cudaMemcpyHostToDevice, s));
                 d_q = ctx->q_rm.p;
+            } else if (io.h_bytes) {
+                CK(cudaMemcpyAsync(ctx->q_bytes.p, io.h_bytes + (size_t)(base0 + sb0) * io.byte_stride,
+                                   (size_t)nb * io.byte_stride, cudaMemcpyHostToDevice, s));
+                CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
+                               (int*)ctx->bad_flag.p, s));
+                ctx->n_launch += 1;
+                d_q = ctx->q_rm.p;
             } else {
                 d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
             }
@@ -385,6 +399,11 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     };
     if (fetch_counts()) return -1;
     CK(cudaStreamSynchronize(s));
+    if (io.h_bytes) {
+        int bad = 0;
+        CK(cudaMemcpy(&bad, ctx->bad_flag.p, 4, cudaMemcpyDeviceToHost));
+        if (bad) return fail(ctx, "query alignment contains bytes the 2-bit nucleotide packing cannot express (only A,C,G,T,-)");
+    }
 
     PlaceArgs pa{};
     pa.K = (const int*)ctx->Kd.p;
@@ -482,9 +501,15 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 CK(cudaMemcpyAsync((char*)ctx->keys.p + (size_t)j * qrow, io.h_rows + g * ctx->n_cols, qrow, cudaMemcpyHostToDevice, s));
             else if (io.h_queries)
                 CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.h_queries + g * qrow, qrow, cudaMemcpyHostToDevice, s));
+            else if (io.h_bytes)
+                CK(cudaMemcpyAsync((char*)ctx->q_bytes.p + (size_t)j * io.byte_stride, io.h_bytes + g * io.byte_stride,
+                                   (size_t)io.byte_stride, cudaMemcpyHostToDevice, s));
             else
                 CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.d_queries + g * qrow, qrow, cudaMemcpyDeviceToDevice, s));
         }
+        if (io.h_bytes)
+            CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
+                           (int*)ctx->bad_flag.p, s));
         SelectArgs sb = sa;
         sb.out_map = (const int*)ctx->qlist.p;
         sb.q_begin = 0;
@@ -626,7 +651,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -738,6 +763,87 @@ int apples_place_batch(apples_ctx* ctx, int64_t nq, const void* packed_queries, 
     io.h_self = self_node;
     io.edge = edge; io.error = error; io.distal = distal; io.pendant = pendant; io.status = status;
     return run_batch(ctx, nq, io, params);
+}
+
+int apples_place_batch_bytes(apples_ctx* ctx, int64_t nq, const uint8_t* bytes, int64_t row_stride,
+                             const int32_t* self_node, const apples_params* params, int32_t* edge, double* error,
+                             double* distal, double* pendant, int32_t* status) {
+    if (!ctx) return -1;
+    if (ctx->kind < 0) return fail(ctx, "apples_set_reference has not been called");
+    if (nq < 0 || (nq > 0 && (!bytes || row_stride < ctx->L || !edge || !error || !distal || !pendant || !status)))
+        return fail(ctx, "apples_place_batch_bytes: bad arguments");
+    BatchIO io;
+    io.h_bytes = bytes;
+    io.byte_stride = row_stride;
+    io.h_self = self_node;
+    io.edge = edge; io.error = error; io.distal = distal; io.pendant = pendant; io.status = status;
+    return run_batch(ctx, nq, io, params);
+}
+
+int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, const uint8_t* ref_bytes,
+                               int64_t row_stride, const int32_t* ref_node, int32_t n_rep, const int32_t* group_offsets,
+                               const int32_t* group_members) {
+    if (!ctx) return -1;
+    if ((kind != APPLES_NUC && kind != APPLES_AA) || L <= 0 || n_ref <= 0 || n_rep <= 0 || !ref_bytes || row_stride < L ||
+        !ref_node || !group_offsets || !group_members)
+        return fail(ctx, "apples_set_reference_bytes: bad arguments");
+    if (kind == APPLES_NUC && L > 65535) return fail(ctx, "nucleotide alignments longer than 65535 columns are not supported");
+    for (int i = 0; i < n_rep; ++i)
+        if (group_offsets[i + 1] < group_offsets[i]) return fail(ctx, "apples_set_reference_bytes: group_offsets not monotone");
+    const int n_mem = group_offsets[n_rep];
+    for (int i = 0; i < n_mem; ++i)
+        if (group_members[i] < 0 || group_members[i] >= n_ref) return fail(ctx, "apples_set_reference_bytes: member out of range");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    ctx->kind = kind;
+    ctx->L = L;
+    ctx->n_ref = n_ref;
+    ctx->n_rep = n_rep;
+    ctx->W = apples_words_per_row(L);
+    ctx->Wp = round_up(ctx->W, DT_WC);
+    ctx->Lp = apples_aa_row_bytes(L);
+    ctx->rep_pad = round_up(n_rep, DT_TR);
+    ctx->ref_pad = round_up(n_ref, DT_TR);
+    ctx->refs_wm_ready = false;
+    const size_t row = query_row_bytes(ctx);
+    DevBuf d_bytes, d_rep_bytes;
+    auto cleanup = [&]() { release(d_bytes); release(d_rep_bytes); };
+    if (ensure(ctx, ctx->refs_rm, (size_t)n_ref * row) || ensure(ctx, ctx->reps_rm, (size_t)n_rep * row) ||
+        ensure(ctx, ctx->ref_node, (size_t)n_ref * 4) || ensure(ctx, ctx->goff, (size_t)(n_rep + 1) * 4) ||
+        ensure(ctx, ctx->gmem, (size_t)std::max(n_mem, 1) * 4) || ensure(ctx, ctx->bad_flag, 4) ||
+        ensure(ctx, d_bytes, (size_t)n_ref * row_stride) || ensure(ctx, d_rep_bytes, (size_t)n_rep * L)) {
+        cleanup();
+        return -1;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_bytes.p, ref_bytes, (size_t)n_ref * row_stride, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->ref_node.p, ref_node, (size_t)n_ref * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->goff.p, group_offsets, (size_t)(n_rep + 1) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n_mem) e = cudaMemcpyAsync(ctx->gmem.p, group_members, (size_t)n_mem * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->bad_flag.p, 0, 4, s);
+    // (f2) consensus representatives, then (f1) packing of references and representatives
+    if (e == cudaSuccess) e = launch_consensus(kind, (const uint8_t*)d_bytes.p, row_stride, L, n_rep, (const int*)ctx->goff.p,
+                                               (const int*)ctx->gmem.p, (uint8_t*)d_rep_bytes.p, L, s);
+    if (e == cudaSuccess) e = launch_pack(kind, (const uint8_t*)d_bytes.p, row_stride, n_ref, L, ctx->refs_rm.p, (int*)ctx->bad_flag.p, s);
+    if (e == cudaSuccess) e = launch_pack(kind, (const uint8_t*)d_rep_bytes.p, L, n_rep, L, ctx->reps_rm.p, (int*)ctx->bad_flag.p, s);
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, ctx->bad_flag.p, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, "apples_set_reference_bytes: %s", cudaGetErrorString(e));
+    if (bad) {
+        ctx->kind = -1;
+        return fail(ctx, "reference alignment contains bytes the 2-bit nucleotide packing cannot express (only A,C,G,T,-)");
+    }
+    if (kind == APPLES_NUC) {
+        const size_t wm = (size_t)3 * ctx->Wp * ctx->rep_pad * 4;
+        if (ensure(ctx, ctx->reps_wm, wm)) return -1;
+        CK(cudaMemsetAsync(ctx->reps_wm.p, 0, wm, s));
+        launch_transpose_nuc((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_wm.p, ctx->Wp,
+                             ctx->rep_pad, s);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(s));
+    }
+    return 0;
 }
 
 int apples_place_batch_matrix(apples_ctx* ctx, int64_t nq, const double* rows, const int32_t* self_node,

@@ -70,9 +70,18 @@ class GpuPlacer:
     def stream(self):
         return self.lib.apples_ctx_stream(self.h)
 
-    def set_reference(self, reference):
-        d = reference.device_arrays(self.name_to_node)
-        self.set_reference_arrays(**d)
+    def set_reference(self, reference, on_device=True):
+        """on_device: ship the raw alignment bytes and let the device pack them and build the consensus
+        representatives; otherwise pack / build on the host with numpy."""
+        if on_device and hasattr(reference, 'device_arrays_bytes'):
+            d = reference.device_arrays_bytes(self.name_to_node)
+            self.kind, self.L, self.ref_names = d['kind'], int(d['L']), d['ref_names']
+            rb, rn, go, gm = d['ref_bytes'], d['ref_node'], d['group_offsets'], d['group_members']
+            self._check(self.lib.apples_set_reference_bytes(self.h, self.kind, self.L, rb.shape[0], _lib.ptr(rb),
+                                                            rb.shape[1], _lib.ptr(rn), len(go) - 1, _lib.ptr(go),
+                                                            _lib.ptr(gm)))
+        else:
+            self.set_reference_arrays(**reference.device_arrays(self.name_to_node))
         self.reference = reference
 
     def set_reference_arrays(self, kind, L, ref_names, packed_refs, ref_node, packed_reps, group_offsets, group_members):
@@ -118,6 +127,17 @@ class GpuPlacer:
         packed = np.ascontiguousarray(packed)
         self._check(self.lib.apples_place_batch(self.h, nq, _lib.ptr(packed), _lib.ptr(self_node), _lib.C.byref(params),
                                                 *[_lib.ptr(o) for o in out]))
+        return out
+
+    def place_bytes(self, mat, self_node, params):
+        """alignment bytes uint8 [nq, L] (host) -> result arrays; packing happens on the device."""
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        if mat.shape[1] != self.L:
+            raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], self.L))
+        nq = int(mat.shape[0])
+        out = self._outputs(nq)
+        self._check(self.lib.apples_place_batch_bytes(self.h, nq, _lib.ptr(mat), mat.shape[1], _lib.ptr(self_node),
+                                                      _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
         return out
 
     def place_rows(self, rows, self_node, params):
@@ -265,8 +285,8 @@ def place_batch(reference, options, name_to_node_map, queries, tree=None, placer
                         rows[i, col[t]] = v
             out = placer.place_rows(rows, self_node, params)
         else:
-            packed = placer.pack_queries([q[1] for q in queries])
-            out = placer.place_packed(packed, self_node, params)
+            mat = _fasta.as_byte_matrix([q[1] for q in queries], placer.L)
+            out = placer.place_bytes(mat, self_node, params)
         return results_to_jplace(names, in_backbone, out, getattr(options, 'exclude_intplace', False))
     finally:
         if own:

@@ -64,19 +64,33 @@ class ReducedReference:
             clusters = _tc.read_cluster_tsv(tmp)
             os.unlink(tmp)
         logging.info('[%s] Clustering is completed in %.3f seconds.' % (time.strftime('%H:%M:%S'), time.time() - start))
-        start = time.time()
-        self.representatives = []
+        # member lists in `representatives` order (Reference.py:101-107): singletons ('-1') are their own cluster
+        self.groups = []
         for key, group in clusters:
             group = [g for g in group if g in self.refs]
             if not group:
                 continue
             if key == '-1':
-                self.representatives.extend((self.refs[g], [g]) for g in group)
+                self.groups.extend([g] for g in group)
             else:
-                mat = np.vstack([self.refs[g].view(np.uint8) for g in group])
-                self.representatives.append((consensus_rows(mat, self.prot_flag).view('S1'), group))
-        logging.info('[%s] Representative sequences are computed in %.3f seconds.'
-                     % (time.strftime('%H:%M:%S'), time.time() - start))
+                self.groups.append(group)
+        self._representatives = None
+
+    @property
+    def representatives(self):
+        """[(consensus 'S1' row, [member names])] like the reference's attribute.  Computed on the host on first use
+        (tests, pickled databases); the placement path computes the consensus rows on the device instead
+        (apples_set_reference_bytes)."""
+        if self._representatives is None:
+            reps = []
+            for group in self.groups:
+                if len(group) == 1:
+                    reps.append((self.refs[group[0]], group))
+                else:
+                    mat = np.vstack([self.refs[g].view(np.uint8) for g in group])
+                    reps.append((consensus_rows(mat, self.prot_flag).view('S1'), group))
+            self._representatives = reps
+        return self._representatives
 
     def set_baseobs(self, baseobs):
         self.baseobs = baseobs
@@ -86,6 +100,21 @@ class ReducedReference:
                            'there is no CPU path in this package')
 
     # ---------------------------------------------------------------- device layout
+    def device_arrays_bytes(self, name_to_node):
+        """Inputs of apples_set_reference_bytes: raw alignment bytes + cluster CSR (packing and consensus on the device)."""
+        names = list(self.refs.keys())
+        row_of = {n: i for i, n in enumerate(names)}
+        L = len(self.refs[names[0]]) if names else 0
+        offs = np.zeros(len(self.groups) + 1, dtype=np.int32)
+        members = []
+        for i, group in enumerate(self.groups):
+            members.extend(row_of[g] for g in group)
+            offs[i + 1] = len(members)
+        return dict(kind=_fasta.AA if self.prot_flag else _fasta.NUC, L=L, ref_names=names,
+                    ref_bytes=_fasta.as_byte_matrix([self.refs[n] for n in names], L),
+                    ref_node=np.array([name_to_node.get(n, -1) for n in names], dtype=np.int32),
+                    group_offsets=offs, group_members=np.asarray(members, dtype=np.int32))
+
     def device_arrays(self, name_to_node):
         """Packed arrays for apples_set_reference (include/apples_b200.h).
 

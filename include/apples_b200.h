@@ -96,6 +96,18 @@ int apples_place_batch(apples_ctx* ctx, int64_t nq, const void* packed_queries, 
                        const apples_params* params, int32_t* edge, double* error, double* distal, double* pendant,
                        int32_t* status);
 
+/* the same two calls fed with ALIGNMENT BYTES as fasta2dic leaves them
+ * (fasta2dic.py:42-72: upper-case letters, '-' for gaps and for letters outside the alphabet), uint8[rows][row_stride]
+ * with the first L bytes of every row used.  Packing into the device layout and the per-cluster consensus
+ * representatives (PoolRepresentativeWorker.py:30-85: column-wise majority in alphabet order, first maximum wins) are
+ * computed on the device.  Nucleotide bytes other than A,C,G,T,- are an error. */
+int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, const uint8_t* ref_bytes,
+                               int64_t row_stride, const int32_t* ref_node, int32_t n_rep, const int32_t* group_offsets,
+                               const int32_t* group_members);
+int apples_place_batch_bytes(apples_ctx* ctx, int64_t nq, const uint8_t* bytes, int64_t row_stride,
+                             const int32_t* self_node, const apples_params* params, int32_t* edge, double* error,
+                             double* distal, double* pendant, int32_t* status);
+
 /* The hot path, distance-matrix input: rows is double[nq][n_cols] (run_apples.py:43-54). */
 int apples_place_batch_matrix(apples_ctx* ctx, int64_t nq, const double* rows, const int32_t* self_node,
                               const apples_params* params, int32_t* edge, double* error, double* distal,

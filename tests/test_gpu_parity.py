@@ -386,3 +386,40 @@ def test_tiny_tree_and_all_singletons(workdir):
         for q, r in zip(qs, res):
             exp, _ = octx.runquery(q[0], q[1], None)
             _check_p('tiny', q[0], r['placements'][0]['p'][0], exp['placements'][0]['p'][0], False, octx, q)
+
+
+@pytest.mark.parametrize('case', ['c1_align_FM_MLSE', 'syn300_OLS_MLSE_pos', 'c3_prot_FM_MLSE'])
+def test_device_packer_and_consensus(case, workdir):
+    """packing and consensus representatives on the device give the same placements, observed sets
+    and counts as the host numpy packer / consensus (which the CPU suite checks against the reference's own)."""
+    from apples_b200 import fasta
+    from apples_b200.placer import GpuPlacer
+    ci = util.CaseInputs(case, workdir)
+    tree, ref = ci.product_state()
+    params = GpuPlacer.params_from_options(ci.options)
+    a = GpuPlacer(tree, None, tree.name_to_node, device=0)
+    a.set_reference(ref, on_device=False)
+    b = GpuPlacer(tree, None, tree.name_to_node, device=0)
+    b.set_reference(ref, on_device=True)
+    seqs = [q[1] for q in ci.queries]
+    names = [q[0] for q in ci.queries]
+    sn = a.self_nodes(names)
+    ra = a.place_packed(a.pack_queries(seqs), sn, params)
+    rb = b.place_bytes(fasta.as_byte_matrix(seqs, b.L), sn, params)
+    for x, y in zip(ra, rb):
+        assert (x == y).all()
+    ca = a.distance_counts(a.pack_queries(seqs[:4]))
+    cb = b.distance_counts(b.pack_queries(seqs[:4]))
+    for x, y in zip(ca, cb):
+        assert (x == y).all()
+    oa = a.observed_sets(params, packed=a.pack_queries(seqs), self_node=sn, cap=2048)
+    ob = b.observed_sets(params, packed=b.pack_queries(seqs), self_node=sn, cap=2048)
+    for x, y in zip(oa, ob):
+        assert (x == y).all()
+    if not ci.protein:
+        bad = fasta.as_byte_matrix(seqs[:2], b.L).copy()
+        bad[1, 7] = ord('.')
+        with pytest.raises(RuntimeError):
+            b.place_bytes(bad, None, params)
+    a.close()
+    b.close()
