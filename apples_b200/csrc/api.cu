@@ -31,6 +31,8 @@ struct apples_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // host->device staging of the next sub-batch overlaps compute
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     std::string err;
 
     // tree
@@ -45,7 +47,7 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
-    DevBuf q_bytes, bad_flag;
+    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag;
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
@@ -117,14 +119,15 @@ cudaEvent_t get_event(apples_ctx* ctx) {
 struct Span {
     apples_ctx* ctx;
     TimedSpan s;
-    Span(apples_ctx* c, int stage) : ctx(c) {
+    cudaStream_t st;
+    Span(apples_ctx* c, int stage, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
         s.stage = stage;
         s.a = get_event(c);
         s.b = get_event(c);
-        cudaEventRecord(s.a, c->stream);
+        cudaEventRecord(s.a, st);
     }
     ~Span() {
-        cudaEventRecord(s.b, ctx->stream);
+        cudaEventRecord(s.b, st);
         ctx->spans.push_back(s);
     }
 };
@@ -244,10 +247,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
     if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
+    const bool two_bufs = n > QB;  // more than one sub-batch: stage the next one while this one computes
     if (io.h_bytes) {
         if (ensure(ctx, ctx->q_bytes, (size_t)QB * io.byte_stride) || ensure(ctx, ctx->bad_flag, 4)) return -1;
+        if (two_bufs && ensure(ctx, ctx->q_bytes2, (size_t)QB * io.byte_stride)) return -1;
         CK(cudaMemsetAsync(ctx->bad_flag.p, 0, 4, s));
     }
+    if (io.h_queries && two_bufs && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
@@ -362,31 +368,56 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.obs_dist = (double*)ctx->obs_dist.p;
     sa.obs_len = (int*)ctx->obs_len.p;
     sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
-    for (int sb0 = 0; sb0 < n; sb0 += QB) {
+    bool used[2] = {false, false};
+    int sbi = 0;
+    for (int sb0 = 0; sb0 < n; sb0 += QB, ++sbi) {
         const int nb = std::min(QB, n - sb0);
         const void* d_q = nullptr;
-        {
+        const int buf = two_bufs ? (sbi & 1) : 0;
+        if (matrix) {
             Span sp(ctx, T_H2D);
-            if (matrix) {
-                CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)(base0 + sb0) * ctx->n_cols, (size_t)nb * qrow,
-                                   cudaMemcpyHostToDevice, s));
-            } else if (io.h_queries) {
-                CK(cudaMemcpyAsync(ctx->q_rm.p, (const char*)io.h_queries + (size_t)(base0 + sb0) * qrow, (size_t)nb * qrow,
-                                   cudaMemcpyHostToDevice, s));
-                d_q = ctx->q_rm.p;
-            } else if (io.h_bytes) {
-                CK(cudaMemcpyAsync(ctx->q_bytes.p, io.h_bytes + (size_t)(base0 + sb0) * io.byte_stride,
-                                   (size_t)nb * io.byte_stride, cudaMemcpyHostToDevice, s));
-                CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
+            CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)(base0 + sb0) * ctx->n_cols, (size_t)nb * qrow,
+                               cudaMemcpyHostToDevice, s));
+        } else if (io.h_queries || io.h_bytes) {
+            // staged on the copy stream into one of two buffers; the compute stream waits for the copy, the copy
+            // stream waits until the compute stream has finished with the buffer's previous contents
+            cudaStream_t cs = ctx->copy_stream;
+            if (used[buf]) CK(cudaStreamWaitEvent(cs, ctx->ev_free[buf], 0));
+            else if (sbi == 0) {
+                // order after whatever the compute stream did before (buffer (re)allocation is synchronous already)
+                CK(cudaEventRecord(ctx->ev_free[buf], s));
+                CK(cudaStreamWaitEvent(cs, ctx->ev_free[buf], 0));
+            }
+            void* stage;
+            {
+                Span sp(ctx, T_H2D, cs);
+                if (io.h_queries) {
+                    stage = buf ? ctx->q_rm2.p : ctx->q_rm.p;
+                    CK(cudaMemcpyAsync(stage, (const char*)io.h_queries + (size_t)(base0 + sb0) * qrow, (size_t)nb * qrow,
+                                       cudaMemcpyHostToDevice, cs));
+                } else {
+                    stage = buf ? ctx->q_bytes2.p : ctx->q_bytes.p;
+                    CK(cudaMemcpyAsync(stage, io.h_bytes + (size_t)(base0 + sb0) * io.byte_stride,
+                                       (size_t)nb * io.byte_stride, cudaMemcpyHostToDevice, cs));
+                }
+            }
+            CK(cudaEventRecord(ctx->ev_ready[buf], cs));
+            CK(cudaStreamWaitEvent(s, ctx->ev_ready[buf], 0));
+            if (io.h_bytes) {
+                CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
                                (int*)ctx->bad_flag.p, s));
                 ctx->n_launch += 1;
                 d_q = ctx->q_rm.p;
             } else {
-                d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
+                d_q = stage;
             }
+            used[buf] = true;
+        } else {
+            d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
         }
         sa.q_begin = sb0;
         if (distances_and_select(d_q, nb, sa)) return -1;
+        if (used[buf]) CK(cudaEventRecord(ctx->ev_free[buf], s));
     }
 
     // ---------------- phase 2 ----------------
@@ -635,6 +666,15 @@ int apples_ctx_create(int device, apples_ctx** out) {
         delete ctx;
         return -4;
     }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return -4;
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
+    }
     if (dense_nuc_configure() != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -651,7 +691,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -662,6 +702,11 @@ void apples_ctx_destroy(apples_ctx* ctx) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+        if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

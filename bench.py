@@ -267,14 +267,19 @@ def main():
     # ---- end to end through the C-ABI call with host buffers ----
     e2e = None
     if not args.no_e2e:
+        # the reference-facing call: aligned query BYTES in (pinned) host memory, as fasta2dic leaves them; packing
+        # happens on the device, host<->device copies are inside the timed region
         self_node = None
+        bytes_host = torch.empty(q_bytes.shape, dtype=torch.uint8).pin_memory()
+        bytes_host.copy_(q_bytes)
+        bytes_np = bytes_host.numpy()
         for _ in range(min(args.warmup, 1)):
-            pl.place_packed(packed_host.numpy(), self_node, params)
+            pl.place_bytes(bytes_np, self_node, params)
         barrier()
         e0.record(stream)
         t0 = time.time()
         for _ in range(args.steps):
-            out = pl.place_packed(packed_host.numpy(), self_node, params)
+            out = pl.place_bytes(bytes_np, self_node, params)
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
@@ -283,7 +288,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {'value': nq * world * args.steps / (ems / 1e3), 'unit': 'queries/s',
-               'h2d_bytes_per_step': int(packed_host.numel() * 4), 'd2h_bytes_per_step': int(nq * 36),
+               'h2d_bytes_per_step': int(bytes_host.numel()), 'd2h_bytes_per_step': int(nq * 32),
+               'input': 'alignment bytes (uint8 per site) in pinned host memory, packed on the device',
                'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps}
         pl.timings(reset=True)
 
