@@ -511,66 +511,81 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     };
 
     // ---------------- overflow reruns: observed set larger than the slot capacity (rare) ----------------
+    // the selection kernel stops a query as soon as it exceeds its slot; it is rerun with a 16x larger slot (256 ->
+    // 4096 -> 65536 -> all leaves) until it fits
+    std::vector<char> is_over(n, 0);
     std::vector<int> over;
     for (int i = 0; i < n; ++i)
-        if (hS[i] == ST_OVERFLOW) over.push_back(i);
-    std::vector<char> is_over(n, 0);
-    for (int g : over) is_over[g] = 1;
-    for (size_t o0 = 0; o0 < over.size(); o0 += QB) {
-        const int ng = (int)std::min<size_t>(QB, over.size() - o0);
-        int maxK = 0;
-        for (int j = 0; j < ng; ++j) maxK = std::max(maxK, hK[over[o0 + j]]);
-        const int cap2 = next_pow2(maxK);
-        if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
-        if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
-        if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
-        if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
-        CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
-        for (int j = 0; j < ng; ++j) {  // gather the rows of the overflowing queries
-            const size_t g = (size_t)base0 + over[o0 + j];
-            if (matrix)
-                CK(cudaMemcpyAsync((char*)ctx->keys.p + (size_t)j * qrow, io.h_rows + g * ctx->n_cols, qrow, cudaMemcpyHostToDevice, s));
-            else if (io.h_queries)
-                CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.h_queries + g * qrow, qrow, cudaMemcpyHostToDevice, s));
-            else if (io.h_bytes)
-                CK(cudaMemcpyAsync((char*)ctx->q_bytes.p + (size_t)j * io.byte_stride, io.h_bytes + g * io.byte_stride,
-                                   (size_t)io.byte_stride, cudaMemcpyHostToDevice, s));
-            else
-                CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.d_queries + g * qrow, qrow, cudaMemcpyDeviceToDevice, s));
+        if (hS[i] == ST_OVERFLOW) {
+            over.push_back(i);
+            is_over[i] = 1;
         }
-        if (io.h_bytes)
-            CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
-                           (int*)ctx->bad_flag.p, s));
-        SelectArgs sb = sa;
-        sb.out_map = (const int*)ctx->qlist.p;
-        sb.q_begin = 0;
-        sb.cap = cap2;
-        sb.obs_node = (int*)ctx->obs_node2.p;
-        sb.obs_dist = (double*)ctx->obs_dist2.p;
-        sb.obs_len = (int*)ctx->obs_len2.p;
-        sb.pair_counter = nullptr;
-        if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
-        if (fetch_counts()) return -1;
-        CK(cudaStreamSynchronize(s));
-        if (io.obs_count) {
-            std::vector<int> un((size_t)ng * cap2);
-            std::vector<double> ud((size_t)ng * cap2);
-            CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
-            for (int j = 0; j < ng; ++j) {
-                const int i = over[o0 + j];
-                const int k = std::min(hK[i], io.obs_cap);
-                memcpy(io.obs_node + (size_t)(base0 + i) * io.obs_cap, &un[(size_t)j * cap2], (size_t)k * 4);
-                memcpy(io.obs_dist + (size_t)(base0 + i) * io.obs_cap, &ud[(size_t)j * cap2], (size_t)k * 8);
+    ctx->n_over += (double)over.size();
+    int cap2 = cap;
+    const int cap_max = next_pow2(std::max(4, n_leaf_bound));
+    while (!over.empty()) {
+        cap2 = (int)std::min<int64_t>((int64_t)cap2 * 16, cap_max);
+        // queries per rerun launch: bounded by the sub-batch size and by 2 GiB of slots
+        const int GB = (int)std::max<int64_t>(1, std::min<int64_t>(QB, ((int64_t)2 << 30) / ((int64_t)cap2 * 16)));
+        std::vector<int> still;
+        for (size_t o0 = 0; o0 < over.size(); o0 += GB) {
+            const int ng = (int)std::min<size_t>(GB, over.size() - o0);
+            if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
+            if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
+            if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
+            if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
+            CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
+            for (int j = 0; j < ng; ++j) {  // gather the rows of the overflowing queries
+                const size_t g = (size_t)base0 + over[o0 + j];
+                if (matrix)
+                    CK(cudaMemcpyAsync((char*)ctx->keys.p + (size_t)j * qrow, io.h_rows + g * ctx->n_cols, qrow, cudaMemcpyHostToDevice, s));
+                else if (io.h_queries)
+                    CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.h_queries + g * qrow, qrow, cudaMemcpyHostToDevice, s));
+                else if (io.h_bytes)
+                    CK(cudaMemcpyAsync((char*)ctx->q_bytes.p + (size_t)j * io.byte_stride, io.h_bytes + g * io.byte_stride,
+                                       (size_t)io.byte_stride, cudaMemcpyHostToDevice, s));
+                else
+                    CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.d_queries + g * qrow, qrow, cudaMemcpyDeviceToDevice, s));
             }
-        }
-        if (!io.stop_after_select) {
-            const int* ov = over.data() + o0;
-            if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, (const int*)ctx->qlist.p, cap2,
-                              (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
-                return -1;
+            if (io.h_bytes)
+                CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
+                               (int*)ctx->bad_flag.p, s));
+            SelectArgs sb = sa;
+            sb.out_map = (const int*)ctx->qlist.p;
+            sb.q_begin = 0;
+            sb.cap = cap2;
+            sb.obs_node = (int*)ctx->obs_node2.p;
+            sb.obs_dist = (double*)ctx->obs_dist2.p;
+            sb.obs_len = (int*)ctx->obs_len2.p;
+            sb.pair_counter = nullptr;
+            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
+            if (fetch_counts()) return -1;
             CK(cudaStreamSynchronize(s));
+            if (io.obs_count) {
+                std::vector<int> un((size_t)ng * cap2);
+                std::vector<double> ud((size_t)ng * cap2);
+                CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
+                for (int j = 0; j < ng; ++j) {
+                    const int i = over[o0 + j];
+                    if (hS[i] == ST_OVERFLOW) continue;
+                    const int k = std::min(hK[i], io.obs_cap);
+                    memcpy(io.obs_node + (size_t)(base0 + i) * io.obs_cap, &un[(size_t)j * cap2], (size_t)k * 4);
+                    memcpy(io.obs_dist + (size_t)(base0 + i) * io.obs_cap, &ud[(size_t)j * cap2], (size_t)k * 8);
+                }
+            }
+            if (!io.stop_after_select) {
+                const int* ov = over.data() + o0;
+                if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, (const int*)ctx->qlist.p, cap2,
+                                  (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
+                    return -1;
+                CK(cudaStreamSynchronize(s));
+            }
+            for (int j = 0; j < ng; ++j)
+                if (hS[over[o0 + j]] == ST_OVERFLOW) still.push_back(over[o0 + j]);
         }
+        if (cap2 >= cap_max && !still.empty()) return fail(ctx, "internal error: observed set larger than the number of leaves");
+        over.swap(still);
     }
 
     // ---------------- parity export of the observed sets ----------------
@@ -588,7 +603,6 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             memcpy(io.obs_dist + (size_t)(base0 + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
         }
     }
-    ctx->n_over += (double)over.size();
     for (int i = 0; i < n; ++i)
         if (hS[i] == ST_PLACE) {
             ctx->n_obs += hK[i];

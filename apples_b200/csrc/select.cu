@@ -265,7 +265,7 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
         if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-            for (int x = b; x < e; x += 2) {
+            for (int x = b; x < e && st.kcount <= a.cap; x += 2) {  // past the slot capacity the query is rerun anyway
                 const int row0 = a.gmem[x];
                 const int row1 = (x + 1 < e) ? a.gmem[x + 1] : row0;
                 uint32_t c0, c1;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
                 if (x + 1 < e) observe_nuc_counts(a, st, slot, self, row1, c1, ukey, x + 1 - b, lane);
             }
         } else {
-            for (int x = b; x < e; ++x) {
+            for (int x = b; x < e && st.kcount <= a.cap; ++x) {
                 const int row = a.gmem[x];
                 const double d = member_dist_aa(a, a.q_aa + (size_t)q * a.Lp, row, lane);
                 if (!(d < 0.0)) observe<KIND>(a, st, slot, self, a.ref_node[row], d, d == 0.0, ukey, x - b, lane);  // Reference.py:150
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
     constexpr int U = 8;  // independent key loads in flight per lane (the scan is latency-bound otherwise)
     Key<KIND> lmin;       // smallest far key among the units u with u % 32 == lane
     bool have_lmin = false;
-    for (int u0 = 0; u0 < a.n_units; u0 += 32 * U) {
+    for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * U) {
         typename RawT<KIND>::T raw[U];
         int cls[U];
 #pragma unroll
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
                     }
                     any |= nearm[j] != 0u;
                 }
-                for (int t = 0; t < qn; ++t) {
+                for (int t = 0; t < qn && st.kcount <= a.cap; ++t) {
                     const Key<KIND> uk = key_shfl(qkey, t);
                     expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
                 }
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
         }
     }
     // ---- far units in ascending (distance, index) order while obs_num < baseobs (Reference.py:146) ----
-    while (st.obs_num < a.baseobs) {
+    while (st.obs_num < a.baseobs && st.kcount <= a.cap) {
         // warp-wide minimum of the lane minima
         Key<KIND> g = lmin;
         int owner = have_lmin ? lane : -1;
@@ -431,12 +431,12 @@ __global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
     // ---- PoolQueryWorker.runquery:72-98 ----
     int status = ST_PLACE;
     int V = 0;
-    if (st.has_zero) {
+    if (st.kcount > a.cap) {
+        status = ST_OVERFLOW;  // the scan was cut short: rerun with a larger slot (the host escalates the capacity)
+    } else if (st.has_zero) {
         status = ST_ZERO;
     } else if (st.kcount <= 2) {
         status = ST_TOO_FEW;
-    } else if (st.kcount > a.cap) {
-        status = ST_OVERFLOW;
     } else {
         int* node = a.obs_node + (size_t)oslot * a.cap;
         double* dist = a.obs_dist + (size_t)oslot * a.cap;
