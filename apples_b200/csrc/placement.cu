@@ -25,6 +25,7 @@
 #include "common.cuh"
 
 #define FULLMASK 0xffffffffu
+constexpr int PL_HIST = 1024;  // attach-level buckets per warp in shared memory
 
 __device__ __forceinline__ void leaf_moments(int method, double D, double* m) {
     m[1] = 0.0; m[2] = 0.0; m[4] = 0.0;
@@ -220,43 +221,96 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a) {
     }
     __syncwarp();
 
-    // ---------------- S moments: level by level from the deepest level up (children before parents) ----------------
-    for (int lv = maxlev - 1; lv > rootlev; --lv) {
-        for (int i = lane; i < K; i += 32) {
-            const int al = ch[i].A, ll = ch[i].last;
-            if (al < lv && lv < ll) {
-                NodeRec& r = rec[ch[i].first + (ll - lv)];
-                const double coef = BME ? 1.0 / (double)r.nchild : 1.0;   // BME.py:19
-                double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                for (int c = r.fchild; c >= 0; c = rec[c].rsib) accumulate<BME>(acc, rec[c].S, rec[c].len, coef);
+    // ---------------- S and R moments ----------------
+    // A chain only depends on chains with a DEEPER attach level (the chains hanging from its nodes) for S, and on the
+    // one chain with a shallower attach level that owns the node it hangs from for R.  So chains are bucketed by attach
+    // level (counting sort in shared memory); S walks the buckets from the deepest level up, R from the shallowest
+    // down, and inside a bucket every lane owns whole chains (sequential along the chain, which is what the recursion
+    // is anyway).  Work is O(V + K) instead of O(levels x K).  Trees deeper than PL_HIST levels below the MRCA fall
+    // back to a level-by-level sweep.
+    auto s_node = [&](int p) {
+        NodeRec& r = rec[p];
+        const double coef = BME ? 1.0 / (double)r.nchild : 1.0;   // BME.py:19
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int c = r.fchild; c >= 0; c = rec[c].rsib) accumulate<BME>(acc, rec[c].S, rec[c].len, coef);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) r.S[k] = acc[k];
-            }
-        }
-        __syncwarp();
-    }
-
-    // ---------------- R moments: level by level down (parents before children) ----------------
+        for (int k = 0; k < 6; ++k) r.S[k] = acc[k];
+    };
     // all_R_values: siblings in child order, then the parent's R shifted by the parent's edge unless the parent is
     // the subtree root (FM.py:53-76); BME: coefficient 1 / (nonroot + #valid siblings) (BME.py:36-37)
-    for (int lv = rootlev + 1; lv <= maxlev; ++lv) {
-        for (int i = lane; i < K; i += 32) {
-            const int al = ch[i].A, ll = ch[i].last;
-            if (al < lv && lv <= ll) {
-                const int p = ch[i].first + (ll - lv);
-                NodeRec& r = rec[p];
-                const int P = r.par;
-                const bool nonroot = P < V;
-                const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + rec[P].nchild - 1) : 1.0;
-                double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-                for (int s = rec[P].fchild; s >= 0; s = rec[s].rsib)
-                    if (s != p) accumulate<BME>(acc, rec[s].S, rec[s].len, coef);
-                if (nonroot) accumulate<BME>(acc, rec[P].R, rec[P].len, coef);
+    auto r_node = [&](int p) {
+        NodeRec& r = rec[p];
+        const int P = r.par;
+        const bool nonroot = P < V;
+        const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + rec[P].nchild - 1) : 1.0;
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int sb = rec[P].fchild; sb >= 0; sb = rec[sb].rsib)
+            if (sb != p) accumulate<BME>(acc, rec[sb].S, rec[sb].len, coef);
+        if (nonroot) accumulate<BME>(acc, rec[P].R, rec[P].len, coef);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) r.R[k] = acc[k];
+        for (int k = 0; k < 6; ++k) r.R[k] = acc[k];
+    };
+    const int range = maxlev - rootlev;  // attach levels lie in [rootlev, maxlev - 1]
+    if (range <= PL_HIST) {
+        __shared__ int s_hist[4][PL_HIST + 1];
+        int* h = s_hist[threadIdx.x >> 5];
+        for (int x = lane; x <= range; x += 32) h[x] = 0;
+        __syncwarp();
+        for (int i = lane; i < K; i += 32) atomicAdd(&h[ch[i].A - rootlev], 1);
+        __syncwarp();
+        {   // exclusive prefix sum over h[0 .. range): every lane owns a contiguous segment
+            const int seg = (range + 31) / 32, b = min(range, lane * seg), e = min(range, b + seg);
+            int sum = 0;
+            for (int x = b; x < e; ++x) sum += h[x];
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULLMASK, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int run = incl - sum;
+            for (int x = b; x < e; ++x) {
+                const int c = h[x];
+                h[x] = run;
+                run += c;
             }
         }
         __syncwarp();
+        for (int i = lane; i < K; i += 32) ch[atomicAdd(&h[ch[i].A - rootlev], 1)].n = i;  // h[x] becomes the bucket END
+        __syncwarp();
+        for (int x = range - 1; x >= 0; --x) {          // S: deepest attach level first
+            const int b = x ? h[x - 1] : 0, e = h[x];
+            for (int k = b + lane; k < e; k += 32) {
+                const int i = ch[k].n;
+                const int off = ch[i].first, len = ch[i].last - ch[i].A;
+                for (int sdx = 1; sdx < len; ++sdx) s_node(off + sdx);
+            }
+            if (b != e) __syncwarp();
+        }
+        for (int x = 0; x < range; ++x) {               // R: shallowest attach level first, each chain top-down
+            const int b = x ? h[x - 1] : 0, e = h[x];
+            for (int k = b + lane; k < e; k += 32) {
+                const int i = ch[k].n;
+                const int off = ch[i].first, len = ch[i].last - ch[i].A;
+                for (int sdx = len - 1; sdx >= 0; --sdx) r_node(off + sdx);
+            }
+            if (b != e) __syncwarp();
+        }
+    } else {
+        for (int lv = maxlev - 1; lv > rootlev; --lv) {  // S: level by level upwards
+            for (int i = lane; i < K; i += 32) {
+                const int al = ch[i].A, ll = ch[i].last;
+                if (al < lv && lv < ll) s_node(ch[i].first + (ll - lv));
+            }
+            __syncwarp();
+        }
+        for (int lv = rootlev + 1; lv <= maxlev; ++lv) {  // R: level by level downwards
+            for (int i = lane; i < K; i += 32) {
+                const int al = ch[i].A, ll = ch[i].last;
+                if (al < lv && lv <= ll) r_node(ch[i].first + (ll - lv));
+            }
+            __syncwarp();
+        }
     }
 
     // ---------------- per-edge closed-form solve + criterion selection (first minimum in post-order) ----------------
