@@ -153,37 +153,41 @@ __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_MATRI
 }
 
 // ---- member distances (warp-cooperative) ----------------------------------------------------------------------
-// packed (mismatch | valid << 16) counts of the query against TWO reference rows at once (independent loads in
-// flight); every lane returns the same totals
-__device__ __forceinline__ void member_counts_nuc2(const SelectArgs& a, const uint32_t* __restrict__ qrow, int row0,
-                                                   int row1, int lane, uint32_t& c0, uint32_t& c1) {
-    const uint32_t* __restrict__ r0 = a.refs_nuc + (size_t)row0 * 3 * a.W;
-    const uint32_t* __restrict__ r1 = a.refs_nuc + (size_t)row1 * 3 * a.W;
-    uint32_t acc0 = 0, acc1 = 0;
+// packed (mismatch | valid << 16) counts of the query against NR reference rows at once (independent loads in
+// flight: the member loop is latency-bound); every lane returns the same totals
+template <int NR>
+__device__ __forceinline__ void member_counts_nuc(const SelectArgs& a, const uint32_t* __restrict__ qrow, const int* rows,
+                                                  int lane, uint32_t* out) {
+    uint32_t acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) acc[k] = 0;
     for (int w = 4 * lane; w < a.W; w += 128) {
         const uint4 ql = *reinterpret_cast<const uint4*>(qrow + w);
         const uint4 qh = *reinterpret_cast<const uint4*>(qrow + a.W + w);
         const uint4 qv = *reinterpret_cast<const uint4*>(qrow + 2 * a.W + w);
-        const uint4 al = *reinterpret_cast<const uint4*>(r0 + w);
-        const uint4 ah = *reinterpret_cast<const uint4*>(r0 + a.W + w);
-        const uint4 av = *reinterpret_cast<const uint4*>(r0 + 2 * a.W + w);
-        const uint4 bl = *reinterpret_cast<const uint4*>(r1 + w);
-        const uint4 bh = *reinterpret_cast<const uint4*>(r1 + a.W + w);
-        const uint4 bv = *reinterpret_cast<const uint4*>(r1 + 2 * a.W + w);
-        uint32_t v, m;
-#define APPLES_ACC(acc, L_, H_, V_, c)                                                  \
-        v = qv.c & V_.c; m = ((ql.c ^ L_.c) | (qh.c ^ H_.c)) & v; acc += __popc(m) + (__popc(v) << 16);
-        APPLES_ACC(acc0, al, ah, av, x) APPLES_ACC(acc0, al, ah, av, y) APPLES_ACC(acc0, al, ah, av, z) APPLES_ACC(acc0, al, ah, av, w)
-        APPLES_ACC(acc1, bl, bh, bv, x) APPLES_ACC(acc1, bl, bh, bv, y) APPLES_ACC(acc1, bl, bh, bv, z) APPLES_ACC(acc1, bl, bh, bv, w)
+        uint4 rl[NR], rh[NR], rv[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const uint32_t* __restrict__ r = a.refs_nuc + (size_t)rows[k] * 3 * a.W;
+            rl[k] = *reinterpret_cast<const uint4*>(r + w);
+            rh[k] = *reinterpret_cast<const uint4*>(r + a.W + w);
+            rv[k] = *reinterpret_cast<const uint4*>(r + 2 * a.W + w);
+        }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            uint32_t v, m;
+#define APPLES_ACC(c)                                                                   \
+            v = qv.c & rv[k].c; m = ((ql.c ^ rl[k].c) | (qh.c ^ rh[k].c)) & v; acc[k] += __popc(m) + (__popc(v) << 16);
+            APPLES_ACC(x) APPLES_ACC(y) APPLES_ACC(z) APPLES_ACC(w)
 #undef APPLES_ACC
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc0 += __shfl_xor_sync(FULLMASK, acc0, o);
-        acc1 += __shfl_xor_sync(FULLMASK, acc1, o);
-    }
-    c0 = acc0;
-    c1 = acc1;
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < NR; ++k) acc[k] += __shfl_xor_sync(FULLMASK, acc[k], o);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) out[k] = acc[k];
 }
 
 __constant__ double c_blosum45_sel[441] = {
@@ -265,13 +269,16 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
         if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-            for (int x = b; x < e && st.kcount <= a.cap; x += 2) {  // past the slot capacity the query is rerun anyway
-                const int row0 = a.gmem[x];
-                const int row1 = (x + 1 < e) ? a.gmem[x + 1] : row0;
-                uint32_t c0, c1;
-                member_counts_nuc2(a, qrow, row0, row1, lane, c0, c1);
-                observe_nuc_counts(a, st, slot, self, row0, c0, ukey, x - b, lane);
-                if (x + 1 < e) observe_nuc_counts(a, st, slot, self, row1, c1, ukey, x + 1 - b, lane);
+            constexpr int NR = 4;
+            for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
+                int rows[NR];
+                uint32_t c[NR];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
+                member_counts_nuc<NR>(a, qrow, rows, lane, c);
+#pragma unroll
+                for (int k = 0; k < NR; ++k)
+                    if (x + k < e) observe_nuc_counts(a, st, slot, self, rows[k], c[k], ukey, x + k - b, lane);
             }
         } else {
             for (int x = b; x < e && st.kcount <= a.cap; ++x) {
@@ -308,7 +315,7 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     if (slot >= a.n) return;

@@ -182,7 +182,7 @@ def main():
             return 0
         dev = 'cuda:0' if torch.cuda.is_available() else 'cpu'
         tree, arrays, packed_q, q_bytes, info, host = build_workload(args, dev, 0, True)
-        n_sample = args.cpu_sample or max(threads * 2, 32)
+        n_sample = args.cpu_sample or max(threads * 4, 32)
         q_host = q_bytes[:n_sample * (args.steps + args.warmup)].cpu().numpy()
         rates = []
         octx = cpu_context(args, tree, host)
@@ -317,17 +317,32 @@ def main():
     cs_rate = cell_sites / (dense_ms * 1e-3)
     sm_max = clocks.get('sm_max_mhz') or float(peaks.get('sm_max_mhz', 1965.0))
     sm_cur = clocks.get('sm_mhz') or sm_max
-    # integer-pipe ceiling: 2 POPC per 32-site word-pair, POPC issues 16 lanes/clk/SM (profiles/microbench_r01.txt)
-    int_peak_max = 148 * 16 * 16 * sm_max * 1e6
-    int_peak_cur = 148 * 16 * 16 * sm_cur * 1e6
+    # integer-pipe ceilings per SM and clock (profiles/microbench_r01.txt: POPC 16 lanes/clk/SM on the XU pipe, LOP3 64
+    # lanes/clk/SM on the ALU pipe).  Per 32-site word pair the kernel issues 1.5 POPC (carry-save valid counter) and 5
+    # LOP3, so its binding pipe is the XU: 16 / 1.5 word pairs/clk/SM.  A plain popcount kernel (2 POPC per word pair)
+    # is bounded by 16 / 2.
+    def ceiling(word_pairs_per_clk_sm, mhz):
+        return 148 * word_pairs_per_clk_sm * 32 * mhz * 1e6
+    xu_peak = ceiling(16 / 1.5, sm_max)
+    alu_peak = ceiling(64 / 5.0, sm_max)
+    plain_peak = ceiling(16 / 2.0, sm_max)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'dense_traffic_r01.json')
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        # dram bytes of one ncu --set full capture, scaled from the captured launch's pair count to this run's
+        traffic = tj['dram_bytes'] * (q_per_launch * n_rep) / tj['pairs']
     roofline = {'kernel': 'dense_nuc_kernel<false> (query x representative mismatch/valid counts)', 'bound': 'hbm',
-                'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': None,
+                'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': traffic,
                 'peak_source': peak_src, 'avg_launch_ms': dense_ms, 'launches': n_dense,
-                'binding_resource': 'integer pipe (POPC/LOP3), not HBM: see int_pipe',
+                'algorithmic_bytes_per_launch': alg_bytes,
+                'binding_resource': 'integer pipes (XU POPC / ALU LOP3), not HBM: see int_pipe',
                 'int_pipe': {'achieved': cs_rate / 1e12, 'unit': 'Tcell-sites/s',
-                             'peak_at_max_clock': int_peak_max / 1e12, 'frac_at_max_clock': cs_rate / int_peak_max,
-                             'peak_at_observed_clock': int_peak_cur / 1e12, 'frac_at_observed_clock': cs_rate / int_peak_cur,
-                             'model': '148 SMs x 16 POPC lanes/clk x 16 sites per POPC (2 POPC per 32-site word pair)'}}
+                             'peak': xu_peak / 1e12, 'frac': cs_rate / xu_peak,
+                             'peak_model': 'XU pipe: 148 SMs x 16 POPC lanes/clk / 1.5 POPC per 32-site word pair x %.0f MHz '
+                                           '(max clock; observed %.0f MHz)' % (sm_max, sm_cur),
+                             'alu_peak': alu_peak / 1e12, 'frac_of_alu_peak': cs_rate / alu_peak,
+                             'plain_popcount_peak': plain_peak / 1e12, 'frac_of_plain_popcount_peak': cs_rate / plain_peak}}
     step_ms = ms / args.steps
     stages = {k: tm[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms')}
     line = {'metric': 'queries placed/sec', 'value': value, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps,
@@ -345,7 +360,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----
     if not args.no_cpu_baseline and world == 1:
-        n_sample = args.cpu_sample or max(threads * 2, 32)
+        n_sample = args.cpu_sample or max(threads * 8, 64)
         q_host = q_bytes[:n_sample].cpu().numpy()
         rate, dt, res = cpu_baseline(cpu_context(args, tree, host), q_host, threads)
         # parity of the timed GPU results on that sample
