@@ -166,6 +166,16 @@ def cpu_baseline(ctx, q_host, threads):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries (NCCL prints its version banner to stdout) are redirected to
+    # stderr at the file-descriptor level and the JSON line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
+
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -201,7 +211,7 @@ def main():
                                  'sample': '%d queries per step through the oracle port of PoolQueryWorker.runquery, '
                                            'fork pool of %d processes' % (n_sample, threads)},
                 'e2e': {'value': val, 'unit': 'queries/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------ our arm
@@ -375,7 +385,7 @@ def main():
                                           'PoolQueryWorker.runquery under a fork pool of %d processes (%.1f s)'
                                           % (n_sample, threads, dt),
                                 'parity_on_sample': '%d/%d identical edge and score within 1e-9' % (same, n_sample)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
