@@ -66,6 +66,7 @@ struct apples_ctx {
     int64_t max_batch = 1 << 20;  // queries per macro-batch (batch-wide observed-list buffers)
     std::vector<int> hK, hV, hS;
     std::vector<long long> h_rec_off, h_stack_off;
+    std::vector<char> h_gather;
     int slot_cap = 256;
 };
 
@@ -535,17 +536,22 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
             if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
             CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
-            for (int j = 0; j < ng; ++j) {  // gather the rows of the overflowing queries
-                const size_t g = (size_t)base0 + over[o0 + j];
-                if (matrix)
-                    CK(cudaMemcpyAsync((char*)ctx->keys.p + (size_t)j * qrow, io.h_rows + g * ctx->n_cols, qrow, cudaMemcpyHostToDevice, s));
-                else if (io.h_queries)
-                    CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.h_queries + g * qrow, qrow, cudaMemcpyHostToDevice, s));
-                else if (io.h_bytes)
-                    CK(cudaMemcpyAsync((char*)ctx->q_bytes.p + (size_t)j * io.byte_stride, io.h_bytes + g * io.byte_stride,
-                                       (size_t)io.byte_stride, cudaMemcpyHostToDevice, s));
-                else
-                    CK(cudaMemcpyAsync((char*)ctx->q_rm.p + (size_t)j * qrow, (const char*)io.d_queries + g * qrow, qrow, cudaMemcpyDeviceToDevice, s));
+            // gather the rows of the overflowing queries: one kernel for device-resident queries, one host-side gather +
+            // one copy otherwise (a memcpy call per row would cost more than the rerun itself)
+            if (!matrix && !io.h_queries && !io.h_bytes) {
+                // qlist holds batch-relative ids; the resident rows of this macro-batch start at base0
+                CK(launch_gather_rows((const char*)io.d_queries + (size_t)base0 * qrow, (const int*)ctx->qlist.p, ctx->q_rm.p, ng,
+                                      qrow, s));
+                ctx->n_launch += 1;
+            } else {
+                const size_t rb = matrix ? qrow : (io.h_queries ? qrow : (size_t)io.byte_stride);
+                const char* src = matrix ? (const char*)io.h_rows : (io.h_queries ? (const char*)io.h_queries : (const char*)io.h_bytes);
+                ctx->h_gather.resize((size_t)ng * rb);
+                for (int j = 0; j < ng; ++j)
+                    memcpy(ctx->h_gather.data() + (size_t)j * rb, src + ((size_t)base0 + over[o0 + j]) * rb, rb);
+                void* dst = matrix ? ctx->keys.p : (io.h_queries ? ctx->q_rm.p : ctx->q_bytes.p);
+                CK(cudaMemcpyAsync(dst, ctx->h_gather.data(), (size_t)ng * rb, cudaMemcpyHostToDevice, s));
+                CK(cudaStreamSynchronize(s));  // h_gather is reused by the next group
             }
             if (io.h_bytes)
                 CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,

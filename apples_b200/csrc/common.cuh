@@ -173,5 +173,6 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
 void launch_place(int method, const PlaceArgs& a, cudaStream_t s);
 cudaError_t dense_nuc_configure();
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad, cudaStream_t s);
+cudaError_t launch_gather_rows(const void* src, const int* idx, void* dst, int n, size_t row_bytes, cudaStream_t s);
 cudaError_t launch_consensus(int kind, const uint8_t* bytes, int64_t row_stride, int L, int n_rep, const int* goff,
                              const int* gmem, uint8_t* out, int64_t out_stride, cudaStream_t s);

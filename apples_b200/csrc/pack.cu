@@ -109,3 +109,20 @@ cudaError_t launch_consensus(int kind, const uint8_t* bytes, int64_t row_stride,
         consensus_kernel<21><<<n_rep, 256, 0, s>>>(bytes, row_stride, L, goff, gmem, out, out_stride);
     return cudaGetLastError();
 }
+
+// gathers whole rows: dst[j] = src[idx[j]] (row_bytes a multiple of 16); used to collect the queries of a rerun
+__global__ void gather_rows_kernel(const uint4* __restrict__ src, const int* __restrict__ idx, uint4* __restrict__ dst,
+                                   int n, int row_vec) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * row_vec) return;
+    const int j = (int)(t / row_vec), c = (int)(t % row_vec);
+    dst[t] = src[(size_t)idx[j] * row_vec + c];
+}
+
+cudaError_t launch_gather_rows(const void* src, const int* idx, void* dst, int n, size_t row_bytes, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int row_vec = (int)(row_bytes / 16);
+    const int64_t total = (int64_t)n * row_vec;
+    gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint4*)src, idx, (uint4*)dst, n, row_vec);
+    return cudaGetLastError();
+}

@@ -423,3 +423,47 @@ def test_device_packer_and_consensus(case, workdir):
             b.place_bytes(bad, None, params)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize('method', ['OLS', 'BME'])
+def test_config4_shapes(method, workdir):
+    """BASELINE.json config 4 at full size: 10 000-leaf backbone, 1500 sites, 100 000 queries, OLS and BME + MLSE.
+    Full-size checks are the size-independent ones (determinism, every query accounted for, branch lengths inside the
+    edge) plus oracle parity on a sample of the same batch."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200 import _lib, fasta
+    from apples_b200.placer import GpuPlacer
+    nwk, tree, refs, ref, queries, _ = _synthetic(10000, 1500, 100000, 300, workdir)
+    pl = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+    params = _lib.make_params(method, 'MLSE')
+    names = list(queries.keys())
+    mat = fasta.as_byte_matrix([queries[n] for n in names], 1500)
+    a = pl.place_bytes(mat, None, params)
+    b = pl.place_bytes(mat, None, params)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    edge, error, distal, pendant, status = a
+    code = status & 0xff
+    assert set(np.unique(code).tolist()) <= {0, 1, 2, 3}
+    placed = (code == 0) | (code == 3)
+    assert placed.mean() > 0.95
+    el = tree.edge_length[edge[placed]]
+    assert (distal[placed] >= -1e-12).all() and (distal[placed] <= el + 1e-12).all() and (pendant[placed] >= 0).all()
+    tfp = os.path.join(workdir, 'c4.nwk')
+    open(tfp, 'w').write(nwk)
+    otree, onames = orc.load_tree(tfp)
+    octx = orc.OracleContext(otree, onames, refs=refs, representatives=ref.representatives, method=method, criterion='MLSE')
+    ties = 0
+    for i in range(0, 100000, 2500):
+        q = (names[i], queries[names[i]], None)
+        exp, st = octx.runquery(*q)
+        p = exp['placements'][0]['p'][0]
+        if st in (0, 3):
+            got = [int(edge[i]), float(error[i]), 1, float(distal[i]), 0 if status[i] & 0x100 else float(pendant[i])]
+            if _check_p('c4', names[i], got, p, False, octx, q) == 'tie':
+                ties += 1
+        else:
+            assert code[i] == st and (st != 1 or edge[i] == p[0])
+    assert ties <= 1
+    pl.close()
