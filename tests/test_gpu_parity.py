@@ -467,3 +467,56 @@ def test_config4_shapes(method, workdir):
             assert code[i] == st and (st != 1 or edge[i] == p[0])
     assert ties <= 1
     pl.close()
+
+
+@pytest.mark.parametrize('method,criterion', [('FM', 'MLSE'), ('BME', 'HYBRID'), ('OLS', 'ME')])
+def test_deep_caterpillar_all_leaves_observed(method, criterion, workdir):
+    """A 1500-leaf caterpillar (1499 levels) placed from a distance matrix with the filter off: every leaf is observed
+    (slot overflow reruns up to the full capacity), the restricted subtree is the whole tree and spans more levels
+    than the shared-memory bucket table of the placement kernel (level-sweep fallback)."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200.placer import place_batch
+    from apples_b200.tree import BackboneTree
+    rng = np.random.default_rng(77)
+    n = 1500
+    s = 'L0:%.5f' % rng.uniform(0.001, 0.02)
+    for i in range(1, n):
+        s = '(%s,L%d:%.5f):%.5f' % (s, i, rng.uniform(0.001, 0.02), rng.uniform(0.0005, 0.01))
+    s = s.rsplit(':', 1)[0] + ';'
+    tfp = os.path.join(workdir, 'cat.nwk')
+    open(tfp, 'w').write(s)
+    tree = BackboneTree.from_newick(tfp)
+    assert tree.level.max() >= 1400
+    # path distances from 4 attachment points (sister to L100, L700, L1200, L1499) plus noise
+    depth = np.zeros(tree.num_nodes)
+    for u in range(tree.num_nodes - 2, -1, -1):
+        depth[u] = depth[tree.parent[u]] + tree.edge_length[u]
+    names = ['L%d' % i for i in range(n)]
+    leaf = np.array([tree.name_to_node[x] for x in names])
+
+    def pathdist(a, b):
+        x, y = a, b
+        while x != y:
+            if x < y:
+                x = tree.parent[x]
+            else:
+                y = tree.parent[y]
+        return depth[a] + depth[b] - 2 * depth[x]
+    queries = []
+    for qi, anchor in enumerate([100, 700, 1200, 1499]):
+        d = np.array([pathdist(leaf[anchor], leaf[j]) for j in range(n)]) + 0.013
+        d = np.round(d * (1 + 0.02 * rng.standard_normal(n)), 6)
+        d[d <= 0] = 0.001
+        queries.append(('q%d' % qi, None, dict(zip(names, d.tolist()))))
+    opt = types.SimpleNamespace(method_name=method, criterion_name=criterion, negative_branch=False,
+                                base_observation_threshold=25, filt_threshold=100.0, minimum_alignment_overlap=0.001,
+                                exclude_intplace=False)
+    res = place_batch(None, opt, tree.name_to_node, queries, tree=tree, device=0)
+    otree, onames = orc.load_tree(tfp)
+    octx = orc.OracleContext(otree, onames, method=method, criterion=criterion, filt_threshold=100.0)
+    for q, r in zip(queries, res):
+        exp, _ = octx.runquery(q[0], None, dict(q[2]))
+        g, e = r['placements'][0]['p'][0], exp['placements'][0]['p'][0]
+        assert g[0] == e[0], (q[0], g, e)
+        assert util.close(g[1], e[1], 1e-9, 1e-9) and g[3] == e[3] and g[4] == e[4], (q[0], g, e)
