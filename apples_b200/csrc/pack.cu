@@ -46,8 +46,6 @@ __global__ void pack_aa_kernel(const uint8_t* __restrict__ bytes, int64_t row_st
     out[t] = s < L ? c_aa_code[bytes[(size_t)row * row_stride + s]] : (uint8_t)20;
 }
 
-static bool g_aa_table_ready = false;
-
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad,
                         cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
@@ -56,19 +54,20 @@ cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int 
         const int64_t total = (int64_t)n * W;
         pack_nuc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, W, (uint32_t*)out, bad);
     } else {
-        if (!g_aa_table_ready) {
-            uint8_t tab[256];
-            memset(tab, 0, sizeof tab);  // NA = 0: unknown bytes count as 'A' (distance.py:418)
-            const char* order = "ARNDCQEGHILKMFPSTWYV";
-            for (int i = 0; i < 20; ++i) {
-                tab[(unsigned char)order[i]] = (uint8_t)i;
-                tab[(unsigned char)(order[i] + 32)] = (uint8_t)i;
-            }
-            tab[(unsigned char)'-'] = 20;
-            cudaError_t e = cudaMemcpyToSymbol(c_aa_code, tab, 256);
-            if (e != cudaSuccess) return e;
-            g_aa_table_ready = true;
+        // the table lives in the constant memory of the CURRENT device: (re)written on every call (256 bytes) so that
+        // several contexts on different devices in one process all see it
+        uint8_t tab[256];
+        memset(tab, 0, sizeof tab);  // NA = 0: unknown bytes count as 'A' (distance.py:418)
+        const char* order = "ARNDCQEGHILKMFPSTWYV";
+        for (int i = 0; i < 20; ++i) {
+            tab[(unsigned char)order[i]] = (uint8_t)i;
+            tab[(unsigned char)(order[i] + 32)] = (uint8_t)i;
         }
+        tab[(unsigned char)'-'] = 20;
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_aa_code, tab, 256, 0, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(s);  // `tab` is a stack buffer
+        if (e != cudaSuccess) return e;
         const int Lp = apples_aa_row_bytes(L);
         const int64_t total = (int64_t)n * Lp;
         pack_aa_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, Lp, (uint8_t*)out);
