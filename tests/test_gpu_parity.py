@@ -520,3 +520,94 @@ def test_deep_caterpillar_all_leaves_observed(method, criterion, workdir):
         g, e = r['placements'][0]['p'][0], exp['placements'][0]['p'][0]
         assert g[0] == e[0], (q[0], g, e)
         assert util.close(g[1], e[1], 1e-9, 1e-9) and g[3] == e[3] and g[4] == e[4], (q[0], g, e)
+
+
+def _random_matrix_case(rng, workdir, tag):
+    """random backbone (polytomies, zero / negative edges) + a random distance-matrix batch with ties, missing
+    values (-1), tags that are not in the tree, zero distances and queries named like backbone leaves"""
+    from apples_b200 import synth
+    from apples_b200.tree import BackboneTree
+    n = int(rng.integers(4, 90))
+    nwk = synth.random_tree(n, seed=int(rng.integers(1, 1 << 30)), polytomy_frac=float(rng.choice([0.0, 0.2, 0.5])),
+                            zero_frac=float(rng.choice([0.0, 0.1])), neg_frac=float(rng.choice([0.0, 0.05])),
+                            model=str(rng.choice(['yule', 'uniform'])))
+    tfp = os.path.join(workdir, 'rnd_%s.nwk' % tag)
+    open(tfp, 'w').write(nwk)
+    tree = BackboneTree.from_newick(tfp)
+    leaves = [tree.label[u] for u in tree.leaf_ids.tolist()]
+    tags = leaves + ['ghost1', 'ghost2']
+    rng.shuffle(tags)
+    depth = np.zeros(tree.num_nodes)
+    for u in range(tree.num_nodes - 2, -1, -1):
+        depth[u] = depth[tree.parent[u]] + abs(tree.edge_length[u])
+    queries = []
+    for qi in range(int(rng.integers(1, 9))):
+        anchor = tree.name_to_node[leaves[int(rng.integers(0, n))]]
+        row = {}
+        for t in tags:
+            if t in tree.name_to_node:
+                a, b = anchor, tree.name_to_node[t]
+                x, y = a, b
+                while x != y:
+                    if x < y:
+                        x = tree.parent[x]
+                    else:
+                        y = tree.parent[y]
+                d = depth[a] + depth[b] - 2 * depth[x] + 0.01
+                d = round(float(d * (1 + 0.1 * rng.standard_normal())), int(rng.choice([2, 3, 6])))  # coarse rounding -> ties
+                d = max(d, 0.001)
+            else:
+                d = float(rng.uniform(0, 0.5))
+            u = rng.random()
+            if u < 0.05:
+                d = -1.0
+            elif u < 0.07:
+                d = 0.0
+            row[t] = d
+        name = leaves[int(rng.integers(0, n))] if rng.random() < 0.15 else 'rq%d' % qi
+        queries.append((name, None, row))
+    return tfp, tree, queries
+
+
+def test_randomized_differential_matrix_mode(workdir):
+    """300 seeded random cases (tree shape, polytomies, zero/negative edges, ties, missing values, zero distances,
+    own-name queries, every method x criterion x -n, random -b / -f) against the oracle: edge, status and int-ness
+    identical, branch lengths bit-identical, score within 1e-9."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200.placer import place_batch
+    rng = np.random.default_rng(20240917)
+    n_checked = 0
+    for case in range(300):
+        tfp, tree, queries = _random_matrix_case(rng, workdir, case)
+        method = str(rng.choice(['FM', 'OLS', 'BME', 'BE']))
+        criterion = str(rng.choice(['MLSE', 'ME', 'HYBRID']))
+        neg = bool(rng.random() < 0.25)
+        b = int(rng.choice([1, 3, 5, 25, 1000]))
+        f = float(rng.choice([0.0, 0.05, 0.2, 100.0]))
+        opt = types.SimpleNamespace(method_name=method, criterion_name=criterion, negative_branch=neg,
+                                    base_observation_threshold=b, filt_threshold=f, minimum_alignment_overlap=0.001,
+                                    exclude_intplace=bool(rng.random() < 0.3))
+        res = place_batch(None, opt, tree.name_to_node, queries, tree=tree, device=0)
+        otree, onames = orc.load_tree(tfp)
+        octx = orc.OracleContext(otree, onames, method=method, criterion=criterion, negative_branch=neg,
+                                 filt_threshold=f, baseobs=b, exclude_intplace=opt.exclude_intplace)
+        for q, r in zip(queries, res):
+            try:
+                exp, st = octx.runquery(q[0], None, dict(q[2]))
+            except (ZeroDivisionError, FloatingPointError, OverflowError):
+                continue  # the reference itself raises here (1 / 0.0 in util.solve2_2): nothing to compare
+            g, e = r['placements'][0]['p'][0], exp['placements'][0]['p'][0]
+            ctx = (case, q[0], method, criterion, neg, b, f, g, e)
+            assert r['placements'][0]['n'] == exp['placements'][0]['n'], ctx
+            if any(isinstance(x, float) and (x != x or abs(x) == float('inf')) for x in e[1:]):
+                continue  # degenerate systems (nan / inf) are outside the parity contract
+            if g[0] != e[0]:
+                det = {}
+                octx.runquery(q[0], None, dict(q[2]), detail=det)
+                assert g[0] in det['edges'] and util.close(det['edges'][g[0]][2], det['edges'][e[0]][2], 1e-9, 1e-12), ctx
+                continue
+            assert [isinstance(x, int) for x in g] == [isinstance(x, int) for x in e], ctx
+            assert util.close(g[1], e[1], 1e-9, 1e-12) and g[3] == e[3] and g[4] == e[4], ctx
+            n_checked += 1
+    assert n_checked > 800
