@@ -611,3 +611,85 @@ def test_randomized_differential_matrix_mode(workdir):
             assert util.close(g[1], e[1], 1e-9, 1e-12) and g[3] == e[3] and g[4] == e[4], ctx
             n_checked += 1
     assert n_checked > 800
+
+
+def test_randomized_differential_alignment_mode(workdir):
+    """120 seeded random alignment cases (nucleotide and protein, heavy random gaps, random clusterings incl. singletons,
+    random -V / -b / -f, copies of references, own-name queries) against the oracle: observed sets identical, edges
+    identical (score ties excepted), values within 1e-9."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200 import synth
+    from apples_b200.placer import GpuPlacer, results_to_jplace
+    from apples_b200.reference import ReducedReference
+    from apples_b200.tree import BackboneTree
+    rng = np.random.default_rng(424242)
+    checked = ties = 0
+    for case in range(120):
+        protein = bool(rng.random() < 0.3)
+        n = int(rng.integers(5, 70))
+        L = int(rng.integers(40, 700))
+        nwk = synth.random_tree(n, seed=int(rng.integers(1, 1 << 30)), mean_edge=float(rng.choice([0.01, 0.03, 0.08])),
+                                polytomy_frac=float(rng.choice([0.0, 0.3])))
+        tfp = os.path.join(workdir, 'rnda_%d.nwk' % case)
+        open(tfp, 'w').write(nwk)
+        tree = BackboneTree.from_newick(tfp)
+        refs, states = synth.evolve_alignment(tree, L, seed=int(rng.integers(1, 1 << 30)), protein=protein,
+                                              gap_frac=float(rng.choice([0.0, 0.05, 0.4])), edge_frac=float(rng.choice([0.0, 0.3])))
+        qd, _ = synth.make_queries(tree, states, int(rng.integers(1, 7)), seed=int(rng.integers(1, 1 << 30)), protein=protein,
+                                   mean_extra=float(rng.choice([0.0, 0.03, 0.2])), gap_frac=float(rng.choice([0.0, 0.1, 0.6])))
+        queries = [(k, v, None) for k, v in qd.items()]
+        names = list(refs.keys())
+        queries.append(('copy', refs[names[int(rng.integers(0, n))]], None))          # zero-distance shortcut
+        own = names[int(rng.integers(0, n))]
+        queries.append((own, refs[own], None))                                        # query named like a leaf
+        # random clustering: random cluster ids, about a third singletons
+        tsv = os.path.join(workdir, 'rnda_%d.tsv' % case)
+        with open(tsv, 'w') as f:
+            f.write('SequenceName\tClusterNumber\n')
+            for nm in names:
+                cid = -1 if rng.random() < 0.35 else int(rng.integers(1, max(2, n // 3)))
+                f.write('%s\t%d\n' % (nm, cid))
+        thr = float(rng.choice([0.05, 0.2, 0.6]))
+        ref = ReducedReference(None, protein, tfp, thr, 1, cluster_tsv=tsv, tree=tree, refs=refs)
+        opt = types.SimpleNamespace(method_name=str(rng.choice(['FM', 'OLS', 'BME', 'BE'])),
+                                    criterion_name=str(rng.choice(['MLSE', 'ME', 'HYBRID'])),
+                                    negative_branch=bool(rng.random() < 0.2), base_observation_threshold=int(rng.choice([2, 5, 25])),
+                                    filt_threshold=thr, minimum_alignment_overlap=float(rng.choice([0.001, 0.2, 0.5])),
+                                    exclude_intplace=False)
+        pl = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+        params = pl.params_from_options(opt)
+        qn = [q[0] for q in queries]
+        sn = pl.self_nodes(qn)
+        packed = pl.pack_queries([q[1] for q in queries])
+        out = pl.place_packed(packed, sn, params)
+        count, node, dist = pl.observed_sets(params, packed=packed, self_node=sn, cap=256)
+        res = results_to_jplace(qn, [x in tree.name_to_node for x in qn], out, log=False)
+        pl.close()
+        otree, onames = orc.load_tree(tfp)
+        octx = orc.OracleContext(otree, onames, refs=refs, representatives=orc.representatives_from_tsv(tsv, refs, protein),
+                                 protein=protein, method=opt.method_name, criterion=opt.criterion_name,
+                                 negative_branch=opt.negative_branch, filt_threshold=thr, baseobs=opt.base_observation_threshold,
+                                 overlap=opt.minimum_alignment_overlap)
+        for qi, (q, r) in enumerate(zip(queries, res)):
+            det = {}
+            try:
+                exp, st = octx.runquery(q[0], q[1], None, detail=det)
+            except (ZeroDivisionError, FloatingPointError, OverflowError):
+                continue
+            ctx = (case, q[0], protein, vars(opt))
+            eobs = {tree.name_to_node[k]: v for k, v in det['observed']}
+            assert int(count[qi]) == len(eobs), ctx
+            if st in (0, 3):
+                k = int(count[qi])
+                assert node[qi, :k].tolist() == sorted(eobs), ctx
+                for u, d in zip(node[qi, :k].tolist(), dist[qi, :k].tolist()):
+                    assert util.close(d, eobs[u], 1e-9, 0.0), ctx
+            g, e = r['placements'][0]['p'][0], exp['placements'][0]['p'][0]
+            assert r['placements'][0]['n'] == exp['placements'][0]['n'], ctx
+            if any(isinstance(x, float) and (x != x or abs(x) == float('inf')) for x in e[1:]):
+                continue
+            if _check_p('rnda', q[0], g, e, False, octx, q) == 'tie':
+                ties += 1
+            checked += 1
+    assert checked > 500 and ties <= 5, (checked, ties)
