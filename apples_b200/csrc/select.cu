@@ -66,21 +66,6 @@ __device__ __forceinline__ Key<KIND> key_shfl(const Key<KIND>& k, int src) {
     o.idx = __shfl_sync(FULLMASK, k.idx, src);
     return o;
 }
-__device__ __forceinline__ Key<SEL_NUC> key_shfl_up(const Key<SEL_NUC>& k) {
-    Key<SEL_NUC> o;
-    o.m = __shfl_up_sync(FULLMASK, k.m, 1);
-    o.v = __shfl_up_sync(FULLMASK, k.v, 1);
-    o.idx = __shfl_up_sync(FULLMASK, k.idx, 1);
-    return o;
-}
-template <int KIND>
-__device__ __forceinline__ Key<KIND> key_shfl_up(const Key<KIND>& k) {
-    Key<KIND> o;
-    o.d = __shfl_up_sync(FULLMASK, k.d, 1);
-    o.idx = __shfl_up_sync(FULLMASK, k.idx, 1);
-    return o;
-}
-
 __device__ __forceinline__ Key<SEL_NUC> key_shfl_xor(const Key<SEL_NUC>& k, int o) {
     Key<SEL_NUC> r;
     r.m = __shfl_xor_sync(FULLMASK, k.m, o);
