@@ -179,7 +179,10 @@ __constant__ double c_blosum45_sel[441] = {
 #include "blosum45.inc"
 };
 
-__device__ __forceinline__ double member_dist_aa(const SelectArgs& a, const uint8_t* qrow, int ref_row, int lane) {
+// `tab` is the 21x21 table in SHARED memory: lanes index it with different (query, reference) code pairs, which the
+// constant cache would serialise
+__device__ __forceinline__ double member_dist_aa(const SelectArgs& a, const double* tab, const uint8_t* qrow, int ref_row,
+                                                 int lane) {
     const uint8_t* r = a.refs_aa + (size_t)ref_row * a.Lp;
     double sum = 0.0;
     uint32_t val = 0;
@@ -189,7 +192,7 @@ __device__ __forceinline__ double member_dist_aa(const SelectArgs& a, const uint
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const uint32_t qc = (qw >> (8 * b)) & 0xffu, rc = (rw >> (8 * b)) & 0xffu;
-            sum += c_blosum45_sel[qc * 21 + rc];
+            sum += tab[qc * 21 + rc];
             val += (qc < 20u && rc < 20u) ? 1u : 0u;
         }
     }
@@ -247,7 +250,7 @@ __device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<
 
 template <int KIND>
 __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& st, int slot, int q, int self,
-                                            const Key<KIND>& ukey, int lane) {
+                                            const Key<KIND>& ukey, int lane, const double* aa_tab) {
     if constexpr (KIND == SEL_MATRIX) {
         observe<KIND>(a, st, slot, self, a.col_node[ukey.idx], ukey.d, ukey.d == 0.0, ukey, 0, lane);
     } else {
@@ -268,7 +271,7 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         } else {
             for (int x = b; x < e && st.kcount <= a.cap; ++x) {
                 const int row = a.gmem[x];
-                const double d = member_dist_aa(a, a.q_aa + (size_t)q * a.Lp, row, lane);
+                const double d = member_dist_aa(a, aa_tab, a.q_aa + (size_t)q * a.Lp, row, lane);
                 if (!(d < 0.0)) observe<KIND>(a, st, slot, self, a.ref_node[row], d, d == 0.0, ukey, x - b, lane);  // Reference.py:150
             }
         }
@@ -303,6 +306,12 @@ template <int KIND>
 __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
+    __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
+    const double* aa_tab = s_aa_tab;
+    if constexpr (KIND == SEL_AA) {
+        for (int i = threadIdx.x; i < 441; i += blockDim.x) s_aa_tab[i] = c_blosum45_sel[i];
+        __syncthreads();
+    }
     if (slot >= a.n) return;
     const int gid = a.out_map ? a.out_map[slot] : a.q_begin + slot;       // query index inside the batch
     const int oslot = a.out_map ? slot : gid;                             // row of the observed-list buffers
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
                 }
                 for (int t = 0; t < qn && st.kcount <= a.cap; ++t) {
                     const Key<KIND> uk = key_shfl(qkey, t);
-                    expand_unit<KIND>(a, st, oslot, slot, self, uk, lane);
+                    expand_unit<KIND>(a, st, oslot, slot, self, uk, lane, aa_tab);
                 }
             }
         }
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
             }
         }
         if (owner < 0) break;  // no far unit left
-        expand_unit<KIND>(a, st, oslot, slot, self, g, lane);
+        expand_unit<KIND>(a, st, oslot, slot, self, g, lane, aa_tab);
         // next-smallest key of the owner's residue class: units owner + 32 k, k split over the lanes
         Key<KIND> nb;
         bool have_nb = false;
