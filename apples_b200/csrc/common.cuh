@@ -7,8 +7,14 @@
 // ---------------------------------------------------------------------------------------------------------------
 // tile shape of the dense query x representative distance kernel (distance.cu)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DT_TQ = 64;       // queries per CTA tile
-constexpr int DT_TR = 64;       // representatives per CTA tile
+#ifndef DT_TQ_V
+#define DT_TQ_V 128
+#endif
+constexpr int DT_TQ = DT_TQ_V;  // queries per CTA tile
+#ifndef DT_TR_V
+#define DT_TR_V 64
+#endif
+constexpr int DT_TR = DT_TR_V;  // representatives per CTA tile
 #ifndef DT_WC_V
 #define DT_WC_V 16
 #endif
@@ -17,10 +23,10 @@ constexpr int DT_WC = DT_WC_V;  // 32-site words per pipeline stage
 #define DT_STAGES_V 4
 #endif
 #ifndef DT_MINBLOCKS
-#define DT_MINBLOCKS 2
+#define DT_MINBLOCKS 1
 #endif
 constexpr int DT_STAGES = DT_STAGES_V;    // TMA pipeline depth
-constexpr int DT_CONSUMERS = 256;
+constexpr int DT_CONSUMERS = (DT_TQ / 4) * (DT_TR / 4);  // one thread per 4x4 block of pairs
 constexpr int DT_THREADS = DT_CONSUMERS + 32;  // + one producer warp
 constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
 constexpr int DT_STAGE_BYTES = DT_STAGE_WORDS * 4;

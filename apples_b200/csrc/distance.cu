@@ -7,8 +7,9 @@
 // The dense kernel computes all pairs of a query block against all representatives with a GEMM-like tiling:
 // operands are stored word-major ([plane][word][row]) so that one (plane, word) slice of a 64-row tile is 256
 // contiguous bytes; a producer warp streams those slices into a 4-stage shared-memory ring with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx), 8 consumer warps hold a 4x4 register tile of pairs each and do the
-// LOP3/POPC work.  The binding resource is the integer pipe (POPC), not HBM ("rooflines").
+// (cp.async.bulk + mbarrier complete_tx), 16 consumer warps hold a 4x4 register tile of pairs per thread (CTA tile 128
+// queries x 64 representatives, one persistent CTA per SM) and do the LOP3/POPC work.  The binding resources are the
+// integer pipes (XU POPC, ALU LOP3), not HBM ("rooflines").
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -38,6 +39,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+#ifdef DT_PRODUCER_SLEEP
+        __nanosleep(DT_PRODUCER_SLEEP);
+#endif
     }
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     }
 
     // ===== consumers: thread (tq, tr) owns queries 4*tq..+3 and representatives 4*tr..+3 of the tile =====
-    const int tq = tid & 15, tr = tid >> 4;
+    const int tq = tid % (DT_TQ / 4), tr = tid / (DT_TQ / 4);
     uint32_t it = 0;
     const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
