@@ -148,7 +148,11 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     }
 
     // ===== consumers: thread (tq, tr) owns queries 4*tq..+3 and representatives 4*tr..+3 of the tile =====
+#ifdef DT_MAP_TR_FAST
+    const int tr = tid % (DT_TR / 4), tq = tid / (DT_TR / 4);
+#else
     const int tq = tid % (DT_TQ / 4), tr = tid / (DT_TQ / 4);
+#endif
     uint32_t it = 0;
     const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
