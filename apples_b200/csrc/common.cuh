@@ -27,7 +27,10 @@ constexpr int DT_WC = DT_WC_V;  // 32-site words per pipeline stage
 #endif
 constexpr int DT_STAGES = DT_STAGES_V;    // TMA pipeline depth
 constexpr int DT_CONSUMERS = (DT_TQ / 4) * (DT_TR / 4);  // one thread per 4x4 block of pairs
-constexpr int DT_THREADS = DT_CONSUMERS + 32;  // + one producer warp
+#ifndef DT_SELF_PRODUCE
+#define DT_SELF_PRODUCE 0
+#endif
+constexpr int DT_THREADS = DT_CONSUMERS + (DT_SELF_PRODUCE ? 0 : 32);  // + one producer warp unless warp 0 produces
 constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
 constexpr int DT_STAGE_BYTES = DT_STAGE_WORDS * 4;
 constexpr int DT_SMEM_BYTES = DT_STAGES * DT_STAGE_BYTES + 2 * DT_STAGES * 8 + 16;

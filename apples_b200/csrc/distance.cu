@@ -123,29 +123,50 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     }
     __syncthreads();
 
+    // one (plane, word) slice of a tile's rows = DT_TQ*4 / DT_TR*4 contiguous bytes per bulk copy
+    auto issue_stage = [&](uint32_t git, int tile, int c) {
+        const int s = git % DT_STAGES;
+        const uint32_t ph = (git / DT_STAGES) & 1;
+        const int qt = tile / n_rt, rt = tile % n_rt;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], DT_STAGE_BYTES);
+        __syncwarp();
+        uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
+        uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
+        for (int i = lane; i < 3 * DT_WC; i += 32) {
+            const int plane = i / DT_WC, w = i % DT_WC;
+            const size_t grow = (size_t)plane * a.Wp + (size_t)c * DT_WC + w;
+            tma_bulk_g2s(sq + i * DT_TQ, a.q_wm + grow * a.q_pad + (size_t)qt * DT_TQ, DT_TQ * 4, &full_bar[s]);
+            tma_bulk_g2s(sr + i * DT_TR, a.r_wm + grow * a.r_pad + (size_t)rt * DT_TR, DT_TR * 4, &full_bar[s]);
+        }
+    };
+#if DT_SELF_PRODUCE
+    // EXPERIMENT (off by default, measured r01: 56 vs 78 Tcell-sites/s with the dedicated producer warp): no producer
+    // warp, consumer warp 0 issues the copies of chunk it + STAGES - 1 before it computes chunk `it`.  It frees the
+    // 17th warp's register granule (128 instead of 96 registers per thread) but couples warp 0 to the slowest warp.
+    uint32_t p_it = 0;
+    int p_tile = blockIdx.x, p_c = 0;
+    auto produce_next = [&]() {
+        if (p_tile < n_tiles) {
+            issue_stage(p_it, p_tile, p_c);
+            ++p_it;
+            if (++p_c == n_chunks) { p_c = 0; p_tile += gridDim.x; }
+        }
+    };
+    if (warp == 0)
+        for (int k = 0; k < DT_STAGES - 1; ++k) produce_next();
+#else
     if (warp == DT_CONSUMERS / 32) {
-        // ===== producer warp: one (plane, word) slice of 64 rows = 256 contiguous bytes per bulk copy =====
+        // ===== producer warp =====
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int qt = tile / n_rt, rt = tile % n_rt;
             for (int c = 0; c < n_chunks; ++c, ++it) {
-                const int s = it % DT_STAGES;
-                const uint32_t ph = (it / DT_STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], DT_STAGE_BYTES);
-                __syncwarp();
-                uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
-                uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
-                for (int i = lane; i < 3 * DT_WC; i += 32) {
-                    const int plane = i / DT_WC, w = i % DT_WC;
-                    const size_t grow = (size_t)plane * a.Wp + (size_t)c * DT_WC + w;
-                    tma_bulk_g2s(sq + i * DT_TQ, a.q_wm + grow * a.q_pad + (size_t)qt * DT_TQ, DT_TQ * 4, &full_bar[s]);
-                    tma_bulk_g2s(sr + i * DT_TR, a.r_wm + grow * a.r_pad + (size_t)rt * DT_TR, DT_TR * 4, &full_bar[s]);
-                }
+                issue_stage(it, tile, c);
             }
         }
         return;
     }
+#endif
 
     // ===== consumers: thread (tq, tr) owns queries 4*tq..+3 and representatives 4*tr..+3 of the tile =====
 #ifdef DT_MAP_TR_FAST
@@ -155,6 +176,9 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
 #endif
     uint32_t it = 0;
     const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
+#ifdef DT_CSA2
+    const uint32_t k_four16 = a.k_two17 << 1;
+#endif
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int qt = tile / n_rt, rt = tile % n_rt;
         // per pair: acc = mismatch count (low 16 bits) | valid count (high 16 bits); `ones` is the weight-1 plane of a
@@ -162,17 +186,83 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
         // the carry (weight 2) is popcounted, which takes a third of the POPC work off the XU pipe -- the kernel's
         // binding unit (DESIGN.md "rooflines")
         uint32_t acc[4][4], ones[4][4];
+#ifdef DT_CSA2
+        uint32_t twos[4][4];
+#endif
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = ones[i][j] = 0u;
+            for (int j = 0; j < 4; ++j) {
+                acc[i][j] = ones[i][j] = 0u;
+#ifdef DT_CSA2
+                twos[i][j] = 0u;
+#endif
+            }
 
         for (int c = 0; c < n_chunks; ++c, ++it) {
             const int s = it % DT_STAGES;
             const uint32_t ph = (it / DT_STAGES) & 1;
+#if DT_SELF_PRODUCE
+            if (warp == 0) produce_next();
+#endif
             mbar_wait(&full_bar[s], ph);
             const uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
             const uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
+#ifdef DT_CSA2
+            // EXPERIMENT (off by default, measured r01: spills at 96 registers, no gain): two-level carry-save counter
+            // over the valid words: per four words three full adders (6 LOP3) and ONE popcount (of the weight-4
+            // carry): 1.25 POPC + 5.5 LOP3 per word pair
+#pragma unroll 1
+            for (int w = 0; w < DT_WC; w += 4) {
+                uint32_t ca[4][4];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int ww = w + 2 * half + h;
+                        const uint4 ql = *reinterpret_cast<const uint4*>(sq + (0 * DT_WC + ww) * DT_TQ + 4 * tq);
+                        const uint4 qh = *reinterpret_cast<const uint4*>(sq + (1 * DT_WC + ww) * DT_TQ + 4 * tq);
+                        const uint4 qv = *reinterpret_cast<const uint4*>(sq + (2 * DT_WC + ww) * DT_TQ + 4 * tq);
+                        const uint4 rl = *reinterpret_cast<const uint4*>(sr + (0 * DT_WC + ww) * DT_TR + 4 * tr);
+                        const uint4 rh = *reinterpret_cast<const uint4*>(sr + (1 * DT_WC + ww) * DT_TR + 4 * tr);
+                        const uint4 rv = *reinterpret_cast<const uint4*>(sr + (2 * DT_WC + ww) * DT_TR + 4 * tr);
+                        qlo[h][0] = ql.x; qlo[h][1] = ql.y; qlo[h][2] = ql.z; qlo[h][3] = ql.w;
+                        qhi[h][0] = qh.x; qhi[h][1] = qh.y; qhi[h][2] = qh.z; qhi[h][3] = qh.w;
+                        qva[h][0] = qv.x; qva[h][1] = qv.y; qva[h][2] = qv.z; qva[h][3] = qv.w;
+                        rlo[h][0] = rl.x; rlo[h][1] = rl.y; rlo[h][2] = rl.z; rlo[h][3] = rl.w;
+                        rhi[h][0] = rh.x; rhi[h][1] = rh.y; rhi[h][2] = rh.z; rhi[h][3] = rh.w;
+                        rva[h][0] = rv.x; rva[h][1] = rv.y; rva[h][2] = rv.z; rva[h][3] = rv.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t v0 = lop3<0xc0>(qva[0][i], rva[0][j], 0u);
+                            const uint32_t v1 = lop3<0xc0>(qva[1][i], rva[1][j], 0u);
+                            const uint32_t x0 = lop3<0x3c>(qlo[0][i], rlo[0][j], 0u);
+                            const uint32_t x1 = lop3<0x3c>(qlo[1][i], rlo[1][j], 0u);
+                            const uint32_t t0 = lop3<0xbe>(qhi[0][i], rhi[0][j], x0);
+                            const uint32_t t1 = lop3<0xbe>(qhi[1][i], rhi[1][j], x1);
+                            const uint32_t m0 = lop3<0xc0>(t0, v0, 0u);
+                            const uint32_t m1 = lop3<0xc0>(t1, v1, 0u);
+                            const uint32_t o = ones[i][j];
+                            const uint32_t c = lop3<0xe8>(o, v0, v1);
+                            ones[i][j] = lop3<0x96>(o, v0, v1);
+                            acc[i][j] = __popc(m0) * k_one + acc[i][j];
+                            acc[i][j] = __popc(m1) * k_one + acc[i][j];
+                            if (half == 0) {
+                                ca[i][j] = c;
+                            } else {
+                                const uint32_t t2 = twos[i][j];
+                                const uint32_t c4 = lop3<0xe8>(t2, ca[i][j], c);
+                                twos[i][j] = lop3<0x96>(t2, ca[i][j], c);
+                                acc[i][j] = __popc(c4) * k_four16 + acc[i][j];
+                            }
+                        }
+                }
+            }
+#else
 #pragma unroll 1
             for (int w = 0; w < DT_WC; w += 2) {
                 uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
@@ -215,6 +305,7 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
                         acc[i][j] = __popc(carry) * k_two17 + acc[i][j];
                     }
             }
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -223,7 +314,11 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+#ifdef DT_CSA2
+                const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16) + (__popc(twos[i][j]) << 17);
+#else
                 const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16);
+#endif
                 accM[i][j] = a2 & 0xffffu;
                 accV[i][j] = a2 >> 16;
             }
