@@ -33,8 +33,6 @@ struct apples_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;       // host->device staging of the next sub-batch overlaps compute
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    cudaStream_t sel_stream = nullptr;        // selection of sub-batch b runs here while the dense kernel of b+1 runs
-    cudaEvent_t ev_dense[2] = {nullptr, nullptr}, ev_sel[2] = {nullptr, nullptr};
     std::string err;
 
     // tree
@@ -48,7 +46,7 @@ struct apples_ctx {
     int n_cols = 0;
     DevBuf col_node;
     // per-batch work buffers
-    DevBuf q_rm, q_wm, keys, keys2, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
+    DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
     DevBuf q_bytes, q_bytes2, q_rm2, bad_flag;
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
@@ -250,16 +248,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
     if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
-    const bool two_bufs = n > QB;  // more than one sub-batch: stage the next one while this one computes, and run the
-                                   // selection of sub-batch b (latency-bound, few issue slots) on a second stream
-                                   // next to the dense kernel of b+1 (integer-pipe-bound): both fit on an SM
-    if (two_bufs && ensure(ctx, ctx->keys2, (size_t)QB * ldk * key_bytes)) return -1;
-    if (two_bufs && !matrix && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
+    const bool two_bufs = n > QB;  // more than one sub-batch: stage the next one while this one computes
     if (io.h_bytes) {
         if (ensure(ctx, ctx->q_bytes, (size_t)QB * io.byte_stride) || ensure(ctx, ctx->bad_flag, 4)) return -1;
         if (two_bufs && ensure(ctx, ctx->q_bytes2, (size_t)QB * io.byte_stride)) return -1;
         CK(cudaMemsetAsync(ctx->bad_flag.p, 0, 4, s));
     }
+    if (io.h_queries && two_bufs && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
@@ -307,6 +302,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     SelectArgs sa{};
     sa.n_units = n_units;
     sa.ldk = ldk;
+    sa.keys_nuc = (const uint32_t*)ctx->keys.p;
+    sa.keys_f64 = (const double*)ctx->keys.p;
     sa.goff = (const int*)ctx->goff.p;
     sa.gmem = (const int*)ctx->gmem.p;
     sa.ref_node = (const int*)ctx->ref_node.p;
@@ -328,11 +325,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.tree = tree_dev(ctx);
 
     // distances + selection of the `nb` queries whose packed rows / matrix rows are at d_q / ctx->keys
-    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a, void* keys_buf, int obuf) -> int {
-        // obuf >= 0: selection goes to the selection stream (overlap), guarded by ev_dense[obuf] / ev_sel[obuf]
+    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a) -> int {
         const int nb_pad = round_up(nb, DT_TQ);
-        a.keys_nuc = (const uint32_t*)keys_buf;
-        a.keys_f64 = (const double*)keys_buf;
         if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
@@ -342,7 +336,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             {
                 Span sp(ctx, T_DENSE);
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, nb_pad, (const uint32_t*)ctx->reps_wm.p, ctx->rep_pad,
-                                      ctx->Wp, (uint32_t*)keys_buf, ldk, ctx->num_sms, s);
+                                      ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -350,7 +344,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         } else if (sel_kind == SEL_AA) {
             Span sp(ctx, T_DENSE);
             launch_dense_aa((const uint8_t*)d_q, nb, (const uint8_t*)ctx->reps_rm.p, ctx->n_rep, ctx->Lp, ctx->L,
-                            prm->overlap_frac, (double*)keys_buf, ldk, nullptr, s);
+                            prm->overlap_frac, (double*)ctx->keys.p, ldk, nullptr, s);
             ctx->n_launch += 1;
             ctx->n_dense_launch += 1;
             ctx->n_pairs += (double)nb * ctx->n_rep;
@@ -359,19 +353,12 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         a.n = nb;
         a.q_nuc = (const uint32_t*)d_q;
         a.q_aa = (const uint8_t*)d_q;
-        cudaStream_t ss = s;
-        if (obuf >= 0) {
-            ss = ctx->sel_stream;
-            CK(cudaEventRecord(ctx->ev_dense[obuf], s));
-            CK(cudaStreamWaitEvent(ss, ctx->ev_dense[obuf], 0));
-        }
         {
-            Span sp(ctx, T_SELECT, ss);
-            launch_select(sel_kind, a, ss);
+            Span sp(ctx, T_SELECT);
+            launch_select(sel_kind, a, s);
             ctx->n_launch += 1;
         }
         CK(cudaGetLastError());
-        if (obuf >= 0) CK(cudaEventRecord(ctx->ev_sel[obuf], ss));
         return 0;
     };
 
@@ -382,25 +369,19 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.obs_dist = (double*)ctx->obs_dist.p;
     sa.obs_len = (int*)ctx->obs_len.p;
     sa.pair_counter = (unsigned long long*)ctx->pair_counter.p;
-    bool used[2] = {false, false};      // staging buffer `buf` holds a sub-batch that a selection may still be reading
-    bool sel_pending[2] = {false, false};
+    bool used[2] = {false, false};
     int sbi = 0;
     for (int sb0 = 0; sb0 < n; sb0 += QB, ++sbi) {
         const int nb = std::min(QB, n - sb0);
         const void* d_q = nullptr;
         const int buf = two_bufs ? (sbi & 1) : 0;
-        void* keys_buf = buf ? ctx->keys2.p : ctx->keys.p;
-        void* qrm_buf = buf ? ctx->q_rm2.p : ctx->q_rm.p;
-        // the selection of sub-batch b-2 read keys[buf] and the query rows of `buf`: the compute stream must not
-        // overwrite them before it has finished
-        if (sel_pending[buf]) CK(cudaStreamWaitEvent(s, ctx->ev_sel[buf], 0));
         if (matrix) {
             Span sp(ctx, T_H2D);
-            CK(cudaMemcpyAsync(keys_buf, io.h_rows + (size_t)(base0 + sb0) * ctx->n_cols, (size_t)nb * qrow,
+            CK(cudaMemcpyAsync(ctx->keys.p, io.h_rows + (size_t)(base0 + sb0) * ctx->n_cols, (size_t)nb * qrow,
                                cudaMemcpyHostToDevice, s));
         } else if (io.h_queries || io.h_bytes) {
             // staged on the copy stream into one of two buffers; the compute stream waits for the copy, the copy
-            // stream waits until the previous user of the buffer (pack kernel or selection) has finished
+            // stream waits until the compute stream has finished with the buffer's previous contents
             cudaStream_t cs = ctx->copy_stream;
             if (used[buf]) CK(cudaStreamWaitEvent(cs, ctx->ev_free[buf], 0));
             else if (sbi == 0) {
@@ -412,7 +393,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             {
                 Span sp(ctx, T_H2D, cs);
                 if (io.h_queries) {
-                    stage = qrm_buf;
+                    stage = buf ? ctx->q_rm2.p : ctx->q_rm.p;
                     CK(cudaMemcpyAsync(stage, (const char*)io.h_queries + (size_t)(base0 + sb0) * qrow, (size_t)nb * qrow,
                                        cudaMemcpyHostToDevice, cs));
                 } else {
@@ -424,23 +405,21 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             CK(cudaEventRecord(ctx->ev_ready[buf], cs));
             CK(cudaStreamWaitEvent(s, ctx->ev_ready[buf], 0));
             if (io.h_bytes) {
-                CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, qrm_buf, (int*)ctx->bad_flag.p, s));
+                CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
+                               (int*)ctx->bad_flag.p, s));
                 ctx->n_launch += 1;
-                // the byte staging buffer is free as soon as the pack kernel has read it
-                CK(cudaEventRecord(ctx->ev_free[buf], s));
+                d_q = ctx->q_rm.p;
+            } else {
+                d_q = stage;
             }
-            d_q = qrm_buf;
             used[buf] = true;
         } else {
             d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
         }
         sa.q_begin = sb0;
-        if (distances_and_select(d_q, nb, sa, keys_buf, two_bufs ? buf : -1)) return -1;
-        if (two_bufs) sel_pending[buf] = true;
-        // packed host queries are read by the selection from the staging buffer itself
-        if (used[buf] && io.h_queries) CK(cudaEventRecord(ctx->ev_free[buf], two_bufs ? ctx->sel_stream : s));
+        if (distances_and_select(d_q, nb, sa)) return -1;
+        if (used[buf]) CK(cudaEventRecord(ctx->ev_free[buf], s));
     }
-    if (two_bufs) CK(cudaStreamSynchronize(ctx->sel_stream));
 
     // ---------------- phase 2 ----------------
     auto fetch_counts = [&]() -> int {
@@ -585,7 +564,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             sb.obs_dist = (double*)ctx->obs_dist2.p;
             sb.obs_len = (int*)ctx->obs_len2.p;
             sb.pair_counter = nullptr;
-            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, ctx->keys.p, -1)) return -1;
+            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
             if (fetch_counts()) return -1;
             CK(cudaStreamSynchronize(s));
             if (io.obs_count) {
@@ -712,17 +691,9 @@ int apples_ctx_create(int device, apples_ctx** out) {
         delete ctx;
         return -4;
     }
-    if (cudaStreamCreateWithFlags(&ctx->sel_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaStreamDestroy(ctx->copy_stream);
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
-        return -4;
-    }
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->ev_dense[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->ev_sel[i], cudaEventDisableTiming);
     }
     if (dense_nuc_configure() != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
@@ -739,7 +710,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
-                     &ctx->q_wm, &ctx->keys, &ctx->keys2, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
+                     &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
@@ -754,10 +725,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
-        if (ctx->ev_dense[i]) cudaEventDestroy(ctx->ev_dense[i]);
-        if (ctx->ev_sel[i]) cudaEventDestroy(ctx->ev_sel[i]);
     }
-    if (ctx->sel_stream) cudaStreamDestroy(ctx->sel_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -257,7 +257,7 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
         if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-            constexpr int NR = 2;  // 96 registers: a selection block then fits on an SM next to the dense kernel's CTA
+            constexpr int NR = 4;
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
                 int rows[NR];
                 uint32_t c[NR];
@@ -303,7 +303,7 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128, 5) select_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
