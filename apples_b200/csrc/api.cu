@@ -40,7 +40,7 @@ struct apples_ctx {
     DevBuf t_parent, t_elen, t_level, t_first;
     // reference
     int kind = -1, L = 0, W = 0, Wp = 0, Lp = 0, n_ref = 0, n_rep = 0, rep_pad = 0, ref_pad = 0;
-    DevBuf refs_rm, reps_rm, reps_wm, refs_wm, ref_node, goff, gmem;
+    DevBuf refs_rm, reps_rm, reps_wm, refs_wm, reps_nv, refs_nv, q_nv, ref_node, goff, gmem;
     bool refs_wm_ready = false;
     // matrix mode
     int n_cols = 0;
@@ -258,6 +258,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
+        if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_nv, (size_t)QB * 4)) return -1;
     }
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
@@ -330,12 +331,14 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
-                launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, s);
-                ctx->n_launch += 1;
+                launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, DT_TQ, s);
+                launch_row_valid((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_nv.p, nb_pad, s);
+                ctx->n_launch += 2;
             }
             {
                 Span sp(ctx, T_DENSE);
-                launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, nb_pad, (const uint32_t*)ctx->reps_wm.p, ctx->rep_pad,
+                launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
+                                      (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
                                       ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
@@ -709,7 +712,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
-                     &ctx->reps_wm, &ctx->refs_wm, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
+                     &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
@@ -800,7 +803,9 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
         if (ensure(ctx, ctx->reps_wm, wm)) return -1;
         CK(cudaMemsetAsync(ctx->reps_wm.p, 0, wm, ctx->stream));
         launch_transpose_nuc((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_wm.p, ctx->Wp,
-                             ctx->rep_pad, ctx->stream);
+                             ctx->rep_pad, DT_TR, ctx->stream);
+        if (ensure(ctx, ctx->reps_nv, (size_t)ctx->rep_pad * 4)) return -1;
+        launch_row_valid((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_nv.p, ctx->rep_pad, ctx->stream);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -904,7 +909,9 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
         if (ensure(ctx, ctx->reps_wm, wm)) return -1;
         CK(cudaMemsetAsync(ctx->reps_wm.p, 0, wm, s));
         launch_transpose_nuc((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_wm.p, ctx->Wp,
-                             ctx->rep_pad, s);
+                             ctx->rep_pad, DT_TR, s);
+        if (ensure(ctx, ctx->reps_nv, (size_t)ctx->rep_pad * 4)) return -1;
+        launch_row_valid((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_nv.p, ctx->rep_pad, s);
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(s));
     }
@@ -995,9 +1002,9 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
     cudaStream_t s = ctx->stream;
     const size_t row = query_row_bytes(ctx);
     const size_t n_out = (size_t)nq * ctx->n_ref;
-    DevBuf dq, dm, dv, dd, qwm;
+    DevBuf dq, dm, dv, dd, qwm, qnv;
     int rc = 0;
-    auto cleanup = [&]() { release(dq); release(dm); release(dv); release(dd); release(qwm); };
+    auto cleanup = [&]() { release(dq); release(dm); release(dv); release(dd); release(qwm); release(qnv); };
     if (ensure(ctx, dq, (size_t)nq * row) || ensure(ctx, dm, n_out * 4) || ensure(ctx, dv, n_out * 4) ||
         ensure(ctx, dd, n_out * 8)) { cleanup(); return -1; }
     cudaMemcpyAsync(dq.p, packed_queries, (size_t)nq * row, cudaMemcpyHostToDevice, s);
@@ -1008,13 +1015,18 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
             if (ensure(ctx, ctx->refs_wm, wm)) { cleanup(); return -1; }
             cudaMemsetAsync(ctx->refs_wm.p, 0, wm, s);
             launch_transpose_nuc((const uint32_t*)ctx->refs_rm.p, ctx->n_ref, ctx->W, (uint32_t*)ctx->refs_wm.p, ctx->Wp,
-                                 ctx->ref_pad, s);
+                                 ctx->ref_pad, DT_TR, s);
+            if (ensure(ctx, ctx->refs_nv, (size_t)ctx->ref_pad * 4)) { cleanup(); return -1; }
+            launch_row_valid((const uint32_t*)ctx->refs_rm.p, ctx->n_ref, ctx->W, (uint32_t*)ctx->refs_nv.p, ctx->ref_pad, s);
             ctx->refs_wm_ready = true;
         }
         const int q_pad = round_up((int)nq, DT_TQ);
         if (ensure(ctx, qwm, (size_t)3 * ctx->Wp * q_pad * 4)) { cleanup(); return -1; }
-        launch_transpose_nuc((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qwm.p, ctx->Wp, q_pad, s);
-        launch_dense_nuc_full((const uint32_t*)qwm.p, q_pad, (int)nq, (const uint32_t*)ctx->refs_wm.p, ctx->ref_pad,
+        if (ensure(ctx, qnv, (size_t)q_pad * 4)) { cleanup(); return -1; }
+        launch_transpose_nuc((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qwm.p, ctx->Wp, q_pad, DT_TQ, s);
+        launch_row_valid((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qnv.p, q_pad, s);
+        launch_dense_nuc_full((const uint32_t*)qwm.p, (const uint32_t*)qnv.p, q_pad, (int)nq,
+                              (const uint32_t*)ctx->refs_wm.p, (const uint32_t*)ctx->refs_nv.p, ctx->ref_pad,
                               ctx->n_ref, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
                               (double*)dd.p, ctx->num_sms, s);
     } else {

@@ -28,7 +28,7 @@ constexpr int DT_WC = DT_WC_V;  // 32-site words per pipeline stage
 constexpr int DT_STAGES = DT_STAGES_V;    // TMA pipeline depth
 constexpr int DT_CONSUMERS = (DT_TQ / 4) * (DT_TR / 4);  // one thread per 4x4 block of pairs
 #ifndef DT_SELF_PRODUCE
-#define DT_SELF_PRODUCE 0
+#define DT_SELF_PRODUCE 1  // 1: no producer warp, thread 0 keeps the ring full (128 registers per thread); 0: 17th warp
 #endif
 constexpr int DT_THREADS = DT_CONSUMERS + (DT_SELF_PRODUCE ? 0 : 32);  // + one producer warp unless warp 0 produces
 constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
@@ -171,11 +171,15 @@ struct PlaceArgs {
 };
 
 // kernels / launchers implemented in the .cu files
-void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int Wp, int rows_pad, cudaStream_t s);
-void launch_dense_nuc_keys(const uint32_t* q_wm, int q_pad, const uint32_t* r_wm, int r_pad, int Wp, uint32_t* keys,
-                           int64_t ldk, int num_sms, cudaStream_t s);
-void launch_dense_nuc_full(const uint32_t* q_wm, int q_pad, int nq, const uint32_t* r_wm, int r_pad, int n_ref, int Wp,
-                           int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms, cudaStream_t s);
+void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int Wp, int rows_pad, int tile_rows,
+                          cudaStream_t s);
+void launch_row_valid(const uint32_t* rm, int rows, int W, uint32_t* nv, int rows_pad, cudaStream_t s);
+void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
+                           const uint32_t* r_nv, int r_pad, int Wp, uint32_t* keys, int64_t ldk, int num_sms,
+                           cudaStream_t s);
+void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
+                           const uint32_t* r_nv, int r_pad, int n_ref, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
+                           double* dist, int num_sms, cudaStream_t s);
 void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
                      int64_t ldd, uint32_t* valid_out, cudaStream_t s);
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s);

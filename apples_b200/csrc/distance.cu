@@ -4,6 +4,11 @@
 // Nucleotide: sequences are three bit-planes (lo, hi, valid) of 32-site words.  For a (query, reference) pair
 //   valid    = popc(qv & rv)                                    distance.py:733-734
 //   mismatch = popc(((qlo ^ rlo) | (qhi ^ rhi)) & qv & rv)      distance.py:737
+// The dense kernel gets both from two cheaper counts.  With the code bits cleared at invalid sites (done when the
+// operands are laid out), x = qv ^ rv marks the sites where exactly one side is valid, and
+// z = (qlo ^ rlo) | (qhi ^ rhi) | x marks those plus the mismatching valid sites, so
+//   E1 = popc(x),  D = popc(z):   mismatch = D - E1,   valid = (nq + nr - E1) / 2
+// (nq, nr = valid sites of the two rows, counted once per row): 3 LOP3 per 32 sites instead of 4.
 // The dense kernel computes all pairs of a query block against all representatives with a GEMM-like tiling:
 // operands are stored word-major ([plane][word][row]) so that one (plane, word) slice of a 64-row tile is 256
 // contiguous bytes; a producer warp streams those slices into a 4-stage shared-memory ring with 1-D TMA bulk copies
@@ -11,6 +16,7 @@
 // queries x 64 representatives, one persistent CTA per SM) and do the LOP3/POPC work.  The binding resources are the
 // integer pipes (XU POPC, ALU LOP3), not HBM ("rooflines").
 #include "common.cuh"
+#include <type_traits>
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk async copy (TMA)
@@ -51,6 +57,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  : "memory");
 }
 
+// which of a thread's 16 pairs also carry-save their mismatch words (DT_MCSA pairs, spread over the 4x4 block)
+#ifndef DT_MCSA
+#define DT_MCSA 14  // measured optimum on B200 (profiles/dense_variants_r01.txt)
+#endif
+__host__ __device__ constexpr int mcsa_slot(int i, int j) { return ((i * 4 + ((j + i) & 3)) * DT_MCSA) / 16; }
+__host__ __device__ constexpr bool mcsa_pair(int i, int j) {
+    const int p = i * 4 + ((j + i) & 3);
+    return DT_MCSA > 0 && (p == 0 ? true : (p * DT_MCSA) / 16 != ((p - 1) * DT_MCSA) / 16);
+}
+
 // three-input logic op with an explicit truth table (a = 0xf0, b = 0xcc, c = 0xaa)
 template <int LUT>
 __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
@@ -60,35 +76,64 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// row-major [rows][3][W]  ->  word-major [3][Wp][rows_pad]   (padding must be pre-zeroed by the caller)
+// row-major [rows][3][W]  ->  tile-major [rows_pad / T][Wp / WC][3][WC][T]   (padding must be pre-zeroed by the caller)
+// One pipeline stage of a tile -- 3 planes x WC words x T rows -- is one contiguous block: a single bulk copy.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void transpose_nuc_kernel(const uint32_t* __restrict__ rm, int rows, int W, uint32_t* __restrict__ wm, int Wp,
-                                     int rows_pad) {
+                                     int rows_pad, int T) {
     __shared__ uint32_t tile[32][33];
     const int plane = blockIdx.z;
     const int r0 = blockIdx.y * 32, w0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int r = r0 + i, w = w0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && w < W) ? rm[((size_t)r * 3 + plane) * W + w] : 0u;
+        uint32_t x = 0u;
+        if (r < rows && w < W) {
+            x = rm[((size_t)r * 3 + plane) * W + w];
+            if (plane < 2) x &= rm[((size_t)r * 3 + 2) * W + w];  // code bits are zero where the site is invalid
+        }
+        tile[i][threadIdx.x] = x;
     }
     __syncthreads();
+    const int n_chunks = Wp / DT_WC;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int w = w0 + i, r = r0 + threadIdx.x;
-        if (w < Wp && r < rows_pad) wm[((size_t)plane * Wp + w) * rows_pad + r] = tile[threadIdx.x][i];
+        if (w < Wp && r < rows_pad) {
+            const size_t blk = (size_t)(r / T) * n_chunks + w / DT_WC;
+            wm[((blk * 3 + plane) * DT_WC + w % DT_WC) * T + r % T] = tile[threadIdx.x][i];
+        }
     }
 }
 
-void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int Wp, int rows_pad, cudaStream_t s) {
+void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int Wp, int rows_pad, int tile_rows,
+                          cudaStream_t s) {
     dim3 grid((Wp + 31) / 32, (rows_pad + 31) / 32, 3), block(32, 8);
-    transpose_nuc_kernel<<<grid, block, 0, s>>>(rm, rows, W, wm, Wp, rows_pad);
+    transpose_nuc_kernel<<<grid, block, 0, s>>>(rm, rows, W, wm, Wp, rows_pad, tile_rows);
+}
+
+// valid sites per row (one warp per row); rows >= `rows` (padding) get 0
+__global__ void row_valid_kernel(const uint32_t* __restrict__ rm, int rows, int W, uint32_t* __restrict__ nv, int rows_pad) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (r >= rows_pad) return;
+    uint32_t c = 0;
+    if (r < rows)
+        for (int w = lane; w < W; w += 32) c += __popc(rm[((size_t)r * 3 + 2) * W + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) nv[r] = c;
+}
+
+void launch_row_valid(const uint32_t* rm, int rows, int W, uint32_t* nv, int rows_pad, cudaStream_t s) {
+    row_valid_kernel<<<(rows_pad + 7) / 8, 256, 0, s>>>(rm, rows, W, nv, rows_pad);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // dense nucleotide kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct DenseNucArgs {
-    const uint32_t* q_wm;  // [3][Wp][q_pad]
-    const uint32_t* r_wm;  // [3][Wp][r_pad]
+    const uint32_t* q_wm;  // [q_pad / TQ][Wp / WC][3][WC][TQ]
+    const uint32_t* r_wm;  // [r_pad / TR][Wp / WC][3][WC][TR]
+    const uint32_t* q_nv;  // [q_pad] valid sites per query row
+    const uint32_t* r_nv;  // [r_pad]
     int q_pad, r_pad, Wp;
     // keys epilogue
     uint32_t* keys;
@@ -123,45 +168,47 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     }
     __syncthreads();
 
-    // one (plane, word) slice of a tile's rows = DT_TQ*4 / DT_TR*4 contiguous bytes per bulk copy
+    // one pipeline stage of a tile is contiguous in global memory (tile-major layout): two bulk copies per stage,
+    // issued by one thread
     auto issue_stage = [&](uint32_t git, int tile, int c) {
         const int s = git % DT_STAGES;
-        const uint32_t ph = (git / DT_STAGES) & 1;
         const int qt = tile / n_rt, rt = tile % n_rt;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], DT_STAGE_BYTES);
-        __syncwarp();
+        mbar_arrive_expect_tx(&full_bar[s], DT_STAGE_BYTES);
         uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
         uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
-        for (int i = lane; i < 3 * DT_WC; i += 32) {
-            const int plane = i / DT_WC, w = i % DT_WC;
-            const size_t grow = (size_t)plane * a.Wp + (size_t)c * DT_WC + w;
-            tma_bulk_g2s(sq + i * DT_TQ, a.q_wm + grow * a.q_pad + (size_t)qt * DT_TQ, DT_TQ * 4, &full_bar[s]);
-            tma_bulk_g2s(sr + i * DT_TR, a.r_wm + grow * a.r_pad + (size_t)rt * DT_TR, DT_TR * 4, &full_bar[s]);
-        }
+        tma_bulk_g2s(sq, a.q_wm + ((size_t)qt * n_chunks + c) * (3 * DT_WC * DT_TQ), 3 * DT_WC * DT_TQ * 4, &full_bar[s]);
+        tma_bulk_g2s(sr, a.r_wm + ((size_t)rt * n_chunks + c) * (3 * DT_WC * DT_TR), 3 * DT_WC * DT_TR * 4, &full_bar[s]);
     };
 #if DT_SELF_PRODUCE
-    // EXPERIMENT (off by default, measured r01: 56 vs 78 Tcell-sites/s with the dedicated producer warp): no producer
-    // warp, consumer warp 0 issues the copies of chunk it + STAGES - 1 before it computes chunk `it`.  It frees the
-    // 17th warp's register granule (128 instead of 96 registers per thread) but couples warp 0 to the slowest warp.
+    // No producer warp (a 17th warp would cap the kernel at 96 registers per thread: 5 warps on one scheduler).  Thread
+    // 0 keeps the ring full: before computing chunk `it` it issues every chunk < it + STAGES whose stage has been
+    // released (non-blocking test), and blocks only if chunk `it` itself has not been issued yet.
     uint32_t p_it = 0;
     int p_tile = blockIdx.x, p_c = 0;
-    auto produce_next = [&]() {
-        if (p_tile < n_tiles) {
+    auto produce = [&](uint32_t it_now) {
+        while (p_tile < n_tiles && p_it < it_now + DT_STAGES) {
+            const int ps = p_it % DT_STAGES;
+            const uint32_t pph = ((p_it / DT_STAGES) & 1) ^ 1;
+            if (p_it == it_now) {
+                mbar_wait(&empty_bar[ps], pph);
+            } else if (!mbar_try_wait(&empty_bar[ps], pph)) {
+                break;
+            }
             issue_stage(p_it, p_tile, p_c);
             ++p_it;
             if (++p_c == n_chunks) { p_c = 0; p_tile += gridDim.x; }
         }
     };
-    if (warp == 0)
-        for (int k = 0; k < DT_STAGES - 1; ++k) produce_next();
 #else
     if (warp == DT_CONSUMERS / 32) {
         // ===== producer warp =====
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int c = 0; c < n_chunks; ++c, ++it) {
-                issue_stage(it, tile, c);
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    mbar_wait(&empty_bar[it % DT_STAGES], ((it / DT_STAGES) & 1) ^ 1);
+                    issue_stage(it, tile, c);
+                }
             }
         }
         return;
@@ -176,93 +223,34 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
 #endif
     uint32_t it = 0;
     const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
-#ifdef DT_CSA2
-    const uint32_t k_four16 = a.k_two17 << 1;
-#endif
+    const uint32_t k_two = a.k_two17 >> 16;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int qt = tile / n_rt, rt = tile % n_rt;
-        // per pair: acc = mismatch count (low 16 bits) | valid count (high 16 bits); `ones` is the weight-1 plane of a
-        // carry-save counter over the valid words: two valid words are folded with one full adder (2 LOP3) and only
-        // the carry (weight 2) is popcounted, which takes a third of the POPC work off the XU pipe -- the kernel's
-        // binding unit (DESIGN.md "rooflines")
+        // per pair: acc = D (low 16 bits) | E1 (high 16 bits); `ones` is the weight-1 plane of a carry-save counter over
+        // the x words: two words are folded with one full adder (2 LOP3) and only the carry (weight 2) is popcounted,
+        // which moves POPC work from the XU pipe to the ALU pipe; DT_MCSA of the 16 pairs do the same for their z
+        // words, which levels the two pipes (DESIGN.md "rooflines")
         uint32_t acc[4][4], ones[4][4];
-#ifdef DT_CSA2
-        uint32_t twos[4][4];
-#endif
+        uint32_t onesM[DT_MCSA > 0 ? DT_MCSA : 1];
+#pragma unroll
+        for (int i = 0; i < (DT_MCSA > 0 ? DT_MCSA : 1); ++i) onesM[i] = 0u;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 acc[i][j] = ones[i][j] = 0u;
-#ifdef DT_CSA2
-                twos[i][j] = 0u;
-#endif
             }
 
         for (int c = 0; c < n_chunks; ++c, ++it) {
             const int s = it % DT_STAGES;
             const uint32_t ph = (it / DT_STAGES) & 1;
 #if DT_SELF_PRODUCE
-            if (warp == 0) produce_next();
+            if (tid == 0) produce(it);
+            if (warp == 0) __syncwarp();
 #endif
             mbar_wait(&full_bar[s], ph);
             const uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
             const uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
-#ifdef DT_CSA2
-            // EXPERIMENT (off by default, measured r01: spills at 96 registers, no gain): two-level carry-save counter
-            // over the valid words: per four words three full adders (6 LOP3) and ONE popcount (of the weight-4
-            // carry): 1.25 POPC + 5.5 LOP3 per word pair
-#pragma unroll 1
-            for (int w = 0; w < DT_WC; w += 4) {
-                uint32_t ca[4][4];
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int ww = w + 2 * half + h;
-                        const uint4 ql = *reinterpret_cast<const uint4*>(sq + (0 * DT_WC + ww) * DT_TQ + 4 * tq);
-                        const uint4 qh = *reinterpret_cast<const uint4*>(sq + (1 * DT_WC + ww) * DT_TQ + 4 * tq);
-                        const uint4 qv = *reinterpret_cast<const uint4*>(sq + (2 * DT_WC + ww) * DT_TQ + 4 * tq);
-                        const uint4 rl = *reinterpret_cast<const uint4*>(sr + (0 * DT_WC + ww) * DT_TR + 4 * tr);
-                        const uint4 rh = *reinterpret_cast<const uint4*>(sr + (1 * DT_WC + ww) * DT_TR + 4 * tr);
-                        const uint4 rv = *reinterpret_cast<const uint4*>(sr + (2 * DT_WC + ww) * DT_TR + 4 * tr);
-                        qlo[h][0] = ql.x; qlo[h][1] = ql.y; qlo[h][2] = ql.z; qlo[h][3] = ql.w;
-                        qhi[h][0] = qh.x; qhi[h][1] = qh.y; qhi[h][2] = qh.z; qhi[h][3] = qh.w;
-                        qva[h][0] = qv.x; qva[h][1] = qv.y; qva[h][2] = qv.z; qva[h][3] = qv.w;
-                        rlo[h][0] = rl.x; rlo[h][1] = rl.y; rlo[h][2] = rl.z; rlo[h][3] = rl.w;
-                        rhi[h][0] = rh.x; rhi[h][1] = rh.y; rhi[h][2] = rh.z; rhi[h][3] = rh.w;
-                        rva[h][0] = rv.x; rva[h][1] = rv.y; rva[h][2] = rv.z; rva[h][3] = rv.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t v0 = lop3<0xc0>(qva[0][i], rva[0][j], 0u);
-                            const uint32_t v1 = lop3<0xc0>(qva[1][i], rva[1][j], 0u);
-                            const uint32_t x0 = lop3<0x3c>(qlo[0][i], rlo[0][j], 0u);
-                            const uint32_t x1 = lop3<0x3c>(qlo[1][i], rlo[1][j], 0u);
-                            const uint32_t t0 = lop3<0xbe>(qhi[0][i], rhi[0][j], x0);
-                            const uint32_t t1 = lop3<0xbe>(qhi[1][i], rhi[1][j], x1);
-                            const uint32_t m0 = lop3<0xc0>(t0, v0, 0u);
-                            const uint32_t m1 = lop3<0xc0>(t1, v1, 0u);
-                            const uint32_t o = ones[i][j];
-                            const uint32_t c = lop3<0xe8>(o, v0, v1);
-                            ones[i][j] = lop3<0x96>(o, v0, v1);
-                            acc[i][j] = __popc(m0) * k_one + acc[i][j];
-                            acc[i][j] = __popc(m1) * k_one + acc[i][j];
-                            if (half == 0) {
-                                ca[i][j] = c;
-                            } else {
-                                const uint32_t t2 = twos[i][j];
-                                const uint32_t c4 = lop3<0xe8>(t2, ca[i][j], c);
-                                twos[i][j] = lop3<0x96>(t2, ca[i][j], c);
-                                acc[i][j] = __popc(c4) * k_four16 + acc[i][j];
-                            }
-                        }
-                }
-            }
-#else
 #pragma unroll 1
             for (int w = 0; w < DT_WC; w += 2) {
                 uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
@@ -285,27 +273,32 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        // 10 LOP3 per pair per two words, pinned with explicit LUTs (left to itself ptxas re-fuses the
-                        // AND into the adder and spends 12)
-                        const uint32_t v0 = lop3<0xc0>(qva[0][i], rva[0][j], 0u);            // qv & rv
-                        const uint32_t v1 = lop3<0xc0>(qva[1][i], rva[1][j], 0u);
-                        const uint32_t x0 = lop3<0x3c>(qlo[0][i], rlo[0][j], 0u);            // qlo ^ rlo
-                        const uint32_t x1 = lop3<0x3c>(qlo[1][i], rlo[1][j], 0u);
-                        const uint32_t t0 = lop3<0xbe>(qhi[0][i], rhi[0][j], x0);            // (qhi ^ rhi) | x
-                        const uint32_t t1 = lop3<0xbe>(qhi[1][i], rhi[1][j], x1);
-                        const uint32_t m0 = lop3<0xc0>(t0, v0, 0u);                          // mismatching valid sites
-                        const uint32_t m1 = lop3<0xc0>(t1, v1, 0u);
+                        // 6 LOP3 per pair per two words (+ 2 per carry-save adder), pinned with explicit LUTs
+                        const uint32_t x0 = lop3<0x3c>(qva[0][i], rva[0][j], 0u);            // exactly one side valid
+                        const uint32_t x1 = lop3<0x3c>(qva[1][i], rva[1][j], 0u);
+                        const uint32_t y0 = lop3<0xbe>(qlo[0][i], rlo[0][j], x0);            // (qlo ^ rlo) | x
+                        const uint32_t y1 = lop3<0xbe>(qlo[1][i], rlo[1][j], x1);
+                        const uint32_t m0 = lop3<0xbe>(qhi[0][i], rhi[0][j], y0);            // (qhi ^ rhi) | y
+                        const uint32_t m1 = lop3<0xbe>(qhi[1][i], rhi[1][j], y1);
                         const uint32_t o = ones[i][j];
-                        const uint32_t carry = lop3<0xe8>(o, v0, v1);                        // full adder: majority
-                        ones[i][j] = lop3<0x96>(o, v0, v1);                                  //             parity
-                        // the three accumulations go to the (idle) FMA pipe as IMADs: the multipliers are opaque
+                        const uint32_t carry = lop3<0xe8>(o, x0, x1);                        // full adder: majority
+                        ones[i][j] = lop3<0x96>(o, x0, x1);                                  //             parity
+                        // the accumulations go to the (idle) FMA pipe as IMADs: the multipliers are opaque
                         // registers so that ptxas cannot turn them back into ALU-pipe adds / shifts
-                        acc[i][j] = __popc(m0) * k_one + acc[i][j];
-                        acc[i][j] = __popc(m1) * k_one + acc[i][j];
+                        if (mcsa_pair(i, j)) {
+                            // DT_MCSA of the 16 pairs also fold their two mismatch words with a full adder (2 more
+                            // LOP3, 1 POPC less): levels the XU (POPC) and ALU (LOP3) pipes
+                            const uint32_t om = onesM[mcsa_slot(i, j)];
+                            const uint32_t cm = lop3<0xe8>(om, m0, m1);
+                            onesM[mcsa_slot(i, j)] = lop3<0x96>(om, m0, m1);
+                            acc[i][j] = __popc(cm) * k_two + acc[i][j];
+                        } else {
+                            acc[i][j] = __popc(m0) * k_one + acc[i][j];
+                            acc[i][j] = __popc(m1) * k_one + acc[i][j];
+                        }
                         acc[i][j] = __popc(carry) * k_two17 + acc[i][j];
                     }
             }
-#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
@@ -314,17 +307,27 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-#ifdef DT_CSA2
-                const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16) + (__popc(twos[i][j]) << 17);
-#else
-                const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16);
-#endif
-                accM[i][j] = a2 & 0xffffu;
-                accV[i][j] = a2 >> 16;
+                const uint32_t a2 = acc[i][j] + (__popc(ones[i][j]) << 16) +
+                                    (mcsa_pair(i, j) ? __popc(onesM[mcsa_slot(i, j)]) : 0);
+                accM[i][j] = a2 & 0xffffu;  // D
+                accV[i][j] = a2 >> 16;      // E1
             }
 
         // ---- epilogue ----
         const int q0 = qt * DT_TQ + 4 * tq, r0 = rt * DT_TR + 4 * tr;
+        {
+            const uint4 nq = *reinterpret_cast<const uint4*>(a.q_nv + q0);
+            const uint4 nr = *reinterpret_cast<const uint4*>(a.r_nv + r0);
+            const uint32_t nqa[4] = {nq.x, nq.y, nq.z, nq.w}, nra[4] = {nr.x, nr.y, nr.z, nr.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t D = accM[i][j], E1 = accV[i][j];
+                    accM[i][j] = D - E1;                         // mismatching valid sites
+                    accV[i][j] = (nqa[i] + nra[j] - E1) >> 1;    // sites valid on both sides
+                }
+        }
         if (!FULL) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -364,18 +367,20 @@ static int dense_grid(int q_pad, int r_pad, int num_sms) {
     return tiles < g ? tiles : g;
 }
 
-void launch_dense_nuc_keys(const uint32_t* q_wm, int q_pad, const uint32_t* r_wm, int r_pad, int Wp, uint32_t* keys,
+void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
+                           const uint32_t* r_nv, int r_pad, int Wp, uint32_t* keys,
                            int64_t ldk, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
-    a.q_wm = q_wm; a.r_wm = r_wm; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
+    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     dense_nuc_kernel<false><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);
 }
 
-void launch_dense_nuc_full(const uint32_t* q_wm, int q_pad, int nq, const uint32_t* r_wm, int r_pad, int n_ref, int Wp,
+void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
+                           const uint32_t* r_nv, int r_pad, int n_ref, int Wp,
                            int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
-    a.q_wm = q_wm; a.r_wm = r_wm; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp;
+    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     a.nq = nq; a.n_ref = n_ref; a.vmin = vmin; a.mism = mism; a.valid = valid; a.dist = dist;
     dense_nuc_kernel<true><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);

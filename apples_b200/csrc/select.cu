@@ -52,6 +52,25 @@ __device__ __forceinline__ bool key_less(const Key<SEL_MATRIX>& a, const Key<SEL
     return a.d < b.d || (a.d == b.d && a.idx < b.idx);
 }
 
+// "no key": compares greater than every real key (ratio 1 / 0 for counts, +inf for distances)
+constexpr int KEY_NONE_IDX = 0x7fffffff;
+template <int KIND>
+__device__ __forceinline__ Key<KIND> key_none() {
+    Key<KIND> k;
+    if constexpr (KIND == SEL_NUC) {
+        k.m = 1u;
+        k.v = 0u;
+    } else {
+        k.d = __longlong_as_double(0x7ff0000000000000ll);
+    }
+    k.idx = KEY_NONE_IDX;
+    return k;
+}
+template <int KIND>
+__device__ __forceinline__ bool key_is_none(const Key<KIND>& k) {
+    return k.idx == KEY_NONE_IDX;
+}
+
 __device__ __forceinline__ Key<SEL_NUC> key_shfl(const Key<SEL_NUC>& k, int src) {
     Key<SEL_NUC> o;
     o.m = __shfl_sync(FULLMASK, k.m, src);
@@ -114,6 +133,18 @@ __device__ __forceinline__ typename RawT<KIND>::T load_raw(const SelectArgs& a, 
         return a.keys_nuc[(size_t)row * a.ldk + u];
     else
         return a.keys_f64[(size_t)row * a.ldk + u];
+}
+
+// VEC consecutive raw keys starting at unit u (u a multiple of VEC; count-key rows are 16-byte aligned and padded)
+template <int KIND, int VEC>
+__device__ __forceinline__ void load_raw_vec(const SelectArgs& a, int row, int u, typename RawT<KIND>::T* out) {
+    if constexpr (KIND == SEL_NUC && VEC == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.keys_nuc + (size_t)row * a.ldk + u);
+        out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+    } else {
+        static_assert(VEC == 1, "fp64 keys are read one at a time");
+        out[0] = load_raw<KIND>(a, row, u);
+    }
 }
 
 // classify one unit.  returns 0 = invalid, 1 = near (dist <= threshold), 2 = far
@@ -326,41 +357,50 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
     st.zkey.idx = 0;
 
     // ---- one scan of the key row.  Near units (dist <= threshold) are expanded as they are met (rare: a handful per
-    // query, handled after a warp vote).  Far units only update a lane-local minimum -- registers only, no warp
-    // traffic -- because the far set is needed only while obs_num < baseobs, and then only its few smallest members:
-    // they are extracted afterwards, one at a time, as the warp-wide minimum of the 32 lane minima; the lane that
-    // owned it gets its next-smallest key by a cooperative re-scan of just its residue class (R / 32 keys). ----
-    constexpr int U = 8;  // independent key loads in flight per lane (the scan is latency-bound otherwise)
-    Key<KIND> lmin;       // smallest far key among the units u with u % 32 == lane
-    bool have_lmin = false;
-    for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * U) {
-        typename RawT<KIND>::T raw[U];
-        int cls[U];
+    // query, handled after a warp vote).  Far units only update the lane's two smallest far keys -- registers only, no
+    // warp traffic -- because the far set is needed only while obs_num < baseobs, and then only its few smallest
+    // members: they are extracted afterwards, one at a time, as the warp-wide minimum of the 32 lane minima; a lane
+    // that has used both of its keys gets the next two by a cooperative re-scan of just its class (R / 32 keys).
+    // Lane l owns the units u with (u / VEC) % 32 == l.  VEC = 1: 16-byte loads of four packed count keys per lane
+    // (VEC = 4, U = 4) measured slower on B200 (19.8 vs 17.0 ms per 125k queries): the scan is bound by the
+    // classification instructions, not by bytes in flight. ----
+    using Raw = typename RawT<KIND>::T;
+    constexpr int VEC = 1;
+    constexpr int U = 8;  // independent loads in flight per lane
+    Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
+    for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * VEC * U) {
+        Raw raw[U * VEC];
+        int cls[U * VEC];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const int u = u0 + j * 32 + lane;
-            raw[j] = 0;
-            if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
+            const int u = u0 + (j * 32 + lane) * VEC;
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) raw[j * VEC + c] = 0;
+            if (u < a.n_units) load_raw_vec<KIND, VEC>(a, slot, u, &raw[j * VEC]);
         }
         bool any_near = false;
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int u = u0 + j * 32 + lane;
+        for (int j = 0; j < U * VEC; ++j) {
+            const int u = u0 + ((j / VEC) * 32 + lane) * VEC + j % VEC;
             const Key<KIND> kj = make_key<KIND>(raw[j], u);
             cls[j] = (u < a.n_units) ? classify(a, kj) : 0;
             any_near |= cls[j] == 1;
-            if (cls[j] == 2 && (!have_lmin || key_less(kj, lmin))) {
-                lmin = kj;
-                have_lmin = true;
+            if (cls[j] == 2 && key_less(kj, l2)) {
+                if (key_less(kj, l1)) {
+                    l2 = l1;
+                    l1 = kj;
+                } else {
+                    l2 = kj;
+                }
             }
         }
         if (__any_sync(FULLMASK, any_near)) {
             // queued (lane t holds the t-th pending key) and expanded from ONE loop so that the member-distance code
             // is instantiated once
-            unsigned nearm[U];
+            unsigned nearm[U * VEC];
             bool any = false;
 #pragma unroll
-            for (int j = 0; j < U; ++j) {
+            for (int j = 0; j < U * VEC; ++j) {
                 nearm[j] = __ballot_sync(FULLMASK, cls[j] == 1);
                 any |= nearm[j] != 0u;
             }
@@ -370,11 +410,12 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
                 qkey.idx = -1;
                 any = false;
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
+                for (int j = 0; j < U * VEC; ++j) {
                     while (nearm[j] && qn < 32) {
                         const int src = __ffs(nearm[j]) - 1;
                         nearm[j] &= nearm[j] - 1;
-                        const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
+                        const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src),
+                                                            u0 + ((j / VEC) * 32 + src) * VEC + j % VEC);
                         if (lane == qn) qkey = uk;
                         ++qn;
                     }
@@ -388,44 +429,67 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
         }
     }
     // ---- far units in ascending (distance, index) order while obs_num < baseobs (Reference.py:146) ----
+    bool more = !key_is_none(l2);  // the class may hold far keys beyond the two kept
     while (st.obs_num < a.baseobs && st.kcount <= a.cap) {
         // warp-wide minimum of the lane minima
-        Key<KIND> g = lmin;
-        int owner = have_lmin ? lane : -1;
+        Key<KIND> g = l1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const Key<KIND> og = key_shfl_xor(g, o);
-            const int oo = __shfl_xor_sync(FULLMASK, owner, o);
-            if (oo >= 0 && (owner < 0 || key_less(og, g))) {
-                g = og;
-                owner = oo;
-            }
+            if (key_less(og, g)) g = og;
         }
-        if (owner < 0) break;  // no far unit left
+        if (key_is_none(g)) break;  // no far unit left
         expand_unit<KIND>(a, st, oslot, slot, self, g, lane, aa_tab);
-        // next-smallest key of the owner's residue class: units owner + 32 k, k split over the lanes
-        Key<KIND> nb;
-        bool have_nb = false;
-        for (int u = owner + 32 * lane; u < a.n_units; u += 32 * 32) {
-            const Key<KIND> kj = make_key<KIND>(load_raw<KIND>(a, slot, u), u);
-            if (classify(a, kj) == 2 && key_less(g, kj) && (!have_nb || key_less(kj, nb))) {
-                nb = kj;
-                have_nb = true;
-            }
+        const bool mine = l1.idx == g.idx;
+        if (mine) {
+            l1 = l2;
+            l2 = key_none<KIND>();
         }
-        int who = have_nb ? lane : -1;
+        const unsigned refill = __ballot_sync(FULLMASK, mine && more && key_is_none(l1));
+        if (refill) {
+            // the owner has used both of its keys: the two next-smallest keys of its class (loads (k * 32 + owner),
+            // k split over the lanes, four in flight per lane)
+            const int owner = __ffs(refill) - 1;
+            Key<KIND> n1 = key_none<KIND>(), n2 = key_none<KIND>();
+            constexpr int RU = 4;
+            for (int k0 = lane; k0 * 32 * VEC < a.n_units; k0 += 32 * RU) {
+                Raw rr[RU * VEC];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const Key<KIND> ob = key_shfl_xor(nb, o);
-            const int ow = __shfl_xor_sync(FULLMASK, who, o);
-            if (ow >= 0 && (who < 0 || key_less(ob, nb))) {
-                nb = ob;
-                who = ow;
+                for (int j = 0; j < RU; ++j) {
+                    const int u = ((k0 + 32 * j) * 32 + owner) * VEC;
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) rr[j * VEC + c] = 0;
+                    if (u < a.n_units) load_raw_vec<KIND, VEC>(a, slot, u, &rr[j * VEC]);
+                }
+#pragma unroll
+                for (int j = 0; j < RU * VEC; ++j) {
+                    const int u = ((k0 + 32 * (j / VEC)) * 32 + owner) * VEC + j % VEC;
+                    const Key<KIND> kj = make_key<KIND>(rr[j], u);
+                    if (u < a.n_units && classify(a, kj) == 2 && key_less(g, kj) && key_less(kj, n2)) {
+                        if (key_less(kj, n1)) {
+                            n2 = n1;
+                            n1 = kj;
+                        } else {
+                            n2 = kj;
+                        }
+                    }
+                }
             }
-        }
-        if (lane == owner) {
-            lmin = nb;
-            have_lmin = who >= 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {  // merge the sorted pairs
+                const Key<KIND> b1 = key_shfl_xor(n1, o), b2 = key_shfl_xor(n2, o);
+                if (key_less(b1, n1)) {
+                    n2 = key_less(n1, b2) ? n1 : b2;
+                    n1 = b1;
+                } else if (key_less(b1, n2)) {
+                    n2 = b1;
+                }
+            }
+            if (lane == owner) {
+                l1 = n1;
+                l2 = n2;
+                more = !key_is_none(n2);
+            }
         }
     }
 
