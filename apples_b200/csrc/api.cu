@@ -339,7 +339,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 Span sp(ctx, T_DENSE);
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
                                       (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
-                                      ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
+                                      ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -1027,7 +1027,7 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
         launch_row_valid((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qnv.p, q_pad, s);
         launch_dense_nuc_full((const uint32_t*)qwm.p, (const uint32_t*)qnv.p, q_pad, (int)nq,
                               (const uint32_t*)ctx->refs_wm.p, (const uint32_t*)ctx->refs_nv.p, ctx->ref_pad,
-                              ctx->n_ref, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
+                              ctx->n_ref, ctx->W, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
                               (double*)dd.p, ctx->num_sms, s);
     } else {
         launch_dense_aa((const uint8_t*)dq.p, (int)nq, (const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, ctx->L,

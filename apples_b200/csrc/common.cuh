@@ -16,11 +16,11 @@ constexpr int DT_TQ = DT_TQ_V;  // queries per CTA tile
 #endif
 constexpr int DT_TR = DT_TR_V;  // representatives per CTA tile
 #ifndef DT_WC_V
-#define DT_WC_V 16
+#define DT_WC_V 32
 #endif
 constexpr int DT_WC = DT_WC_V;  // 32-site words per pipeline stage
 #ifndef DT_STAGES_V
-#define DT_STAGES_V 4
+#define DT_STAGES_V 2
 #endif
 #ifndef DT_MINBLOCKS
 #define DT_MINBLOCKS 1
@@ -175,10 +175,10 @@ void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int
                           cudaStream_t s);
 void launch_row_valid(const uint32_t* rm, int rows, int W, uint32_t* nv, int rows_pad, cudaStream_t s);
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
-                           const uint32_t* r_nv, int r_pad, int Wp, uint32_t* keys, int64_t ldk, int num_sms,
+                           const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys, int64_t ldk, int num_sms,
                            cudaStream_t s);
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
-                           const uint32_t* r_nv, int r_pad, int n_ref, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
+                           const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
                            double* dist, int num_sms, cudaStream_t s);
 void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
                      int64_t ldd, uint32_t* valid_out, cudaStream_t s);

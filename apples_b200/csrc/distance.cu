@@ -59,7 +59,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 
 // which of a thread's 16 pairs also carry-save their mismatch words (DT_MCSA pairs, spread over the 4x4 block)
 #ifndef DT_MCSA
-#define DT_MCSA 14  // measured optimum on B200 (profiles/dense_variants_r01.txt)
+#define DT_MCSA 13  // measured optimum on B200 (profiles/dense_variants_r01.txt)
 #endif
 __host__ __device__ constexpr int mcsa_slot(int i, int j) { return ((i * 4 + ((j + i) & 3)) * DT_MCSA) / 16; }
 __host__ __device__ constexpr bool mcsa_pair(int i, int j) {
@@ -134,7 +134,7 @@ struct DenseNucArgs {
     const uint32_t* r_wm;  // [r_pad / TR][Wp / WC][3][WC][TR]
     const uint32_t* q_nv;  // [q_pad] valid sites per query row
     const uint32_t* r_nv;  // [r_pad]
-    int q_pad, r_pad, Wp;
+    int q_pad, r_pad, W, Wp;  // W words hold sites, Wp = W rounded up to whole pipeline stages (zero words)
     // keys epilogue
     uint32_t* keys;
     int64_t ldk;
@@ -251,8 +251,10 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
             mbar_wait(&full_bar[s], ph);
             const uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
             const uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
+            // the zero words that pad the last stage are not computed on
+            const int wend = min(DT_WC, ((a.W + 1) & ~1) - c * DT_WC);
 #pragma unroll 1
-            for (int w = 0; w < DT_WC; w += 2) {
+            for (int w = 0; w < wend; w += 2) {
                 uint32_t qlo[2][4], qhi[2][4], qva[2][4], rlo[2][4], rhi[2][4], rva[2][4];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -368,19 +370,19 @@ static int dense_grid(int q_pad, int r_pad, int num_sms) {
 }
 
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
-                           const uint32_t* r_nv, int r_pad, int Wp, uint32_t* keys,
+                           const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys,
                            int64_t ldk, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
-    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
+    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.W = W; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     dense_nuc_kernel<false><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);
 }
 
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
-                           const uint32_t* r_nv, int r_pad, int n_ref, int Wp,
+                           const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp,
                            int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
-    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.Wp = Wp;
+    a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.W = W; a.Wp = Wp;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     a.nq = nq; a.n_ref = n_ref; a.vmin = vmin; a.mism = mism; a.valid = valid; a.dist = dist;
     dense_nuc_kernel<true><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);

@@ -331,12 +331,12 @@ def main():
     # lanes/clk/SM on the ALU pipe).  Per 32-site word pair the counting needs 3 LOP3 + 2 POPC; every carry-save step
     # trades 1 POPC for 2 LOP3.  With k steps per word pair the pipes take (3 + 2k) / 64 and (2 - k) / 16 clk: the
     # pipe-balanced optimum is k = 5/6, 13.71 word pairs/clk/SM -- that is the roofline (`peak`).  The kernel runs
-    # k = 0.5 + 0.5 * 14/16 (distance.cu: DT_MCSA = 14), i.e. 4.875 LOP3 + 1.0625 POPC: its own binding pipe is the ALU.
+    # k = 0.5 + 0.5 * 13/16 (distance.cu: DT_MCSA = 13), i.e. 4.8125 LOP3 + 1.09375 POPC: its own binding pipe is the ALU.
     def ceiling(word_pairs_per_clk_sm, mhz):
         return 148 * word_pairs_per_clk_sm * 32 * mhz * 1e6
     k_opt = 5.0 / 6.0
     bal_peak = ceiling(64 / (3 + 2 * k_opt), sm_max)
-    k_run = 0.5 + 0.5 * 14 / 16
+    k_run = 0.5 + 0.5 * 13 / 16
     alu_peak = ceiling(64 / (3 + 2 * k_run), sm_max)
     xu_peak = ceiling(16 / (2 - k_run), sm_max)
     plain_peak = ceiling(16 / 2.0, sm_max)
