@@ -47,7 +47,8 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
-    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag;
+    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe;
+    double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
@@ -259,6 +260,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_nv, (size_t)QB * 4)) return -1;
+        if (sel_kind == SEL_NUC && ensure(ctx, ctx->clk_probe, 32)) return -1;
     }
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
@@ -339,7 +341,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 Span sp(ctx, T_DENSE);
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
                                       (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
-                                      ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, ctx->num_sms, s);
+                                      ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, (unsigned long long*)ctx->clk_probe.p,
+                                      ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -647,6 +650,11 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         CK(cudaMemcpy(&pc, ctx->pair_counter.p, 8, cudaMemcpyDeviceToHost));
         ctx->n_pairs += (double)pc;
     }
+    if (sel_kind == SEL_NUC && !matrix && ctx->clk_probe.p) {
+        unsigned long long c[4] = {0, 0, 0, 0};
+        CK(cudaMemcpy(c, ctx->clk_probe.p, 32, cudaMemcpyDeviceToHost));
+        if (c[3] > c[1]) ctx->dense_mhz = 1e3 * (double)(c[2] - c[0]) / (double)(c[3] - c[1]);
+    }
     collect_spans(ctx);
     return 0;
 }
@@ -714,7 +722,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -1079,10 +1087,10 @@ int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const doubl
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
     if (!ctx || !out) return -1;
-    double v[14] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+    double v[15] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
                     ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid,
-                    ctx->n_over, ctx->max_K, ctx->max_V};
-    for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
+                    ctx->n_over, ctx->max_K, ctx->max_V, ctx->dense_mhz};
+    for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
     if (reset) {
         for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
         ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = ctx->n_over = ctx->max_K = ctx->max_V = 0;

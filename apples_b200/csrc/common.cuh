@@ -175,8 +175,8 @@ void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int
                           cudaStream_t s);
 void launch_row_valid(const uint32_t* rm, int rows, int W, uint32_t* nv, int rows_pad, cudaStream_t s);
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
-                           const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys, int64_t ldk, int num_sms,
-                           cudaStream_t s);
+                           const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys, int64_t ldk,
+                           unsigned long long* clk, int num_sms, cudaStream_t s);
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
                            double* dist, int num_sms, cudaStream_t s);

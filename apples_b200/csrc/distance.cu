@@ -139,6 +139,7 @@ struct DenseNucArgs {
     uint32_t* keys;
     int64_t ldk;
     uint32_t k_one, k_two17;  // 1 and 1 << 17 (see the consumer loop)
+    unsigned long long* clk;  // optional: {clock64, globaltimer} of CTA 0 at start and end -> effective SM clock
     // full epilogue (parity export)
     int nq, n_ref, vmin;
     uint32_t* mism;
@@ -159,6 +160,12 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     const int n_tiles = (a.q_pad / DT_TQ) * n_rt;
     const int n_chunks = a.Wp / DT_WC;
 
+    if (tid == 0 && blockIdx.x == 0 && a.clk) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.clk[0] = (unsigned long long)clock64();
+        a.clk[1] = t;
+    }
     if (tid == 0) {
         for (int s = 0; s < DT_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -355,6 +362,12 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
                 }
         }
     }
+    if (tid == 0 && blockIdx.x == 0 && a.clk) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        a.clk[2] = (unsigned long long)clock64();
+        a.clk[3] = t;
+    }
 }
 
 cudaError_t dense_nuc_configure() {
@@ -371,8 +384,9 @@ static int dense_grid(int q_pad, int r_pad, int num_sms) {
 
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys,
-                           int64_t ldk, int num_sms, cudaStream_t s) {
+                           int64_t ldk, unsigned long long* clk, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
+    a.clk = clk;
     a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.W = W; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     dense_nuc_kernel<false><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);

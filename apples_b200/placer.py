@@ -167,11 +167,11 @@ class GpuPlacer:
         self._check(self.lib.apples_results_to_device(self.h, *[t.data_ptr() for t in (edge, error, distal, pendant, status)]))
 
     def timings(self, reset=False):
-        v = np.zeros(14, np.float64)
-        self.lib.apples_get_timings(self.h, _lib.ptr(v), 14, 1 if reset else 0)
+        v = np.zeros(15, np.float64)
+        self.lib.apples_get_timings(self.h, _lib.ptr(v), 15, 1 if reset else 0)
         keys = ['h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms', 'launches',
                 'rep_distance_launches', 'pairs', 'observed', 'valid_nodes', 'overflow_queries', 'max_observed',
-                'max_valid_nodes']
+                'max_valid_nodes', 'rep_distance_sm_mhz']
         return dict(zip(keys, v.tolist()))
 
     # ------------------------------------------------------------------------------------------------ parity exports

@@ -270,14 +270,15 @@ def main():
     tm = pl.timings(reset=True)
     per_rank = None
     if world > 1:
-        # every rank's own step time, dense-kernel time and SM clock, so that a slow rank is visible in the line
-        mine = torch.tensor([ms / args.steps, tm['rep_distance_ms'] / args.steps, float(clocks.get('sm_mhz') or 0.0),
+        # every rank's own step time, dense-kernel time and the SM clock measured inside the dense kernel (clock64 /
+        # globaltimer), so that a slow rank or a clock nvidia-smi does not show is visible in the line
+        mine = torch.tensor([ms / args.steps, tm['rep_distance_ms'] / args.steps, float(tm.get('rep_distance_sm_mhz') or 0.0),
                              1.0 if clocks.get('reasons') else 0.0], dtype=torch.float64, device=device)
         allr = torch.empty(world * 4, dtype=torch.float64, device=device)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.view(world, 4).cpu().tolist()
         per_rank = {'ms_per_step': [round(r[0], 2) for r in allr], 'rep_distance_ms': [round(r[1], 2) for r in allr],
-                    'sm_mhz': [r[2] for r in allr], 'throttled': [bool(r[3]) for r in allr]}
+                    'rep_distance_sm_mhz': [round(r[2], 1) for r in allr], 'throttled': [bool(r[3]) for r in allr]}
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -378,7 +379,7 @@ def main():
                              % (nq * 3 * W * 4 / 1e6, (args.leaves + n_rep) * 3 * W * 4 / 1e6),
                        'parallelism': 'queries sharded over %d GPU(s), reference + tree replicated, final NCCL all-gather' % world},
             'distance_gcell_sites_per_s': (tm['pairs'] / args.steps) * args.sites / (step_ms * 1e-3) / 1e9 * world,
-            'stage_ms_per_step': stages, 'per_rank': per_rank, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
+            'stage_ms_per_step': stages, 'rep_distance_sm_mhz': tm.get('rep_distance_sm_mhz'), 'per_rank': per_rank, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
             'observed_per_query': tm['observed'] / (nq * args.steps), 'valid_nodes_per_query': tm['valid_nodes'] / (nq * args.steps),
             'overflow_queries_per_step': tm['overflow_queries'] / args.steps, 'max_observed': tm['max_observed'],
             'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'setup': info}

@@ -144,7 +144,8 @@ int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const doubl
 /* accumulated device time per stage since the last call with reset != 0, in milliseconds (CUDA events):
  * [0] h2d  [1] transpose  [2] rep distance  [3] selection  [4] placement  [5] d2h  [6] launches (count)
  * [7] rep-distance launches (count) [8] query-representative pairs evaluated [9] observed leaves [10] valid nodes
- * [11] overflow reruns (queries) [12] largest observed set [13] largest restricted subtree */
+ * [11] overflow reruns (queries) [12] largest observed set [13] largest restricted subtree
+ * [14] effective SM clock in MHz during the last representative-distance launch (clock64 / globaltimer, in-kernel) */
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset);
 
 #ifdef __cplusplus
