@@ -383,9 +383,26 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
         for (int j = 0; j < U * VEC; ++j) {
             const int u = u0 + ((j / VEC) * 32 + lane) * VEC + j % VEC;
             const Key<KIND> kj = make_key<KIND>(raw[j], u);
-            cls[j] = (u < a.n_units) ? classify(a, kj) : 0;
+            bool cand;  // a far key smaller than the lane's second-smallest
+            if constexpr (KIND == SEL_NUC) {
+                // lean path (the scan was 70 % of this kernel's instructions): almost every key is certainly far
+                // (above the guard band) and not smaller than l2 -- three multiplies and three compares decide that.
+                // Only keys below the band's upper edge (near, or inside the band) take the exact classification.
+                // Keys past the end of the row were loaded as 0: v = 0 fails the overlap gate (vmin >= 1).
+                const bool ok = (int)kj.v >= a.gate.vmin;
+                const bool pfar = (raw[j] << 16) >= a.gate.P_hi * kj.v;
+                cls[j] = 0;
+                cand = ok && pfar && kj.m * l2.v < l2.m * kj.v && 4u * kj.m < 3u * kj.v;
+                if (ok && !pfar) {
+                    cls[j] = classify(a, kj);
+                    cand = cls[j] == 2 && key_less(kj, l2);
+                }
+            } else {
+                cls[j] = (u < a.n_units) ? classify(a, kj) : 0;
+                cand = cls[j] == 2 && key_less(kj, l2);
+            }
             any_near |= cls[j] == 1;
-            if (cls[j] == 2 && key_less(kj, l2)) {
+            if (cand) {
                 if (key_less(kj, l1)) {
                     l2 = l1;
                     l1 = kj;

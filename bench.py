@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=0, help='queries in the CPU-baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--slot-cap', type=int, default=0, help='observed-list slots per query before a rerun (0 = library default)')
+    ap.add_argument('--sub-batch', type=int, default=0, help='queries per dense/selection launch (0 = library default)')
     return ap.parse_args()
 
 
@@ -229,6 +231,8 @@ def main():
     nq = args.queries_per_gpu
     pl = GpuPlacer(tree, None, tree.name_to_node, device=local_rank)
     pl.set_reference_arrays(**arrays)
+    if args.slot_cap or args.sub_batch:
+        pl.set_limits(max_subbatch=args.sub_batch, slot_cap=args.slot_cap)
     params = _lib.make_params(args.method, args.criterion)
     packed_host = torch.empty(packed_q.shape, dtype=torch.int32).pin_memory()
     packed_host.copy_(packed_q)
