@@ -147,6 +147,12 @@ __device__ __forceinline__ void load_raw_vec(const SelectArgs& a, int row, int u
     }
 }
 
+// inside the guard band the fp64 distance decides.  Not inlined: the scan loop is unrolled eight times and this path
+// is taken by a handful of keys per million
+__device__ __noinline__ bool band_is_near(uint32_t m, uint32_t v, int vmin, double thr) {
+    return jc69_from_counts(m, v, vmin) <= thr;
+}
+
 // classify one unit.  returns 0 = invalid, 1 = near (dist <= threshold), 2 = far
 __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_NUC>& k) {
     // distance.py:735 (no overlap), :741-743 (1 - 4p/3 <= 0  <=>  4 m >= 3 v)
@@ -157,7 +163,7 @@ __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_NUC>&
     if (a.gate.P_hi == 0u) return 2;  // negative threshold: nothing is near
     if (lhs <= a.gate.P_lo * k.v) return 1;
     if (lhs >= a.gate.P_hi * k.v) return 2;
-    return jc69_from_counts(k.m, k.v, a.gate.vmin) <= a.thr ? 1 : 2;
+    return band_is_near(k.m, k.v, a.gate.vmin, a.thr) ? 1 : 2;
 }
 __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_AA>& k) {
     if (!(k.d >= 0.0)) return 0;  // Reference.py:141
@@ -361,64 +367,71 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
     // warp traffic -- because the far set is needed only while obs_num < baseobs, and then only its few smallest
     // members: they are extracted afterwards, one at a time, as the warp-wide minimum of the 32 lane minima; a lane
     // that has used both of its keys gets the next two by a cooperative re-scan of just its class (R / 32 keys).
-    // Lane l owns the units u with (u / VEC) % 32 == l.  VEC = 1: 16-byte loads of four packed count keys per lane
-    // (VEC = 4, U = 4) measured slower on B200 (19.8 vs 17.0 ms per 125k queries): the scan is bound by the
-    // classification instructions, not by bytes in flight. ----
+    // Lane l owns the units u with u % 32 == l.  16-byte loads of four packed count keys per lane measured slower on
+    // B200 (15.9 vs 14.0 ms per 125k queries), as did 16 scalar loads in flight: the scan is bound by its instructions,
+    // not by bytes in flight. ----
     using Raw = typename RawT<KIND>::T;
     constexpr int VEC = 1;
     constexpr int U = 8;  // independent loads in flight per lane
     Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
-    for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * VEC * U) {
-        Raw raw[U * VEC];
-        int cls[U * VEC];
+    for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * U) {
+        Raw raw[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const int u = u0 + (j * 32 + lane) * VEC;
-#pragma unroll
-            for (int c = 0; c < VEC; ++c) raw[j * VEC + c] = 0;
-            if (u < a.n_units) load_raw_vec<KIND, VEC>(a, slot, u, &raw[j * VEC]);
+            const int u = u0 + j * 32 + lane;
+            raw[j] = 0;
+            if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
         }
-        bool any_near = false;
+        // Per key, branch-free: is it an EVENT for this lane -- a far key smaller than the lane's second-smallest
+        // (bit j of `ev`), or a key that needs the exact classification (near, or inside the guard band)?  Almost
+        // every key is neither: certainly far (above the band) and not smaller than l2, decided by three multiplies
+        // and four compares (the scan used to be 70 % of this kernel's instructions).  Keys past the end of the row
+        // were loaded as 0: v = 0 fails the overlap gate (vmin >= 1).
+        unsigned ev = 0u;
 #pragma unroll
-        for (int j = 0; j < U * VEC; ++j) {
-            const int u = u0 + ((j / VEC) * 32 + lane) * VEC + j % VEC;
-            const Key<KIND> kj = make_key<KIND>(raw[j], u);
-            bool cand;  // a far key smaller than the lane's second-smallest
+        for (int j = 0; j < U; ++j) {
             if constexpr (KIND == SEL_NUC) {
-                // lean path (the scan was 70 % of this kernel's instructions): almost every key is certainly far
-                // (above the guard band) and not smaller than l2 -- three multiplies and three compares decide that.
-                // Only keys below the band's upper edge (near, or inside the band) take the exact classification.
-                // Keys past the end of the row were loaded as 0: v = 0 fails the overlap gate (vmin >= 1).
-                const bool ok = (int)kj.v >= a.gate.vmin;
-                const bool pfar = (raw[j] << 16) >= a.gate.P_hi * kj.v;
-                cls[j] = 0;
-                cand = ok && pfar && kj.m * l2.v < l2.m * kj.v && 4u * kj.m < 3u * kj.v;
-                if (ok && !pfar) {
-                    cls[j] = classify(a, kj);
-                    cand = cls[j] == 2 && key_less(kj, l2);
-                }
+                const uint32_t r = raw[j], m = r & 0xffffu, v = r >> 16;
+                const bool ok = (int)v >= a.gate.vmin;
+                const bool pfar = (r << 16) >= a.gate.P_hi * v;
+                const bool less = m * l2.v < l2.m * v;  // by ratio; units arrive in ascending order, ties are not less
+                if (ok && (!pfar || less)) ev |= 1u << j;
             } else {
-                cls[j] = (u < a.n_units) ? classify(a, kj) : 0;
-                cand = cls[j] == 2 && key_less(kj, l2);
+                const int u = u0 + j * 32 + lane;
+                if (u < a.n_units && !(raw[j] > l2.d)) ev |= 1u << j;  // NaN and near keys included
             }
-            any_near |= cls[j] == 1;
-            if (cand) {
-                if (key_less(kj, l1)) {
-                    l2 = l1;
-                    l1 = kj;
-                } else {
-                    l2 = kj;
+        }
+        unsigned nearb = 0u;  // bit j: raw[j] is a near unit
+        if (__any_sync(FULLMASK, ev != 0u)) {
+            // events, one per round (a lane rarely has two among its eight keys)
+            while (ev) {
+                const int j = __ffs(ev) - 1;
+                ev &= ev - 1;
+                Raw rj = raw[0];
+#pragma unroll
+                for (int t = 1; t < U; ++t)
+                    if (j == t) rj = raw[t];
+                const Key<KIND> kj = make_key<KIND>(rj, u0 + j * 32 + lane);
+                const int c = classify(a, kj);
+                if (c == 1) nearb |= 1u << j;
+                if (c == 2 && key_less(kj, l2)) {
+                    if (key_less(kj, l1)) {
+                        l2 = l1;
+                        l1 = kj;
+                    } else {
+                        l2 = kj;
+                    }
                 }
             }
         }
-        if (__any_sync(FULLMASK, any_near)) {
+        if (__any_sync(FULLMASK, nearb != 0u)) {
             // queued (lane t holds the t-th pending key) and expanded from ONE loop so that the member-distance code
             // is instantiated once
-            unsigned nearm[U * VEC];
+            unsigned nearm[U];
             bool any = false;
 #pragma unroll
-            for (int j = 0; j < U * VEC; ++j) {
-                nearm[j] = __ballot_sync(FULLMASK, cls[j] == 1);
+            for (int j = 0; j < U; ++j) {
+                nearm[j] = __ballot_sync(FULLMASK, (nearb >> j) & 1u);
                 any |= nearm[j] != 0u;
             }
             while (any) {
@@ -427,12 +440,11 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
                 qkey.idx = -1;
                 any = false;
 #pragma unroll
-                for (int j = 0; j < U * VEC; ++j) {
+                for (int j = 0; j < U; ++j) {
                     while (nearm[j] && qn < 32) {
                         const int src = __ffs(nearm[j]) - 1;
                         nearm[j] &= nearm[j] - 1;
-                        const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src),
-                                                            u0 + ((j / VEC) * 32 + src) * VEC + j % VEC);
+                        const Key<KIND> uk = make_key<KIND>(__shfl_sync(FULLMASK, raw[j], src), u0 + j * 32 + src);
                         if (lane == qn) qkey = uk;
                         ++qn;
                     }
