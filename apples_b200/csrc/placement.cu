@@ -25,7 +25,13 @@
 #include "common.cuh"
 
 #define FULLMASK 0xffffffffu
-constexpr int PL_HIST = 1024;  // attach-level buckets per warp in shared memory
+#ifndef PL_HIST_V
+#define PL_HIST_V 512
+#endif
+#ifndef PL_MINBLOCKS
+#define PL_MINBLOCKS 1
+#endif
+constexpr int PL_HIST = PL_HIST_V;  // attach-level buckets per warp in shared memory
 
 __device__ __forceinline__ void leaf_moments(int method, double D, double* m) {
     m[1] = 0.0; m[2] = 0.0; m[4] = 0.0;
@@ -119,7 +125,7 @@ __device__ __forceinline__ void warp_argmin(double& val, int& idx) {
 }
 
 template <int METHOD>
-__global__ void __launch_bounds__(128) place_kernel(const PlaceArgs a) {
+__global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArgs a) {
     constexpr bool BME = METHOD == APPLES_BME;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

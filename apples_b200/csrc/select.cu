@@ -294,7 +294,10 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
         if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-            constexpr int NR = 4;
+#ifndef SEL_NR
+#define SEL_NR 2
+#endif
+            constexpr int NR = SEL_NR;
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
                 int rows[NR];
                 uint32_t c[NR];
@@ -339,8 +342,13 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
     }
 }
 
+// nucleotide mode: 8 blocks of 4 warps per SM (64 registers, some spills) measured faster than 4 (128 registers): 12.1
+// vs 12.9 ms per 125k queries -- the kernel is latency-bound and wants warps, not registers
+#ifndef SEL_MINBLOCKS
+#define SEL_MINBLOCKS 8
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(128, KIND == SEL_NUC ? SEL_MINBLOCKS : 4) select_kernel(const SelectArgs a) {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
