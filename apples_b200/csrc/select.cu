@@ -285,7 +285,7 @@ __device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<
     observe<SEL_NUC>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
 }
 
-template <int KIND>
+template <int KIND, int NR = 2>
 __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& st, int slot, int q, int self,
                                             const Key<KIND>& ukey, int lane, const double* aa_tab) {
     if constexpr (KIND == SEL_MATRIX) {
@@ -294,10 +294,6 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
         if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-#ifndef SEL_NR
-#define SEL_NR 2
-#endif
-            constexpr int NR = SEL_NR;
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
                 int rows[NR];
                 uint32_t c[NR];
@@ -347,8 +343,14 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
 #ifndef SEL_MINBLOCKS
 #define SEL_MINBLOCKS 8
 #endif
-template <int KIND>
-__global__ void __launch_bounds__(128, KIND == SEL_NUC ? SEL_MINBLOCKS : 4) select_kernel(const SelectArgs a) {
+#ifndef SEL_NR
+#define SEL_NR 2
+#endif
+// HEAVY: the rerun launches of the few queries with hundreds to thousands of observed leaves -- one partial wave of
+// warps whose time is the member loop of the largest query: eight reference rows in flight and the full register file
+template <int KIND, bool HEAVY>
+__global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOCKS : 4) select_kernel(const SelectArgs a) {
+    constexpr int NR = HEAVY ? 8 : SEL_NR;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
     __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(128, KIND == SEL_NUC ? SEL_MINBLOCKS : 4) sele
                 }
                 for (int t = 0; t < qn && st.kcount <= a.cap; ++t) {
                     const Key<KIND> uk = key_shfl(qkey, t);
-                    expand_unit<KIND>(a, st, oslot, slot, self, uk, lane, aa_tab);
+                    expand_unit<KIND, NR>(a, st, oslot, slot, self, uk, lane, aa_tab);
                 }
             }
         }
@@ -476,7 +478,7 @@ __global__ void __launch_bounds__(128, KIND == SEL_NUC ? SEL_MINBLOCKS : 4) sele
             if (key_less(og, g)) g = og;
         }
         if (key_is_none(g)) break;  // no far unit left
-        expand_unit<KIND>(a, st, oslot, slot, self, g, lane, aa_tab);
+        expand_unit<KIND, NR>(a, st, oslot, slot, self, g, lane, aa_tab);
         const bool mine = l1.idx == g.idx;
         if (mine) {
             l1 = l2;
@@ -593,10 +595,12 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
     const int warps = 4;
     dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
     if (a.n <= 0) return;
-    if (kind == SEL_NUC)
-        select_kernel<SEL_NUC><<<grid, block, 0, s>>>(a);
+    if (kind == SEL_NUC && a.out_map)  // overflow rerun
+        select_kernel<SEL_NUC, true><<<grid, block, 0, s>>>(a);
+    else if (kind == SEL_NUC)
+        select_kernel<SEL_NUC, false><<<grid, block, 0, s>>>(a);
     else if (kind == SEL_AA)
-        select_kernel<SEL_AA><<<grid, block, 0, s>>>(a);
+        select_kernel<SEL_AA, false><<<grid, block, 0, s>>>(a);
     else
-        select_kernel<SEL_MATRIX><<<grid, block, 0, s>>>(a);
+        select_kernel<SEL_MATRIX, false><<<grid, block, 0, s>>>(a);
 }
