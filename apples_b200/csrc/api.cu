@@ -47,7 +47,7 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
-    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe;
+    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
@@ -326,11 +326,26 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.status = (int*)ctx->statusd.p;
     sa.zero_edge = (int*)ctx->zero_edge.p;
     sa.tree = tree_dev(ctx);
+    // key-row stash for the overflow reruns (alignment-mode nucleotides): up to 256 MiB of key rows
+    int stash_cap = 0;
+    if (sel_kind == SEL_NUC && !matrix) {
+        stash_cap = (int)std::min<int64_t>(n, std::max<int64_t>(1, ((int64_t)256 << 20) / (ldk * 4)));
+        if (ensure(ctx, ctx->stash_keys, (size_t)stash_cap * ldk * 4) || ensure(ctx, ctx->stash_ids, (size_t)stash_cap * 4) ||
+            ensure(ctx, ctx->stash_count, 4))
+            return -1;
+        CK(cudaMemsetAsync(ctx->stash_count.p, 0, 4, s));
+        sa.stash_keys = (uint32_t*)ctx->stash_keys.p;
+        sa.stash_ids = (int*)ctx->stash_ids.p;
+        sa.stash_count = (int*)ctx->stash_count.p;
+        sa.stash_cap = stash_cap;
+    }
 
     // distances + selection of the `nb` queries whose packed rows / matrix rows are at d_q / ctx->keys
-    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a) -> int {
+    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a, bool keys_ready = false) -> int {
         const int nb_pad = round_up(nb, DT_TQ);
-        if (sel_kind == SEL_NUC) {
+        if (keys_ready) {
+            // the key rows are already in a.keys_nuc (stash of the first pass)
+        } else if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
                 launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, DT_TQ, s);
@@ -528,6 +543,16 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             is_over[i] = 1;
         }
     ctx->n_over += (double)over.size();
+    // first-level reruns read their key rows from the stash when every overflowing query got a stash row
+    bool use_stash = false;
+    if (stash_cap > 0 && !over.empty()) {
+        int cnt = 0;
+        CK(cudaMemcpy(&cnt, ctx->stash_count.p, 4, cudaMemcpyDeviceToHost));
+        if (cnt == (int)over.size() && cnt <= stash_cap) {
+            CK(cudaMemcpy(over.data(), ctx->stash_ids.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost));  // stash order
+            use_stash = true;
+        }
+    }
     int cap2 = cap;
     const int cap_max = next_pow2(std::max(4, n_leaf_bound));
     while (!over.empty()) {
@@ -570,7 +595,9 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             sb.obs_dist = (double*)ctx->obs_dist2.p;
             sb.obs_len = (int*)ctx->obs_len2.p;
             sb.pair_counter = nullptr;
-            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb)) return -1;
+            sb.stash_keys = nullptr;
+            if (use_stash) sb.keys_nuc = (const uint32_t*)ctx->stash_keys.p + (size_t)o0 * ldk;
+            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_stash)) return -1;
             if (fetch_counts()) return -1;
             CK(cudaStreamSynchronize(s));
             if (io.obs_count) {
@@ -598,6 +625,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
         if (cap2 >= cap_max && !still.empty()) return fail(ctx, "internal error: observed set larger than the number of leaves");
         over.swap(still);
+        use_stash = false;  // deeper levels recompute: their rows are no longer contiguous in the stash
     }
 
     // ---------------- parity export of the observed sets ----------------
@@ -722,7 +750,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,

@@ -116,6 +116,13 @@ struct SelectArgs {
     int* status;           // [nq] ST_*
     int* zero_edge;        // [nq]
     unsigned long long* pair_counter;  // number of member distances evaluated (statistics)
+    // key-row stash (nucleotide alignment mode, first pass only): a query that overflows its slot copies its key row
+    // aside so that its rerun needs no second distance pass.  stash_count is bumped for every overflowing query; only
+    // the first stash_cap of them are stored (the host falls back to recomputing when there are more)
+    uint32_t* stash_keys;  // [stash_cap][ldk] or NULL
+    int* stash_ids;        // [stash_cap] query index inside the batch
+    int* stash_count;
+    int stash_cap;
     TreeDev tree;
 };
 

@@ -537,6 +537,19 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
     int V = 0;
     if (st.kcount > a.cap) {
         status = ST_OVERFLOW;  // the scan was cut short: rerun with a larger slot (the host escalates the capacity)
+        if constexpr (KIND == SEL_NUC) {
+            if (a.stash_keys != nullptr) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(a.stash_count, 1);
+                pos = __shfl_sync(FULLMASK, pos, 0);
+                if (pos < a.stash_cap) {
+                    const uint4* src = reinterpret_cast<const uint4*>(a.keys_nuc + (size_t)slot * a.ldk);
+                    uint4* dst = reinterpret_cast<uint4*>(a.stash_keys + (size_t)pos * a.ldk);
+                    for (int64_t x = lane; x < a.ldk / 4; x += 32) dst[x] = src[x];
+                    if (lane == 0) a.stash_ids[pos] = gid;
+                }
+            }
+        }
     } else if (st.has_zero) {
         status = ST_ZERO;
     } else if (st.kcount <= 2) {
