@@ -58,6 +58,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t_begin = 0.0
 
     def start(self):
         try:
@@ -71,7 +72,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            self.rows.append((time.time(), [x.strip() for x in line.split(',')]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -84,7 +88,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t_end = time.time()
+        inside = [r for t, r in self.rows if self.t_begin <= t <= t_end + 0.3]
+        for r in (inside if inside else [r for _, r in self.rows[-3:]]):
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -257,12 +263,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the clock sampler (one nvidia-smi process per rank) is started BEFORE the warm-up: its NVML start-up attaches to
+    # every GPU of the node and, started at the edge of the timed region by eight ranks at once, slowed the dense
+    # kernel of all of them by ~10 % for the first second.  Only samples taken inside the timed region are kept.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     pl.timings(reset=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
