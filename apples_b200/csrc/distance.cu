@@ -10,11 +10,11 @@
 //   E1 = popc(x),  D = popc(z):   mismatch = D - E1,   valid = (nq + nr - E1) / 2
 // (nq, nr = valid sites of the two rows, counted once per row): 3 LOP3 per 32 sites instead of 4.
 // The dense kernel computes all pairs of a query block against all representatives with a GEMM-like tiling:
-// operands are stored word-major ([plane][word][row]) so that one (plane, word) slice of a 64-row tile is 256
-// contiguous bytes; a producer warp streams those slices into a 4-stage shared-memory ring with 1-D TMA bulk copies
-// (cp.async.bulk + mbarrier complete_tx), 16 consumer warps hold a 4x4 register tile of pairs per thread (CTA tile 128
-// queries x 64 representatives, one persistent CTA per SM) and do the LOP3/POPC work.  The binding resources are the
-// integer pipes (XU POPC, ALU LOP3), not HBM ("rooflines").
+// operands are stored tile-major ([row tile][32-word chunk][plane][word][row in tile]) so that one pipeline stage of a
+// tile is one contiguous block; thread 0 keeps a 2-stage shared-memory ring full with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx, two copies per stage), 16 warps hold a 4x4 register tile of pairs per thread
+// (CTA tile 128 queries x 64 representatives, one persistent CTA per SM, 128 registers per thread) and do the
+// LOP3/POPC work.  The binding resources are the integer pipes (ALU LOP3, XU POPC), not HBM ("rooflines").
 #include "common.cuh"
 #include <type_traits>
 
