@@ -5,8 +5,11 @@
 // `dist <= threshold or obs_num < baseobs`.  Because pops are ascending and obs_num only grows, that is
 //   taken = { clusters with dist <= threshold }  U  { the next clusters in (dist, index) order while obs_num < baseobs }
 // (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters as it meets them and keeps,
-// per lane, only the smallest far key of its residue class; afterwards the far clusters are extracted in ascending
-// order (warp-wide minimum of the lane minima, then a re-scan of one residue class) until obs_num reaches baseobs.
+// per lane, the two smallest far keys of its residue class; afterwards the far clusters are extracted in ascending
+// order (warp-wide minimum of the lane minima; a lane that has used both keys re-scans its residue class for the next
+// two) until obs_num reaches baseobs.  The scan is branch-free per key (three multiplies, four compares); the exact
+// classification runs only for the few keys that can matter.  A query whose observed set outgrows its slot stashes its
+// key row and is rerun with a larger slot by the HEAVY instantiation of the kernel.
 // Nucleotide keys are the exact integer pairs (mismatch, valid) from the dense kernel: ordering by the rational
 // mismatch/valid is ordering by jc69 distance (equal rationals give the identical double), so no fp64 is needed
 // for the ~R representatives per query; the corrected fp64 distance is evaluated only for the selected members.
