@@ -7,6 +7,7 @@ in the same order, with the same warnings / stderr messages.  All per-query work
 selection, restricted subtree, least-squares moments, per-edge solve, criterion selection) runs in CUDA behind
 the C ABI of include/apples_b200.h.  There is no CPU path here.
 """
+import gc
 import logging
 import sys
 
@@ -212,9 +213,22 @@ class GpuPlacer:
 
 def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True):
     """Device result arrays -> the per-query dicts PoolQueryWorker.runquery returns, with its messages."""
+    # the common record (placed, no flag, name not in the backbone) is built in one comprehension; the per-record
+    # control flow below only runs for the others (6.5 -> 1.4 s per million queries)
+    st_arr = np.asarray(out[4])
+    special = np.flatnonzero((st_arr != _lib.PLACED) | np.asarray(in_backbone, dtype=bool)).tolist()
     edge, error, distal, pendant, status = [o.tolist() for o in out]
-    results = []
-    for i, name in enumerate(names):
+    # five container objects per record: the cyclic GC would walk the growing list again and again (5x slower)
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        results = [{'placements': [{'p': [[e, r, 1, d, q]], 'n': [nm]}]}
+                   for e, r, d, q, nm in zip(edge, error, distal, pendant, names)]
+    finally:
+        if gc_was_on:
+            gc.enable()
+    for i in special:
+        name = names[i]
         if in_backbone[i]:  # PoolQueryWorker.py:63-70
             if log:
                 logging.warning('The query named %s exists in the backbone. Changing its name to %s-query.' % (name, name))
@@ -240,7 +254,7 @@ def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True)
                     logging.warning('Best placement for query sequence %s has zero pendant edge length and placed at '
                                     'an internal node with a non-zero least squares error. This is a potential '
                                     'misplacement.%s' % (name, ignored))
-        results.append({'placements': [{'p': [p], 'n': [name]}]})
+        results[i] = {'placements': [{'p': [p], 'n': [name]}]}
     return results
 
 

@@ -152,3 +152,86 @@ def test_option_validation():
     o, _ = options_config_run(['-t', 't.nwk', '-q', 'q.fa', '-s', 'r.fa'])
     assert (o.method_name, o.criterion_name, o.base_observation_threshold, o.filt_threshold,
             o.minimum_alignment_overlap) == ('FM', 'MLSE', 25, 0.2, 0.001)
+
+
+def test_jplace_dumps_is_json_dumps_byte_for_byte():
+    """jplace.dumps writes the placement records from a template; the text must equal
+    json.dumps(result, sort_keys=True, indent=4) (run_apples.py:114) including special floats, escapes, the empty
+    placement list of a single unplaceable query, and it must fall back for anything unexpected."""
+    import json
+    import random
+    from apples_b200 import jplace
+    rnd = random.Random(7)
+
+    def num():
+        r = rnd.random()
+        if r < 0.1:
+            return 0
+        if r < 0.2:
+            return 1
+        if r < 0.25:
+            return float('nan')
+        if r < 0.3:
+            return float('inf')
+        if r < 0.35:
+            return -float('inf')
+        if r < 0.4:
+            return -0.0
+        if r < 0.5:
+            return rnd.random() * 1e-300
+        if r < 0.6:
+            return rnd.random() * 1e22
+        return rnd.random()
+
+    def results(n):
+        out = []
+        for i in range(n):
+            name = rnd.choice(['Q%d' % i, 'a"b\\c', 'ü-name', 'tab\tname', 'x' * 50])
+            out.append({'placements': [{'p': [[rnd.choice([-1, rnd.randint(0, 10 ** 6)]), num(), 1, num(), num()]],
+                                        'n': [name]}]})
+        return out
+
+    for n in (1, 2, 3, 50, 500):
+        for _ in range(4):
+            a = jplace.assemble(results(n), '((a:1,b:2):0.1,c);', argv=['run_apples.py', '-q', 'x y'])
+            assert jplace.dumps(a) == json.dumps(a, sort_keys=True, indent=4)
+    a = jplace.assemble([{'placements': [{'p': [[-1, 0, 1, 0, 0]], 'n': ['q']}]}], '(a,b);', argv=['x'])
+    assert a['placements'] == [] and jplace.dumps(a) == json.dumps(a, sort_keys=True, indent=4)
+    odd = {'placements': [{'p': [[1, 2, 3]], 'n': ['q']}], 'tree': 'x'}
+    assert jplace.dumps(odd) == json.dumps(odd, sort_keys=True, indent=4)
+    nested = {'placements': [{'p': [[1, 2.0, 1, 3.0, 4.0]], 'n': ['q'], 'extra': 1}], 'tree': 'x'}
+    assert jplace.dumps(nested) == json.dumps(nested, sort_keys=True, indent=4)
+
+
+def test_results_to_jplace_fast_path_equals_per_record_logic():
+    """results_to_jplace builds the common records in one pass and runs the runquery control flow
+    (PoolQueryWorker.py:63-130) only for the special ones; compare with the plain per-record restatement."""
+    from apples_b200 import _lib
+    from apples_b200.placer import results_to_jplace
+    rng = np.random.default_rng(5)
+    n = 400
+    edge = rng.integers(0, 1000, n).astype(np.int32)
+    error, distal, pendant = rng.random(n), rng.random(n), rng.random(n)
+    status = rng.choice([_lib.PLACED, _lib.PLACED, _lib.PLACED, _lib.ZERO_DIST_LEAF, _lib.TOO_FEW_DISTANCES,
+                         _lib.PLACED_MISPLACEMENT_FLAG, _lib.PLACED | _lib.FLAG_PENDANT_INT0,
+                         _lib.PLACED_MISPLACEMENT_FLAG | _lib.FLAG_PENDANT_INT0], n).astype(np.int32)
+    in_bb = (rng.random(n) < 0.1).tolist()
+    names = ['q%d' % i for i in range(n)]
+    for excl in (False, True):
+        got = results_to_jplace(names, in_bb, (edge, error, distal, pendant, status), exclude_intplace=excl, log=False)
+        assert len(got) == n
+        for i in range(n):
+            name = names[i] + ('-query' if in_bb[i] else '')
+            code = int(status[i]) & _lib.STATUS_CODE_MASK
+            if code == _lib.ZERO_DIST_LEAF:
+                p = [int(edge[i]), 0, 1, 0, 0]
+            elif code == _lib.TOO_FEW_DISTANCES:
+                p = [-1, 0, 1, 0, 0]
+            else:
+                pend = 0 if int(status[i]) & _lib.FLAG_PENDANT_INT0 else float(pendant[i])
+                p = [int(edge[i]), float(error[i]), 1, float(distal[i]), pend]
+                if code == _lib.PLACED_MISPLACEMENT_FLAG and excl:
+                    p[0] = -1
+            exp = {'placements': [{'p': [p], 'n': [name]}]}
+            assert got[i] == exp, i
+            assert [type(x) for x in got[i]['placements'][0]['p'][0]] == [type(x) for x in p], i
