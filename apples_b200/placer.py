@@ -292,7 +292,7 @@ def place_batch(reference, options, name_to_node_map, queries, tree=None, placer
             rows = np.full((len(queries), len(tags)), -1.0, dtype=np.float64)
             col = {t: j for j, t in enumerate(tags)}
             for i, q in enumerate(queries):
-                if len(q[2]) == len(tags):
+                if len(q[2]) == len(tags) and list(q[2]) == tags:  # same header order (run_apples.py:43-54)
                     rows[i] = np.fromiter(q[2].values(), dtype=np.float64, count=len(tags))
                 else:
                     for t, v in q[2].items():
