@@ -47,7 +47,7 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
-    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
+    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count, tile_counter;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
@@ -261,6 +261,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_nv, (size_t)QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->clk_probe, 32)) return -1;
+        if (sel_kind == SEL_NUC && ensure(ctx, ctx->tile_counter, 4)) return -1;
     }
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
@@ -354,10 +355,11 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             }
             {
                 Span sp(ctx, T_DENSE);
+                if (DT_DYNAMIC_TILES) CK(cudaMemsetAsync(ctx->tile_counter.p, 0, 4, s));
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
                                       (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
                                       ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, (unsigned long long*)ctx->clk_probe.p,
-                                      ctx->num_sms, s);
+                                      (int*)ctx->tile_counter.p, ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -750,7 +752,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->tile_counter, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -1061,10 +1063,12 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
         if (ensure(ctx, qnv, (size_t)q_pad * 4)) { cleanup(); return -1; }
         launch_transpose_nuc((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qwm.p, ctx->Wp, q_pad, DT_TQ, s);
         launch_row_valid((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qnv.p, q_pad, s);
+        if (ensure(ctx, ctx->tile_counter, 4)) { cleanup(); return -1; }
+        cudaMemsetAsync(ctx->tile_counter.p, 0, 4, s);
         launch_dense_nuc_full((const uint32_t*)qwm.p, (const uint32_t*)qnv.p, q_pad, (int)nq,
                               (const uint32_t*)ctx->refs_wm.p, (const uint32_t*)ctx->refs_nv.p, ctx->ref_pad,
                               ctx->n_ref, ctx->W, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
-                              (double*)dd.p, ctx->num_sms, s);
+                              (double*)dd.p, (int*)ctx->tile_counter.p, ctx->num_sms, s);
     } else {
         launch_dense_aa((const uint8_t*)dq.p, (int)nq, (const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, ctx->L,
                         overlap_frac, (double*)dd.p, ctx->n_ref, (uint32_t*)dv.p, s);
