@@ -17,13 +17,14 @@ CRITERIA = {'MLSE': MLSE, 'ME': ME, 'HYBRID': HYBRID}
 STATUS_CODE_MASK = 0xff
 PLACED, ZERO_DIST_LEAF, TOO_FEW_DISTANCES, PLACED_MISPLACEMENT_FLAG = 0, 1, 2, 3
 FLAG_PENDANT_INT0 = 0x100
+FLAG_DEGENERATE = 0x200
 
 # every symbol the header declares (tests/test_cabi.py checks the library exports exactly these)
 SYMBOLS = [
-    'apples_words_per_row', 'apples_aa_row_bytes', 'apples_ctx_create', 'apples_ctx_destroy', 'apples_last_error',
+    'apples_words_per_row', 'apples_aa_row_bytes', 'apples_device_count', 'apples_ctx_create', 'apples_ctx_destroy', 'apples_last_error',
     'apples_ctx_stream', 'apples_ctx_set_limits', 'apples_set_tree', 'apples_set_reference', 'apples_set_matrix_columns', 'apples_place_batch',
     'apples_place_batch_matrix', 'apples_set_reference_bytes', 'apples_place_batch_bytes', 'apples_queries_upload', 'apples_place_resident', 'apples_results_download', 'apples_results_to_device',
-    'apples_distance_counts', 'apples_observed_sets', 'apples_edge_solutions', 'apples_get_timings',
+    'apples_distance_counts', 'apples_observed_sets', 'apples_edge_solutions', 'apples_get_timings', 'apples_last_counts',
 ]
 
 
@@ -50,6 +51,7 @@ def load():
     lib.apples_words_per_row.restype = i32
     lib.apples_aa_row_bytes.argtypes = [i32]
     lib.apples_aa_row_bytes.restype = i32
+    lib.apples_device_count.argtypes = [C.POINTER(i32)]
     lib.apples_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.apples_ctx_destroy.argtypes = [vp]
     lib.apples_ctx_destroy.restype = None
@@ -73,8 +75,16 @@ def load():
     lib.apples_observed_sets.argtypes = [vp, i64, vp, vp, vp, C.POINTER(Params), i32, vp, vp, vp]
     lib.apples_edge_solutions.argtypes = [vp, vp, vp, i32, C.POINTER(Params), vp, vp, vp, vp]
     lib.apples_get_timings.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.apples_last_counts.argtypes = [vp, i64, vp, vp, vp]
     _lib = lib
     return lib
+
+
+def device_count():
+    """CUDA devices visible to the process (0 when there is no usable driver / device)."""
+    n = C.c_int32(0)
+    load().apples_device_count(C.byref(n))
+    return int(n.value)
 
 
 def ptr(a):

@@ -47,7 +47,7 @@ struct apples_ctx {
     DevBuf col_node;
     // per-batch work buffers
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
-    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count, tile_counter;
+    DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
     DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
@@ -66,6 +66,9 @@ struct apples_ctx {
     int64_t max_subbatch = 65536;
     int64_t max_batch = 1 << 20;  // queries per macro-batch (batch-wide observed-list buffers)
     std::vector<int> hK, hV, hS;
+    std::vector<char> h_over;      // last macro-batch: query went through the overflow rerun
+    std::vector<int> h_first;      // host copy of first[]: node u is a leaf iff first[u] == u
+    std::vector<int> h_ref_node, h_col_node;  // re-validated when the tree changes
     std::vector<long long> h_rec_off, h_stack_off;
     std::vector<char> h_gather;
     int slot_cap = 256;
@@ -184,6 +187,18 @@ NucGate make_gate(int L, double thr, double overlap) {
     return g;
 }
 
+// every mapped node id must be -1 (not in the tree) or a LEAF of the current tree (ids index tree arrays in the kernels)
+int check_leaf_ids(apples_ctx* ctx, const char* what, const int32_t* ids, int n) {
+    if (ctx->M <= 0) return 0;  // no tree yet: validated again by apples_set_tree
+    for (int i = 0; i < n; ++i) {
+        const int v = ids[i];
+        if (v == -1) continue;
+        if (v < 0 || v >= ctx->M) return fail(ctx, "%s[%d] = %d is outside [-1, %d)", what, i, v, ctx->M);
+        if (ctx->h_first[v] != v) return fail(ctx, "%s[%d] = %d is not a leaf of the tree", what, i, v);
+    }
+    return 0;
+}
+
 TreeDev tree_dev(apples_ctx* ctx) {
     TreeDev t;
     t.M = ctx->M;
@@ -245,7 +260,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     qb = qb / DT_TQ * DT_TQ;
     qb = std::min<int64_t>(qb, round_up(n, DT_TQ));
     const int QB = (int)qb;
-    const int cap = io.obs_cap > 0 ? next_pow2(io.obs_cap) : std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
+    const int cap = std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
     if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
@@ -261,7 +276,6 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_nv, (size_t)QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->clk_probe, 32)) return -1;
-        if (sel_kind == SEL_NUC && ensure(ctx, ctx->tile_counter, 4)) return -1;
     }
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
@@ -291,6 +305,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     }
     const int* d_self = nullptr;
     if (io.h_self) {
+        for (int i = 0; i < n; ++i) {
+            const int v = io.h_self[base0 + i];
+            if (v < -1 || v >= ctx->M) return fail(ctx, "self_node[%lld] = %d is outside [-1, %d)", (long long)(base0 + i), v, ctx->M);
+        }
         CK(cudaMemcpyAsync(ctx->self_node.p, io.h_self + base0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         d_self = (const int*)ctx->self_node.p;
     } else if (io.d_self) {
@@ -355,11 +373,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             }
             {
                 Span sp(ctx, T_DENSE);
-                if (DT_DYNAMIC_TILES) CK(cudaMemsetAsync(ctx->tile_counter.p, 0, 4, s));
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
                                       (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
                                       ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, (unsigned long long*)ctx->clk_probe.p,
-                                      (int*)ctx->tile_counter.p, ctx->num_sms, s);
+                                      ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -537,7 +554,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     // ---------------- overflow reruns: observed set larger than the slot capacity (rare) ----------------
     // the selection kernel stops a query as soon as it exceeds its slot; it is rerun with a 16x larger slot (256 ->
     // 4096 -> 65536 -> all leaves) until it fits
-    std::vector<char> is_over(n, 0);
+    std::vector<char>& is_over = ctx->h_over;
+    is_over.assign(n, 0);
     std::vector<int> over;
     for (int i = 0; i < n; ++i)
         if (hS[i] == ST_OVERFLOW) {
@@ -710,8 +728,21 @@ int run_batch(apples_ctx* ctx, int64_t nq, const BatchIO& io, const apples_param
 // =================================================================================================================
 extern "C" {
 
+void apples_ctx_destroy(apples_ctx* ctx);
+
 int32_t apples_words_per_row(int32_t L) { return ((L + 31) / 32 + 3) / 4 * 4; }
 int32_t apples_aa_row_bytes(int32_t L) { return (L + 15) / 16 * 16; }
+
+int apples_device_count(int32_t* count) {
+    if (!count) return -1;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        *count = 0;
+        return -2;
+    }
+    *count = n;
+    return 0;
+}
 
 int apples_ctx_create(int device, apples_ctx** out) {
     if (!out) return -1;
@@ -723,23 +754,17 @@ int apples_ctx_create(int device, apples_ctx** out) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        delete ctx;
-        return -4;
-    }
-    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
-        return -4;
-    }
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
-    }
-    if (dense_nuc_configure() != cudaSuccess) {
-        cudaStreamDestroy(ctx->stream);
-        delete ctx;
-        return -5;
+    int rc = 0;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) rc = -4;
+    if (!rc && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) rc = -4;
+    for (int i = 0; i < 2 && !rc; ++i)
+        if (cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = -4;
+    if (!rc && dense_nuc_configure() != cudaSuccess) rc = -5;
+    if (rc) {
+        apples_ctx_destroy(ctx);  // releases whatever was created
+        return rc;
     }
     *out = ctx;
     return 0;
@@ -748,11 +773,11 @@ int apples_ctx_create(int device, apples_ctx** out) {
 void apples_ctx_destroy(apples_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->tile_counter, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -768,7 +793,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -790,6 +815,11 @@ int apples_set_tree(apples_ctx* ctx, int32_t M, const int32_t* parent, const dou
     for (int u = 0; u < M - 1; ++u)
         if (parent[u] <= u || parent[u] >= M) return fail(ctx, "apples_set_tree: node ids must be post-order ranks");
     if (parent[M - 1] != -1) return fail(ctx, "apples_set_tree: last node must be the root");
+    for (int u = 0; u < M; ++u) {
+        if (first[u] < 0 || first[u] > u) return fail(ctx, "apples_set_tree: first[%d] = %d is not the smallest id of the subtree", u, first[u]);
+        if (level[u] < 0 || (u < M - 1 && level[u] != level[parent[u]] + 1))
+            return fail(ctx, "apples_set_tree: level[%d] = %d is not the depth of the node", u, level[u]);
+    }
     CK(cudaSetDevice(ctx->device));
     if (ensure(ctx, ctx->t_parent, (size_t)M * 4) || ensure(ctx, ctx->t_elen, (size_t)M * 8) ||
         ensure(ctx, ctx->t_level, (size_t)M * 4) || ensure(ctx, ctx->t_first, (size_t)M * 4))
@@ -799,6 +829,10 @@ int apples_set_tree(apples_ctx* ctx, int32_t M, const int32_t* parent, const dou
     CK(cudaMemcpy(ctx->t_level.p, level, (size_t)M * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->t_first.p, first, (size_t)M * 4, cudaMemcpyHostToDevice));
     ctx->M = M;
+    ctx->h_first.assign(first, first + M);
+    if (check_leaf_ids(ctx, "ref_node", ctx->h_ref_node.data(), (int)ctx->h_ref_node.size()) ||
+        check_leaf_ids(ctx, "col_node", ctx->h_col_node.data(), (int)ctx->h_col_node.size()))
+        return -1;
     return 0;
 }
 
@@ -815,6 +849,8 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
     const int n_mem = group_offsets[n_rep];
     for (int i = 0; i < n_mem; ++i)
         if (group_members[i] < 0 || group_members[i] >= n_ref) return fail(ctx, "apples_set_reference: member out of range");
+    if (check_leaf_ids(ctx, "ref_node", ref_node, n_ref)) return -1;
+    ctx->h_ref_node.assign(ref_node, ref_node + n_ref);
     CK(cudaSetDevice(ctx->device));
     ctx->kind = kind;
     ctx->L = L;
@@ -853,6 +889,8 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
 int apples_set_matrix_columns(apples_ctx* ctx, int32_t n_cols, const int32_t* col_node) {
     if (!ctx) return -1;
     if (n_cols <= 0 || !col_node) return fail(ctx, "apples_set_matrix_columns: bad arguments");
+    if (check_leaf_ids(ctx, "col_node", col_node, n_cols)) return -1;
+    ctx->h_col_node.assign(col_node, col_node + n_cols);
     CK(cudaSetDevice(ctx->device));
     if (ensure(ctx, ctx->col_node, (size_t)n_cols * 4)) return -1;
     CK(cudaMemcpy(ctx->col_node.p, col_node, (size_t)n_cols * 4, cudaMemcpyHostToDevice));
@@ -901,6 +939,8 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
     const int n_mem = group_offsets[n_rep];
     for (int i = 0; i < n_mem; ++i)
         if (group_members[i] < 0 || group_members[i] >= n_ref) return fail(ctx, "apples_set_reference_bytes: member out of range");
+    if (check_leaf_ids(ctx, "ref_node", ref_node, n_ref)) return -1;
+    ctx->h_ref_node.assign(ref_node, ref_node + n_ref);
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     ctx->kind = kind;
@@ -1063,12 +1103,10 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
         if (ensure(ctx, qnv, (size_t)q_pad * 4)) { cleanup(); return -1; }
         launch_transpose_nuc((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qwm.p, ctx->Wp, q_pad, DT_TQ, s);
         launch_row_valid((const uint32_t*)dq.p, (int)nq, ctx->W, (uint32_t*)qnv.p, q_pad, s);
-        if (ensure(ctx, ctx->tile_counter, 4)) { cleanup(); return -1; }
-        cudaMemsetAsync(ctx->tile_counter.p, 0, 4, s);
         launch_dense_nuc_full((const uint32_t*)qwm.p, (const uint32_t*)qnv.p, q_pad, (int)nq,
                               (const uint32_t*)ctx->refs_wm.p, (const uint32_t*)ctx->refs_nv.p, ctx->ref_pad,
                               ctx->n_ref, ctx->W, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
-                              (double*)dd.p, (int*)ctx->tile_counter.p, ctx->num_sms, s);
+                              (double*)dd.p, ctx->num_sms, s);
     } else {
         launch_dense_aa((const uint8_t*)dq.p, (int)nq, (const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, ctx->L,
                         overlap_frac, (double*)dd.p, ctx->n_ref, (uint32_t*)dv.p, s);
@@ -1115,6 +1153,17 @@ int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const doubl
     io.edge = &e; io.error = &er; io.distal = &di; io.pendant = &pe; io.status = &st;
     io.dbg_x1 = x1; io.dbg_x2 = x2; io.dbg_err = err; io.dbg_valid = valid;
     return run_batch(ctx, 1, io, params);
+}
+
+int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32_t* overflowed) {
+    if (!ctx) return -1;
+    if (n < 0 || (size_t)n > ctx->hK.size() || (size_t)n > ctx->h_over.size()) return fail(ctx, "apples_last_counts: the last batch had %zu queries", ctx->hK.size());
+    for (int64_t i = 0; i < n; ++i) {
+        if (K) K[i] = ctx->hK[i];
+        if (V) V[i] = ctx->hV[i];
+        if (overflowed) overflowed[i] = ctx->h_over[i];
+    }
+    return 0;
 }
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {

@@ -30,12 +30,6 @@ constexpr int DT_CONSUMERS = (DT_TQ / 4) * (DT_TR / 4);  // one thread per 4x4 b
 #ifndef DT_SELF_PRODUCE
 #define DT_SELF_PRODUCE 1  // 1: no producer warp, thread 0 keeps the ring full (128 registers per thread); 0: 17th warp
 #endif
-#ifndef DT_DYNAMIC_TILES
-#define DT_DYNAMIC_TILES 0  // EXPERIMENT (written after round 1's GPU budget was spent, not yet run on hardware): tiles
-                            // are handed out by an atomic counter instead of static striping, so that CTAs delayed by
-                            // a co-running kernel do not set the kernel's duration
-#endif
-static_assert(!DT_DYNAMIC_TILES || (DT_SELF_PRODUCE && DT_STAGES_V <= 3), "dynamic tiles need the polling producer and a 4-entry tile ring");
 constexpr int DT_THREADS = DT_CONSUMERS + (DT_SELF_PRODUCE ? 0 : 32);  // + one producer warp unless warp 0 produces
 constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
 constexpr int DT_STAGE_BYTES = DT_STAGE_WORDS * 4;
@@ -189,10 +183,10 @@ void launch_transpose_nuc(const uint32_t* rm, int rows, int W, uint32_t* wm, int
 void launch_row_valid(const uint32_t* rm, int rows, int W, uint32_t* nv, int rows_pad, cudaStream_t s);
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys, int64_t ldk,
-                           unsigned long long* clk, int* tile_counter, int num_sms, cudaStream_t s);
+                           unsigned long long* clk, int num_sms, cudaStream_t s);
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
-                           double* dist, int* tile_counter, int num_sms, cudaStream_t s);
+                           double* dist, int num_sms, cudaStream_t s);
 void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
                      int64_t ldd, uint32_t* valid_out, cudaStream_t s);
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s);

@@ -140,7 +140,6 @@ struct DenseNucArgs {
     int64_t ldk;
     uint32_t k_one, k_two17;  // 1 and 1 << 17 (see the consumer loop)
     unsigned long long* clk;  // optional: {clock64, globaltimer} of CTA 0 at start and end -> effective SM clock
-    int* tile_counter;        // DT_DYNAMIC_TILES: next tile to hand out (zeroed before the launch)
     // full epilogue (parity export)
     int nq, n_ref, vmin;
     uint32_t* mism;
@@ -193,23 +192,9 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     // released (non-blocking test), and blocks only if chunk `it` itself has not been issued yet.
     uint32_t p_it = 0;
     int p_c = 0;
-#if DT_DYNAMIC_TILES
-    // tiles come from an atomic counter; the id of the p_seq-th tile of this CTA is published in a 4-entry ring before
-    // its first stage is issued (the mbarrier arrive / wait pair orders the two), -1 = no more tiles
-    int* tile_ring = reinterpret_cast<int*>(empty_bar + DT_STAGES);
-    uint32_t p_seq = 0;
-    bool p_done = false;
-    int p_tile = 0;
-    if (tid == 0) p_tile = atomicAdd(a.tile_counter, 1);
-#else
     int p_tile = blockIdx.x;
-#endif
     auto produce = [&](uint32_t it_now) {
-#if DT_DYNAMIC_TILES
-        while (!p_done && p_it < it_now + DT_STAGES) {
-#else
         while (p_tile < n_tiles && p_it < it_now + DT_STAGES) {
-#endif
             const int ps = p_it % DT_STAGES;
             const uint32_t pph = ((p_it / DT_STAGES) & 1) ^ 1;
             if (p_it == it_now) {
@@ -217,21 +202,9 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
             } else if (!mbar_try_wait(&empty_bar[ps], pph)) {
                 break;
             }
-#if DT_DYNAMIC_TILES
-            if (p_c == 0) tile_ring[p_seq & 3] = p_tile < n_tiles ? p_tile : -1;
-            if (p_tile >= n_tiles) {  // an empty stage wakes the consumers, which read the -1 and leave
-                mbar_arrive(&full_bar[ps]);
-                p_done = true;
-                break;
-            }
-#endif
             issue_stage(p_it, p_tile, p_c);
             ++p_it;
-#if DT_DYNAMIC_TILES
-            if (++p_c == n_chunks) { p_c = 0; ++p_seq; p_tile = atomicAdd(a.tile_counter, 1); }
-#else
             if (++p_c == n_chunks) { p_c = 0; p_tile += gridDim.x; }
-#endif
         }
     };
 #else
@@ -259,14 +232,8 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
     uint32_t it = 0;
     const uint32_t k_one = a.k_one, k_two17 = a.k_two17;  // run-time multipliers: keeps the accumulations IMADs
     const uint32_t k_two = a.k_two17 >> 16;
-#if DT_DYNAMIC_TILES
-    bool c_done = false;
-    for (uint32_t c_seq = 0; !c_done; ++c_seq) {
-        int qt = 0, rt = 0;
-#else
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int qt = tile / n_rt, rt = tile % n_rt;
-#endif
         // per pair: acc = D (low 16 bits) | E1 (high 16 bits); `ones` is the weight-1 plane of a carry-save counter over
         // the x words: two words are folded with one full adder (2 LOP3) and only the carry (weight 2) is popcounted,
         // which moves POPC work from the XU pipe to the ALU pipe; DT_MCSA of the 16 pairs do the same for their z
@@ -290,17 +257,6 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
             if (warp == 0) __syncwarp();
 #endif
             mbar_wait(&full_bar[s], ph);
-#if DT_DYNAMIC_TILES
-            if (c == 0) {
-                const int tile = tile_ring[c_seq & 3];
-                if (tile < 0) {
-                    c_done = true;
-                    break;
-                }
-                qt = tile / n_rt;
-                rt = tile % n_rt;
-            }
-#endif
             const uint32_t* sq = stage_base + (size_t)s * DT_STAGE_WORDS;
             const uint32_t* sr = sq + 3 * DT_WC * DT_TQ;
             // the zero words that pad the last stage are not computed on
@@ -356,9 +312,6 @@ __global__ void __launch_bounds__(DT_THREADS, DT_MINBLOCKS) dense_nuc_kernel(con
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
-#if DT_DYNAMIC_TILES
-        if (c_done) break;
-#endif
         uint32_t accM[4][4], accV[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -432,10 +385,9 @@ static int dense_grid(int q_pad, int r_pad, int num_sms) {
 
 void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int W, int Wp, uint32_t* keys,
-                           int64_t ldk, unsigned long long* clk, int* tile_counter, int num_sms, cudaStream_t s) {
+                           int64_t ldk, unsigned long long* clk, int num_sms, cudaStream_t s) {
     DenseNucArgs a{};
     a.clk = clk;
-    a.tile_counter = tile_counter;
     a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.W = W; a.Wp = Wp; a.keys = keys; a.ldk = ldk;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     dense_nuc_kernel<false><<<dense_grid(q_pad, r_pad, num_sms), DT_THREADS, DT_SMEM_BYTES, s>>>(a);
@@ -443,10 +395,9 @@ void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad
 
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp,
-                           int vmin, uint32_t* mism, uint32_t* valid, double* dist, int* tile_counter, int num_sms,
+                           int vmin, uint32_t* mism, uint32_t* valid, double* dist, int num_sms,
                            cudaStream_t s) {
     DenseNucArgs a{};
-    a.tile_counter = tile_counter;
     a.q_wm = q_wm; a.r_wm = r_wm; a.q_nv = q_nv; a.r_nv = r_nv; a.q_pad = q_pad; a.r_pad = r_pad; a.W = W; a.Wp = Wp;
     a.k_one = 1u; a.k_two17 = 1u << 17;
     a.nq = nq; a.n_ref = n_ref; a.vmin = vmin; a.mism = mism; a.valid = valid; a.dist = dist;

@@ -36,14 +36,28 @@ __global__ void pack_nuc_kernel(const uint8_t* __restrict__ bytes, int64_t row_s
     o[2 * W] = va;
 }
 
-__constant__ uint8_t c_aa_code[256];
+// byte -> amino-acid code, built at compile time so that the module's static initialiser puts it into the constant
+// memory of EVERY device the library is used on (no per-call upload, no synchronisation)
+struct AaCodeTable {
+    uint8_t t[256];
+    constexpr AaCodeTable() : t{} {
+        const char order[21] = "ARNDCQEGHILKMFPSTWYV";
+        for (int i = 0; i < 256; ++i) t[i] = 0;  // NA = 0: unknown bytes count as 'A' (distance.py:418)
+        for (int i = 0; i < 20; ++i) {
+            t[(unsigned char)order[i]] = (uint8_t)i;
+            t[(unsigned char)(order[i] + 32)] = (uint8_t)i;
+        }
+        t[(unsigned char)'-'] = 20;
+    }
+};
+__constant__ AaCodeTable c_aa_code = AaCodeTable();
 
 __global__ void pack_aa_kernel(const uint8_t* __restrict__ bytes, int64_t row_stride, int n, int L, int Lp,
                                uint8_t* __restrict__ out) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n * Lp) return;
     const int row = (int)(t / Lp), s = (int)(t % Lp);
-    out[t] = s < L ? c_aa_code[bytes[(size_t)row * row_stride + s]] : (uint8_t)20;
+    out[t] = s < L ? c_aa_code.t[bytes[(size_t)row * row_stride + s]] : (uint8_t)20;
 }
 
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad,
@@ -54,20 +68,6 @@ cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int 
         const int64_t total = (int64_t)n * W;
         pack_nuc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, W, (uint32_t*)out, bad);
     } else {
-        // the table lives in the constant memory of the CURRENT device: (re)written on every call (256 bytes) so that
-        // several contexts on different devices in one process all see it
-        uint8_t tab[256];
-        memset(tab, 0, sizeof tab);  // NA = 0: unknown bytes count as 'A' (distance.py:418)
-        const char* order = "ARNDCQEGHILKMFPSTWYV";
-        for (int i = 0; i < 20; ++i) {
-            tab[(unsigned char)order[i]] = (uint8_t)i;
-            tab[(unsigned char)(order[i] + 32)] = (uint8_t)i;
-        }
-        tab[(unsigned char)'-'] = 20;
-        cudaError_t e = cudaMemcpyToSymbolAsync(c_aa_code, tab, 256, 0, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) return e;
-        e = cudaStreamSynchronize(s);  // `tab` is a stack buffer
-        if (e != cudaSuccess) return e;
         const int Lp = apples_aa_row_bytes(L);
         const int64_t total = (int64_t)n * Lp;
         pack_aa_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, Lp, (uint8_t*)out);

@@ -65,6 +65,7 @@ __device__ __forceinline__ void accumulate(double* acc, const double* m, double 
 struct EdgeSol {
     double x1, x2, err;
     bool int0;
+    bool deg;   // the reference raises here: 1 / 0.0 (ZeroDivisionError) or det == 0 (assert), util.py:26-27
 };
 
 // placement_per_edge + solve2_2 + error_per_edge for one node
@@ -74,13 +75,15 @@ __device__ __forceinline__ EdgeSol solve_edge(const double* S, const double* R, 
     const double a21 = a12, a22 = a11;
     const double c1 = R[3] + S[3] - ln * S[0] - R[1] - S[1];
     const double c2 = R[3] - S[3] + ln * S[0] - R[1] + S[1];
-    const double det = 1.0 / (a11 * a22 - a12 * a21);
+    const double den = a11 * a22 - a12 * a21;
+    const double det = 1.0 / den;
     const double x1n = (a22 * c1 - a12 * c2) * det;
     const double x2n = (-a21 * c1 + a11 * c2) * det;
     EdgeSol e;
     e.x1 = x1n;
     e.x2 = x2n;
     e.int0 = false;
+    e.deg = den == 0.0 || det == 0.0;
     if (!negative_branch) {  // util.py:32-49, same case order and strict inequalities
         if (x1n < 0.0 && x2n < 0.0) {
             e.x1 = 0.0; e.x2 = 0.0; e.int0 = true;
@@ -323,9 +326,11 @@ __global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArg
     const bool dbg = a.dbg_x1 != nullptr && q == a.dbg_query;
     double bval = 0.0;
     int bidx = 0x7fffffff;
+    bool degenerate = false;
     for (int p = lane; p < V; p += 32) {
         NodeRec& r = rec[p];
         const EdgeSol e = solve_edge(r.S, r.R, r.len, a.negative_branch);
+        degenerate |= e.deg;
         if (dbg) {
             a.dbg_x1[r.orig] = e.x1;
             a.dbg_x2[r.orig] = e.x2;
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArg
         if (bidx == 0x7fffffff || key < bval) { bval = key; bidx = p; }  // ascending p per lane: first minimum kept
     }
     warp_argmin(bval, bidx);
+    degenerate = __any_sync(FULLMASK, degenerate);
     int best = bidx;
     if (a.criterion == APPLES_HYBRID) {
         // heapq.nsmallest(floor(log2 V), key=error) in (error, order) order, then the first minimum of x_1 among
@@ -371,7 +377,8 @@ __global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArg
         a.out_error[q] = bs.err;
         a.out_distal[q] = rb.len - bs.x2;
         a.out_pendant[q] = bs.x1;
-        a.out_status[q] = (flag ? APPLES_PLACED_MISPLACEMENT_FLAG : APPLES_PLACED) | (bs.int0 ? APPLES_FLAG_PENDANT_INT0 : 0);
+        a.out_status[q] = (flag ? APPLES_PLACED_MISPLACEMENT_FLAG : APPLES_PLACED) | (bs.int0 ? APPLES_FLAG_PENDANT_INT0 : 0) |
+                          (degenerate ? APPLES_FLAG_DEGENERATE : 0);
     }
 }
 

@@ -2,9 +2,10 @@
 apples/OptionsRun.py:5-112 and apples/OptionsBuild.py:4-10, plus two additions that do not exist upstream:
   --clusters FILE   TreeCluster-format TSV to use instead of running a clustering (TreeCluster.py is an external
                     dependency of the reference, Reference.py:87-88)
-  --device N        CUDA device ordinal (default 0); -T/--threads is accepted and ignored (no CPU workers).
+  --device N        first CUDA device ordinal (default 0); -T/--threads is accepted and ignored (no CPU workers);
+  --gpus N          GPUs to shard the queries over (0 = all visible: the analogue of upstream's -T 0 = all cores).
 Backbone re-estimation with FastTree (reestimateBackbone.py) is outside the hot path: it is never run here, as with
-the reference's -D flag.
+the reference's -D flag; without -D a warning says that results can differ from upstream's default.
 """
 import logging
 from optparse import OptionParser
@@ -30,7 +31,9 @@ def _basic(output_filetype):
     p.add_option('-v', '--version', dest='print_version', action='store_true', default=False,
                  help='print APPLES version number. ')
     p.add_option('--clusters', dest='cluster_fp', metavar='FILE', help='TreeCluster-format cluster TSV')
-    p.add_option('--device', dest='device', type=int, default=0, metavar='NUMBER', help='CUDA device ordinal')
+    p.add_option('--device', dest='device', type=int, default=0, metavar='NUMBER', help='first CUDA device ordinal')
+    p.add_option('--gpus', dest='num_gpus', type=int, default=0, metavar='NUMBER',
+                 help='number of GPUs to shard the queries over (0 = all visible, like -T 0 = all cores upstream)')
     return p
 
 
@@ -39,7 +42,14 @@ def _parse(p, argv=None):
     if options.print_version:
         print('APPLES version ' + __version__, flush=True)
         raise SystemExit(0)
+    # Upstream re-estimates the backbone branch lengths with FastTree unless -D is given (OptionsBasic.py:
+    # reestimate_backbone = not disable_reestimation; reestimateBackbone.py).  That step is outside this build: the tree
+    # is always used as given, i.e. -D semantics.  Say so instead of silently differing from upstream's default.
     options.reestimate_backbone = False
+    if getattr(options, 'ref_fp', None) and getattr(options, 'tree_fp', None) and not options.disable_reestimation:
+        logging.warning('Backbone branch-length re-estimation (FastTree, upstream default without -D) is not part of this '
+                        'build: the tree is used as given, as with -D. Placements can differ from an upstream run made '
+                        'without -D; pass -D to silence this warning.')
     if options.debug_mode:
         logging.getLogger().setLevel(logging.DEBUG)
     return options, args

@@ -3,7 +3,7 @@
 The reference's only parallelism is `mp.Pool.starmap` over queries with fork-inherited read-only state
 (run_apples.py:20,94-102).  Here: one process per GPU, queries split into contiguous blocks of ceil(Q / G), the packed
 reference + tree replicated on every GPU, no data-path collective; the single collective is the final all-gather of
-the placements (edge i32, error f64, distal f64, pendant f64, status i32 = 32 B per query), after which every rank
+the placements (ONE collective of 32-byte records: edge i32, status i32, error f64, distal f64, pendant f64), after which every rank
 holds the results of all queries in input order -- so the N-GPU output is byte-identical to the 1-GPU output.
 
 torch.distributed is plumbing here: `nccl` on GPUs (NVLink / NVSwitch), `gloo` in the CPU tests.
@@ -17,31 +17,64 @@ def shard_bounds(n_items, world):
     return [(min(r * per, n_items), min((r + 1) * per, n_items)) for r in range(world)]
 
 
+RECORD_BYTES = 32  # one placement: edge i32 | status i32 | error f64 | distal f64 | pendant f64
+
+
+def pack_records(edge, error, distal, pendant, status):
+    """Five result arrays (torch tensors on one device) -> one int64 [n, 4] tensor of 32-byte records, so that the final
+    gather is ONE collective.  Word 0 = edge (low 32 bits) | status (high 32 bits), words 1-3 = the doubles' bit patterns."""
+    import torch
+    n = edge.shape[0]
+    rec = torch.empty((n, 4), dtype=torch.int64, device=edge.device)
+    rec[:, 0] = (edge.to(torch.int64) & 0xffffffff) | (status.to(torch.int64) << 32)
+    rec[:, 1] = error.view(torch.int64)
+    rec[:, 2] = distal.view(torch.int64)
+    rec[:, 3] = pendant.view(torch.int64)
+    return rec
+
+
+def unpack_records(rec):
+    """int64 [n, 4] records -> (edge i32, error f64, distal f64, pendant f64, status i32) tensors (same device)."""
+    import torch
+    w0 = rec[:, 0]
+    edge = (w0 << 32 >> 32).to(torch.int32)   # arithmetic shift: sign-extends the low half (edge may be -1)
+    status = (w0 >> 32).to(torch.int32)
+    return (edge, rec[:, 1].contiguous().view(torch.float64), rec[:, 2].contiguous().view(torch.float64),
+            rec[:, 3].contiguous().view(torch.float64), status)
+
+
+def gather_records(rec, n_total=None, out=None):
+    """All-gather of the ranks' record blocks (each rank holds the block of ceil(n_total / world) queries that
+    shard_bounds gives it, the last ones possibly shorter).  Returns the records of all queries in input order on every
+    rank.  `out` may be a preallocated [per * world, 4] tensor (bench.py reuses it every step)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return rec
+    world = dist.get_world_size()
+    if n_total is None:
+        n_total = rec.shape[0] * world
+    per = -(-int(n_total) // world)
+    if rec.shape[0] < per:
+        rec = torch.cat([rec, torch.zeros((per - rec.shape[0], 4), dtype=rec.dtype, device=rec.device)])
+    full = out if out is not None else torch.empty((per * world, 4), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(full, rec.contiguous())
+    return full[:n_total]
+
+
 def gather_placements(local, n_total, device=None):
     """local: tuple (edge i32, error f64, distal f64, pendant f64, status i32) of this rank's shard as numpy arrays or
-    torch tensors.  Returns the same tuple for all `n_total` queries in input order, as numpy arrays.
-
-    Shards are padded to the common block size ceil(n_total / world) so one all_gather_into_tensor per array suffices.
-    """
+    torch tensors.  Returns the same tuple for all `n_total` queries in input order, as numpy arrays, after ONE
+    all-gather of 32-byte records."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return tuple(np.asarray(a.cpu() if hasattr(a, 'cpu') else a) for a in local)
-    world = dist.get_world_size()
-    bounds = shard_bounds(n_total, world)
-    per = bounds[0][1] - bounds[0][0]
     if device is None:
         device = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
-    out = []
-    for a in local:
-        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-        t = t.to(device)
-        if t.numel() < per:
-            t = torch.cat([t, torch.zeros(per - t.numel(), dtype=t.dtype, device=device)])
-        full = torch.empty(per * world, dtype=t.dtype, device=device)
-        dist.all_gather_into_tensor(full, t.contiguous())
-        out.append(full[:n_total].cpu().numpy())
-    return tuple(out)
+    ts = [(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device) for a in local]
+    full = gather_records(pack_records(*ts), n_total)
+    return tuple(t.cpu().numpy() for t in unpack_records(full))
 
 
 def place_sharded(place_fn, n_total):

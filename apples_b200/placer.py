@@ -111,9 +111,15 @@ class GpuPlacer:
         return np.array([self.name_to_node.get(n, -1) for n in names], dtype=np.int32)
 
     @staticmethod
-    def params_from_options(options):
+    def params_from_options(options, reference=None):
+        """Alignment mode takes the cluster-expansion threshold from the REFERENCE object, as upstream does
+        (Reference.py:146 `head.dist <= self.threshold`; with `-a database` that is the build-time -f, whatever -f the
+        run was given); distance-matrix mode uses the run's -f (PoolQueryWorker.py:55)."""
+        thr = options.filt_threshold
+        if reference is not None and getattr(reference, 'threshold', None) is not None:
+            thr = reference.threshold
         return _lib.make_params(options.method_name, options.criterion_name, bool(options.negative_branch),
-                                options.base_observation_threshold, options.filt_threshold,
+                                options.base_observation_threshold, thr,
                                 getattr(options, 'minimum_alignment_overlap', 0.001))
 
     # ------------------------------------------------------------------------------------------------ hot path
@@ -121,31 +127,31 @@ class GpuPlacer:
         return (np.empty(nq, np.int32), np.empty(nq, np.float64), np.empty(nq, np.float64), np.empty(nq, np.float64),
                 np.empty(nq, np.int32))
 
-    def place_packed(self, packed, self_node, params):
+    def place_packed(self, packed, self_node, params, out=None):
         """packed queries (host) -> (edge, error, distal, pendant, status) arrays."""
         nq = int(packed.shape[0])
-        out = self._outputs(nq)
+        out = out if out is not None else self._outputs(nq)
         packed = np.ascontiguousarray(packed)
         self._check(self.lib.apples_place_batch(self.h, nq, _lib.ptr(packed), _lib.ptr(self_node), _lib.C.byref(params),
                                                 *[_lib.ptr(o) for o in out]))
         return out
 
-    def place_bytes(self, mat, self_node, params):
+    def place_bytes(self, mat, self_node, params, out=None):
         """alignment bytes uint8 [nq, L] (host) -> result arrays; packing happens on the device."""
         mat = np.ascontiguousarray(mat, dtype=np.uint8)
         if mat.shape[1] != self.L:
             raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], self.L))
         nq = int(mat.shape[0])
-        out = self._outputs(nq)
+        out = out if out is not None else self._outputs(nq)
         self._check(self.lib.apples_place_batch_bytes(self.h, nq, _lib.ptr(mat), mat.shape[1], _lib.ptr(self_node),
                                                       _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
         return out
 
-    def place_rows(self, rows, self_node, params):
+    def place_rows(self, rows, self_node, params, out=None):
         """distance-matrix rows float64 [nq, n_cols] -> result arrays."""
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         nq = int(rows.shape[0])
-        out = self._outputs(nq)
+        out = out if out is not None else self._outputs(nq)
         self._check(self.lib.apples_place_batch_matrix(self.h, nq, _lib.ptr(rows), _lib.ptr(self_node),
                                                        _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
         return out
@@ -166,6 +172,12 @@ class GpuPlacer:
     def results_to_device(self, edge, error, distal, pendant, status):
         """copy the resident results into caller-owned device tensors (objects with .data_ptr())"""
         self._check(self.lib.apples_results_to_device(self.h, *[t.data_ptr() for t in (edge, error, distal, pendant, status)]))
+
+    def last_counts(self, n):
+        """(K observed leaves, V valid nodes, overflowed flag) per query of the last macro-batch (test seam)."""
+        K, V, ov = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self._check(self.lib.apples_last_counts(self.h, int(n), _lib.ptr(K), _lib.ptr(V), _lib.ptr(ov)))
+        return K, V, ov
 
     def timings(self, reset=False):
         v = np.zeros(15, np.float64)
@@ -211,11 +223,20 @@ class GpuPlacer:
         return x1, x2, err, valid
 
 
-def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True):
-    """Device result arrays -> the per-query dicts PoolQueryWorker.runquery returns, with its messages."""
+def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True, degenerate='raise'):
+    """Device result arrays -> the per-query dicts PoolQueryWorker.runquery returns, with its messages.
+
+    degenerate='raise' (default): a query whose status carries APPLES_FLAG_DEGENERATE raises ZeroDivisionError, as the
+    reference does in util.solve2_2 (util.py:26-27: `1 / (a_11 * a_22 - a_12 * a_21)`, `assert det != 0`), where the
+    exception ends the whole run.  degenerate='keep' returns the record with whatever inf/nan arithmetic produced."""
     # the common record (placed, no flag, name not in the backbone) is built in one comprehension; the per-record
     # control flow below only runs for the others (6.5 -> 1.4 s per million queries)
     st_arr = np.asarray(out[4])
+    if degenerate == 'raise':
+        bad = np.flatnonzero(st_arr & _lib.FLAG_DEGENERATE)
+        if bad.size:
+            raise ZeroDivisionError('float division by zero: the least-squares system of query %s is singular on at least '
+                                    'one edge (the reference raises in util.solve2_2 as well)' % names[int(bad[0])])
     special = np.flatnonzero((st_arr != _lib.PLACED) | np.asarray(in_backbone, dtype=bool)).tolist()
     edge, error, distal, pendant, status = [o.tolist() for o in out]
     # five container objects per record: the cyclic GC would walk the growing list again and again (5x slower)
@@ -258,27 +279,122 @@ def results_to_jplace(names, in_backbone, out, exclude_intplace=False, log=True)
     return results
 
 
-def place_batch(reference, options, name_to_node_map, queries, tree=None, placer=None, device=0):
-    """Drop-in for `pool.starmap(queryworker.runquery, queries)` (run_apples.py:94-102).
+class MultiGpuPlacer:
+    """Queries sharded over several GPUs of one box: one GpuPlacer (context) per device with the tree and the packed
+    reference replicated, one host thread per context (the C ABI's threading rule), contiguous blocks of
+    ceil(Q / G) queries per GPU.  Every context writes its block straight into the shared host
+    result arrays, so the output is in input order and byte-identical to the single-GPU output.  This is the in-process
+    analogue of upstream's `mp.Pool(num_thread)` (run_apples.py:101-102); under torchrun the same split runs with one
+    process per GPU and a final NCCL gather (apples_b200.parallel)."""
 
-    queries yields (query_name, query_seq 'S1' row or None, obs_dist dict or None) exactly as run_apples.py builds
-    them (:43-54 distance matrix, :85-89 alignment).  Returns the list of jplace dicts in input order.
-    `tree` is the BackboneTree the name_to_node_map belongs to (or pass an existing GpuPlacer).
-    """
-    queries = list(queries)
-    if not queries:
-        return []
+    def __init__(self, tree, reference=None, name_to_node_map=None, devices=(0,), matrix_tags=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.devices = [int(d) for d in devices]
+        if not self.devices:
+            raise ValueError('MultiGpuPlacer needs at least one device')
+        self.pool = ThreadPoolExecutor(max_workers=len(self.devices))
+        # contexts are built in parallel: each uploads its own replica of the reference
+        self.placers = list(self.pool.map(
+            lambda d: GpuPlacer(tree, reference, name_to_node_map, device=d, matrix_tags=matrix_tags), self.devices))
+        p0 = self.placers[0]
+        self.name_to_node, self.L, self.kind, self.ref_names = p0.name_to_node, p0.L, p0.kind, p0.ref_names
+        self.matrix_tags = p0.matrix_tags
+        self.params_from_options = p0.params_from_options
+
+    def close(self):
+        for p in self.placers:
+            p.close()
+        self.pool.shutdown(wait=True)
+
+    def self_nodes(self, names):
+        return self.placers[0].self_nodes(names)
+
+    def _outputs(self, nq):
+        return self.placers[0]._outputs(nq)
+
+    def set_matrix_tags(self, tags):
+        for p in self.placers:
+            p.set_matrix_tags(tags)
+        self.matrix_tags = self.placers[0].matrix_tags
+
+    def _sharded(self, method, mat, self_node, params):
+        from .parallel import shard_bounds
+        nq = int(mat.shape[0])
+        out = self.placers[0]._outputs(nq)
+        bounds = shard_bounds(nq, len(self.placers))
+
+        def run(i):
+            b, e = bounds[i]
+            if e > b:
+                part = getattr(self.placers[i], method)(mat[b:e], None if self_node is None else self_node[b:e], params,
+                                                        out=tuple(o[b:e] for o in out))
+                assert part[0].ctypes.data == out[0][b:e].ctypes.data
+        list(self.pool.map(run, range(len(self.placers))))
+        return out
+
+    def place_bytes(self, mat, self_node, params):
+        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        return self._sharded('place_bytes', mat, self_node, params)
+
+    def place_rows(self, rows, self_node, params):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        return self._sharded('place_rows', rows, self_node, params)
+
+
+def visible_devices(first=0, count=0):
+    """Device ordinals for `--device first --gpus count` (count 0 = every visible device from `first` on)."""
+    n = _lib.device_count()
+    if n <= 0:
+        raise RuntimeError('no CUDA device is visible; apples_b200 has no CPU fallback')
+    if count <= 0:
+        count = n - first
+    if first < 0 or count <= 0 or first + count > n:
+        raise ValueError('--device %d --gpus %d does not fit the %d visible CUDA device(s)' % (first, count, n))
+    return list(range(first, first + count))
+
+
+def _distributed_world():
+    """(rank, world) when torch.distributed has been initialised (torchrun: one process per GPU), else (0, 1)."""
+    if 'torch' not in sys.modules:
+        return 0, 1
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def place_arrays(reference, options, name_to_node_map, queries, tree=None, placer=None, device=0, devices=None):
+    """The device part of place_batch: returns (names, in_backbone, (edge, error, distal, pendant, status)) for ALL
+    queries in input order.  Inside an initialised torch.distributed job every rank places its contiguous block of
+    ceil(Q / world) queries on its own GPU and the blocks are exchanged with one all-gather of 32-byte records
+    (apples_b200.parallel); otherwise the queries are sharded over `devices` inside this process."""
+    names = [q[0] for q in queries]
+    rank, world = _distributed_world()
+    lo, hi = 0, len(queries)
+    if world > 1:
+        from .parallel import shard_bounds
+        lo, hi = shard_bounds(len(queries), world)[rank]
     own = placer is None
     if placer is None:
         if tree is None:
             raise ValueError('place_batch needs the BackboneTree (tree=) or a GpuPlacer (placer=)')
-        placer = GpuPlacer(tree, reference, name_to_node_map, device=device)
+        devs = [int(d) for d in devices] if devices else [int(device)]
+        devs = devs[:max(1, min(len(devs), hi - lo))]
+        if len(devs) > 1:
+            placer = MultiGpuPlacer(tree, reference, name_to_node_map, devices=devs)
+        else:
+            placer = GpuPlacer(tree, reference, name_to_node_map, device=devs[0])
     try:
-        params = placer.params_from_options(options)
-        names = [q[0] for q in queries]
         in_backbone = [n in placer.name_to_node for n in names]
-        self_node = placer.self_nodes(names)
-        if queries[0][2]:
+        # upstream decides per query (`if obs_dist` in runquery, PoolQueryWorker.py:40); one batch is one mode here
+        matrix = bool(queries[0][2])
+        for q in queries:
+            if bool(q[2]) != matrix:
+                raise ValueError('place_batch: query %s mixes distance-matrix and alignment input in one batch' % q[0])
+        mine = queries[lo:hi]
+        self_node = placer.self_nodes(names[lo:hi])
+        if matrix:
+            params = placer.params_from_options(options)
             # distance-matrix mode: every row is a {tag: float} dict in header order
             tags = list(queries[0][2].keys())
             seen = set(tags)
@@ -289,19 +405,41 @@ def place_batch(reference, options, name_to_node_map, queries, tree=None, placer
                         tags.append(t)
             if placer.matrix_tags != tags:
                 placer.set_matrix_tags(tags)
-            rows = np.full((len(queries), len(tags)), -1.0, dtype=np.float64)
+            rows = np.full((len(mine), len(tags)), -1.0, dtype=np.float64)
             col = {t: j for j, t in enumerate(tags)}
-            for i, q in enumerate(queries):
+            for i, q in enumerate(mine):
                 if len(q[2]) == len(tags) and list(q[2]) == tags:  # same header order (run_apples.py:43-54)
                     rows[i] = np.fromiter(q[2].values(), dtype=np.float64, count=len(tags))
                 else:
                     for t, v in q[2].items():
                         rows[i, col[t]] = v
-            out = placer.place_rows(rows, self_node, params)
+            out = placer.place_rows(rows, self_node, params) if mine else placer._outputs(0)
         else:
-            mat = _fasta.as_byte_matrix([q[1] for q in queries], placer.L)
-            out = placer.place_bytes(mat, self_node, params)
-        return results_to_jplace(names, in_backbone, out, getattr(options, 'exclude_intplace', False))
+            params = placer.params_from_options(options, reference)
+            mat = _fasta.as_byte_matrix([q[1] for q in mine], placer.L)
+            out = placer.place_bytes(mat, self_node, params) if mine else placer._outputs(0)
+        if world > 1:
+            from .parallel import gather_placements
+            out = gather_placements(out, len(queries))
+        return names, in_backbone, out
     finally:
         if own:
             placer.close()
+
+
+def place_batch(reference, options, name_to_node_map, queries, tree=None, placer=None, device=0, devices=None):
+    """Drop-in for `pool.starmap(queryworker.runquery, queries)` (run_apples.py:94-102).
+
+    queries yields (query_name, query_seq 'S1' row or None, obs_dist dict or None) exactly as run_apples.py builds
+    them (:43-54 distance matrix, :85-89 alignment).  Returns the list of jplace dicts in input order.
+    `tree` is the BackboneTree the name_to_node_map belongs to (or pass an existing GpuPlacer / MultiGpuPlacer).
+    `devices` = list of CUDA ordinals to shard the queries over (default: the single `device`); the result does not
+    depend on it.  Under torchrun (torch.distributed initialised) every rank returns the full list.
+    """
+    queries = list(queries)
+    if not queries:
+        return []
+    names, in_backbone, out = place_arrays(reference, options, name_to_node_map, queries, tree=tree, placer=placer,
+                                           device=device, devices=devices)
+    log = _distributed_world()[0] == 0   # messages once per job
+    return results_to_jplace(names, in_backbone, out, getattr(options, 'exclude_intplace', False), log=log)

@@ -47,14 +47,22 @@ class ReducedReference:
         if cluster_tsv is None and shutil.which('TreeCluster.py') and tree_file and os.path.isfile(str(tree_file)):
             # the reference's own route (Reference.py:85-92)
             out = tempfile.NamedTemporaryFile(delete=False, mode='w+t').name
-            with open(os.devnull, 'w') as nul:
-                subprocess.call(['TreeCluster.py', '-t', str(threshold * 1.2), '-i', tree_file, '-m', 'max',
-                                 '-o', out], stdout=nul, stderr=nul)
-            if os.path.getsize(out) > 0:
-                cluster_tsv = out
-        if cluster_tsv is not None:
+            try:
+                with open(os.devnull, 'w') as nul:
+                    subprocess.call(['TreeCluster.py', '-t', str(threshold * 1.2), '-i', tree_file, '-m', 'max',
+                                     '-o', out], stdout=nul, stderr=nul)
+                if os.path.getsize(out) > 0:
+                    clusters = _tc.read_cluster_tsv(out)
+            finally:
+                os.unlink(out)
+        if clusters is not None:
+            pass
+        elif cluster_tsv is not None:
             clusters = _tc.read_cluster_tsv(cluster_tsv)
         else:
+            logging.warning('TreeCluster.py is not on PATH (or produced no output) and no --clusters file was given: '
+                            'using the built-in max-diameter clustering, whose parity with TreeCluster is not pinned. '
+                            'Representatives and observed sets can differ from an upstream run.')
             if tree is None:
                 from .tree import BackboneTree
                 tree = BackboneTree.from_newick(tree_file)

@@ -20,28 +20,24 @@ def max_diameter_clusters(tree, threshold):
     M = tree.num_nodes
     par = tree.parent.tolist()
     el = tree.edge_length.tolist()
-    first = tree.first.tolist()
+    is_leaf = tree.is_leaf.tolist()
     depth = [0.0] * M          # max distance from node to an attached leaf below it
     attached = [True] * M      # node's own subtree part still attached to its parent
-    cut_roots = []             # nodes cut off (cluster = their still-attached leaves at cut time)
     kids = [[] for _ in range(M)]
-    owner = [-1] * M           # cluster root owning each node once cut
+    # still-attached leaves below each node as a singly linked list in left-to-right order (head, tail, next): joining
+    # the lists of the attached children is O(children), cutting a child off hands over its list -- O(M) overall, also on
+    # caterpillar backbones (a rescan of the id range [first[c], c] per cut is quadratic there)
+    head = [-1] * M
+    tail = [-1] * M
+    nxt = [-1] * M
     clusters = []
 
-    def collect(u):
-        # leaves of u's subtree that are not owned by an earlier cut
+    def take(c):
         out = []
-        c = first[u]
-        while c <= u:
-            if owner[c] >= 0:
-                # skip the whole earlier cluster piece rooted at owner-root? pieces are not contiguous in general,
-                # so test node by node
-                c += 1
-                continue
-            owner[c] = u
-            if tree.is_leaf[c]:
-                out.append(c)
-            c += 1
+        x = head[c]
+        while x >= 0:
+            out.append(x)
+            x = nxt[x]
         return out
 
     for u in range(M):
@@ -53,19 +49,27 @@ def max_diameter_clusters(tree, threshold):
             while len(cand) >= 2 and cand[-1][0] + cand[-2][0] > threshold:
                 _, c = cand.pop()
                 attached[c] = False
-                leaves = collect(c)
+                leaves = take(c)
                 if leaves:
                     clusters.append(leaves)
             if cand:
                 depth[u] = cand[-1][0]
+                for c in ch:                      # children in left-to-right order
+                    if attached[c] and head[c] >= 0:
+                        if head[u] < 0:
+                            head[u] = head[c]
+                        else:
+                            nxt[tail[u]] = head[c]
+                        tail[u] = tail[c]
             else:
                 # every child was cut: u has no attached leaf; drop it from its parent as an empty piece
                 attached[u] = False
-                owner[u] = u
+        elif is_leaf[u]:
+            head[u] = tail[u] = u
         kids[u] = None
         if p >= 0:
             kids[p].append(u)
-    rest = collect(M - 1)
+    rest = take(M - 1)
     if rest:
         clusters.append(rest)
     return clusters

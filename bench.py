@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def parse():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -45,7 +45,7 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--slot-cap', type=int, default=0, help='observed-list slots per query before a rerun (0 = library default)')
     ap.add_argument('--sub-batch', type=int, default=0, help='queries per dense/selection launch (0 = library default)')
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 class ClockSampler:
@@ -375,19 +375,40 @@ def main():
         tj = json.load(open(tpath))
         # dram bytes of one ncu --set full capture, scaled from the captured launch's pair count to this run's
         traffic = tj['dram_bytes'] * (q_per_launch * n_rep) / tj['pairs']
-    roofline = {'kernel': 'dense_nuc_kernel<false> (query x representative mismatch/valid counts)', 'bound': 'hbm',
-                'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak, 'traffic': traffic,
-                'peak_source': peak_src, 'avg_launch_ms': dense_ms, 'launches': n_dense,
-                'algorithmic_bytes_per_launch': alg_bytes,
-                'binding_resource': 'integer pipes (XU POPC / ALU LOP3), not HBM: see int_pipe',
-                'int_pipe': {'achieved': cs_rate / 1e12, 'unit': 'Tcell-sites/s',
-                             'peak': bal_peak / 1e12, 'frac': cs_rate / bal_peak,
-                             'peak_model': 'ALU/XU pipe-balanced optimum of the 3 LOP3 + 2 POPC per 32-site word pair '
-                                           'counting with carry-save steps (1 POPC <-> 2 LOP3): 148 SMs x 13.71 word '
-                                           'pairs/clk x %.0f MHz (max clock; observed %.0f MHz)' % (sm_max, sm_cur),
-                             'alu_peak_this_mix': alu_peak / 1e12, 'frac_of_alu_peak': cs_rate / alu_peak,
-                             'xu_peak_this_mix': xu_peak / 1e12, 'frac_of_xu_peak': cs_rate / xu_peak,
-                             'plain_popcount_peak': plain_peak / 1e12, 'frac_of_plain_popcount_peak': cs_rate / plain_peak}}
+    # top level = the BINDING resource of the dominant kernel (integer pipes); its HBM figures are nested under `hbm`
+    roofline = {'kernel': 'dense_nuc_kernel<false> (query x representative mismatch/valid counts)', 'bound': 'int_pipe',
+                'achieved': cs_rate / 1e12, 'peak': bal_peak / 1e12, 'unit': 'Tcell-sites/s', 'frac': cs_rate / bal_peak,
+                'traffic': traffic, 'avg_launch_ms': dense_ms, 'launches': n_dense,
+                'peak_model': 'no integer-pipe peak exists in MEASURED_PEAKS.json: peak = ALU/XU pipe-balanced optimum of '
+                              'the 3 LOP3 + 2 POPC per 32-site word pair counting with carry-save steps (1 POPC <-> 2 '
+                              'LOP3), LOP3 64 and POPC 16 lanes/clk/SM as measured by tools/microbench.cu '
+                              '(profiles/microbench_r02.txt): 148 SMs x 13.71 word pairs/clk x %.0f MHz (max clock; '
+                              'observed %.0f MHz)' % (sm_max, sm_cur),
+                'alu_peak_this_mix': alu_peak / 1e12, 'frac_of_alu_peak': cs_rate / alu_peak,
+                'xu_peak_this_mix': xu_peak / 1e12, 'frac_of_xu_peak': cs_rate / xu_peak,
+                'plain_popcount_peak': plain_peak / 1e12, 'frac_of_plain_popcount_peak': cs_rate / plain_peak,
+                'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                        'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes}}
+    # selection and placement kernels: per 125k-query step from the stage timers (CUDA events around their launches)
+    n_steps = args.steps
+    K_avg = tm['observed'] / (nq * n_steps)
+    V_avg = tm['valid_nodes'] / (nq * n_steps)
+    sel_ms = tm['selection_ms'] / n_steps
+    pla_ms = tm['placement_ms'] / n_steps
+    sel_bytes = nq * (4.0 * n_rep + K_avg * 3 * W * 4 + 16.0 * K_avg)     # key row + member rows + observed list
+    pla_bytes = nq * (12.0 * K_avg + 20.0 * V_avg + 36.0)
+    pla_flops = nq * 110.0 * V_avg
+    roofline_select = {'kernel': 'select_kernel<SEL_NUC> (all launches of a step incl. overflow reruns)', 'bound': 'hbm',
+                       'achieved': sel_bytes / (sel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                       'frac': sel_bytes / (sel_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'ms_per_step': sel_ms,
+                       'algorithmic_bytes_per_step': sel_bytes, 'peak_source': peak_src}
+    roofline_place = {'kernel': 'place_kernel (all launches of a step incl. overflow reruns)', 'bound': 'hbm',
+                      'achieved': pla_bytes / (pla_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                      'frac': pla_bytes / (pla_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'ms_per_step': pla_ms,
+                      'algorithmic_bytes_per_step': pla_bytes, 'peak_source': peak_src,
+                      'fp64_gflops': pla_flops / (pla_ms * 1e-3) / 1e9,
+                      'note': 'bound in practice by the dependency chain over tree levels (DESIGN.md 3b), neither by '
+                              'HBM nor by the fp64 pipe'}
     step_ms = ms / args.steps
     stages = {k: tm[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms')}
     line = {'metric': 'queries placed/sec', 'value': value, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps,
@@ -401,25 +422,39 @@ def main():
             'stage_ms_per_step': stages, 'rep_distance_sm_mhz': tm.get('rep_distance_sm_mhz'), 'per_rank': per_rank, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
             'observed_per_query': tm['observed'] / (nq * args.steps), 'valid_nodes_per_query': tm['valid_nodes'] / (nq * args.steps),
             'overflow_queries_per_step': tm['overflow_queries'] / args.steps, 'max_observed': tm['max_observed'],
-            'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'setup': info}
+            'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_select': roofline_select,
+            'roofline_place': roofline_place, 'setup': info}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----
     if not args.no_cpu_baseline and world == 1:
         n_sample = args.cpu_sample or max(threads * 8, 64)
-        q_host = q_bytes[:n_sample].cpu().numpy()
-        rate, dt, res = cpu_baseline(cpu_context(args, tree, host), q_host, threads)
-        # parity of the timed GPU results on that sample
+        # the sample is drawn across the whole batch and always holds queries of the overflow set (observed set larger
+        # than the slot: key-row stash, gather, rerun selection and placement)
         edge, error, distal, pendant, status = pl.download_results()
+        Kq, Vq, over = pl.last_counts(nq)
+        rng = np.random.default_rng(12345)
+        ov_idx = np.flatnonzero(over == 1)
+        n_ov = min(len(ov_idx), max(1, n_sample // 8))
+        pick = np.concatenate([rng.choice(ov_idx, n_ov, replace=False) if n_ov else np.zeros(0, np.int64),
+                               rng.choice(np.flatnonzero(over == 0), n_sample - n_ov, replace=False)]).astype(np.int64)
+        q_host = q_bytes[torch.from_numpy(pick).to(q_bytes.device)].cpu().numpy()
+        rate, dt, res = cpu_baseline(cpu_context(args, tree, host), q_host, threads)
+        # parity of the timed GPU results on that sample: edge identical, error / distal / pendant within 1e-9
+        def near(a, b, floor):
+            return abs(a - b) <= 1e-9 * max(abs(a), abs(b)) + floor
         same = 0
-        for i, r in enumerate(res):
+        for i, r in zip(pick.tolist(), res):
             p = r[0]['placements'][0]['p'][0]
-            if p[0] == int(edge[i]) and abs(p[1] - error[i]) <= 1e-9 * max(abs(p[1]), 1e-3):
+            pend = 0.0 if int(status[i]) & 0x100 else float(pendant[i])
+            if (p[0] == int(edge[i]) and near(p[1], float(error[i]), 1e-12) and near(p[3], float(distal[i]), 1e-15)
+                    and near(p[4], pend, 1e-15)):
                 same += 1
         line['cpu_baseline'] = {'value': rate, 'unit': 'queries/s', 'cores': threads, 'kind': 'port',
-                                'sample': '%d of this step\'s queries through the oracle port of '
-                                          'PoolQueryWorker.runquery under a fork pool of %d processes (%.1f s)'
-                                          % (n_sample, threads, dt),
-                                'parity_on_sample': '%d/%d identical edge and score within 1e-9' % (same, n_sample)}
+                                'sample': '%d of this step\'s queries, drawn across the batch (%d of them from the '
+                                          'overflow-rerun set), through the oracle port of PoolQueryWorker.runquery '
+                                          'under a fork pool of %d processes (%.1f s)' % (n_sample, n_ov, threads, dt),
+                                'parity_on_sample': '%d/%d identical edge; error, distal and pendant within 1e-9 '
+                                                    '(%d overflow-rerun queries in the sample)' % (same, n_sample, n_ov)}
     emit(line)
     if world > 1:
         dist.barrier()

@@ -48,6 +48,11 @@ typedef struct apples_ctx apples_ctx;
 #define APPLES_TOO_FEW_DISTANCES 2        /* <= 2 observed distances: edge = -1                         (:97-98)   */
 #define APPLES_PLACED_MISPLACEMENT_FLAG 3 /* placed, potential_misplacement_flag == 1                   (:121-130) */
 #define APPLES_FLAG_PENDANT_INT0 0x100    /* pendant is the Python int 0 (clipped), prints as 0 not 0.0 (util.py:34-47) */
+#define APPLES_FLAG_DEGENERATE 0x200      /* the 2x2 system of at least one edge of this query is singular in fp64
+                                           * (a_11 a_22 - a_12 a_21 == 0 or its reciprocal == 0): the reference raises
+                                           * ZeroDivisionError / AssertionError in util.solve2_2 (util.py:26-27) and the
+                                           * whole run dies; the other outputs of the query are then inf/nan arithmetic
+                                           * and carry no meaning.  apples_b200.placer.place_batch raises likewise. */
 
 typedef struct apples_params {
     int32_t method;                     /* -m  APPLES_FM|OLS|BME|BE                 (OptionsRun.py:26-33) */
@@ -61,6 +66,8 @@ typedef struct apples_params {
 int32_t apples_words_per_row(int32_t L); /* uint32 words per bit-plane row (multiple of 4) */
 int32_t apples_aa_row_bytes(int32_t L);  /* bytes per amino-acid code row (multiple of 16) */
 
+/* number of CUDA devices visible to the process (run_apples.py --gpus 0 = all of them, like -T 0 = all cores) */
+int apples_device_count(int32_t* count);
 int apples_ctx_create(int device, apples_ctx** out);
 void apples_ctx_destroy(apples_ctx* ctx);
 const char* apples_last_error(const apples_ctx* ctx);
@@ -140,6 +147,11 @@ int apples_observed_sets(apples_ctx* ctx, int64_t nq, const void* packed_queries
  * tree (arrays of M), valid[u] = 1 where the node is in the query's restricted subtree (Subtree.py:23-43). */
 int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const double* row, int32_t self_node,
                           const apples_params* params, double* x1, double* x2, double* err, uint8_t* valid);
+
+/* test seam: per-query counts of the LAST macro-batch placed through this context (at most 2^20 queries): K = observed
+ * leaves, V = valid nodes of the restricted subtree (Subtree.num_nodes, Subtree.py:42), overflowed = 1 where the query
+ * went through the overflow rerun (observed set larger than the slot capacity).  Any pointer may be NULL. */
+int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32_t* overflowed);
 
 /* accumulated device time per stage since the last call with reset != 0, in milliseconds (CUDA events):
  * [0] h2d  [1] transpose  [2] rep distance  [3] selection  [4] placement  [5] d2h  [6] launches (count)

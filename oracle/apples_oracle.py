@@ -306,7 +306,8 @@ def solve_edge(n, negative_branch):
     a22 = a11
     c1 = R[3] + S[3] - ln * S[0] - R[1] - S[1]
     c2 = R[3] - S[3] + ln * S[0] - R[1] + S[1]
-    det = 1 / (a11 * a22 - a12 * a21)
+    det = 1 / (a11 * a22 - a12 * a21)   # ZeroDivisionError on a singular system, like util.py:26
+    assert det != 0                      # util.py:27
     x1n = (a22 * c1 - a12 * c2) * det
     x2n = (-a21 * c1 + a11 * c2) * det
     x1, x2 = x1n, x2n
@@ -448,6 +449,26 @@ def run_pool(ctx, queries, num_thread):
     mpctx = mp.get_context('fork')
     with mpctx.Pool(num_thread) as pool:
         return pool.map(_pool_run, queries, chunksize=max(1, len(queries) // (num_thread * 4)))
+
+
+def _pool_run_detail(args):
+    det = {}
+    res, status = _CTX.runquery(*args, detail=det)
+    return res, status, {'observed': det.get('observed'), 'num_nodes': det.get('num_nodes')}
+
+
+def run_pool_detail(ctx, queries, num_thread):
+    """run_pool that also returns, per query, the status code and the observed set / valid-node count the placement saw
+    (for the parity tests at sizes where one process would take minutes)."""
+    global _CTX
+    import multiprocessing as mp
+    _CTX = ctx
+    queries = list(queries)
+    if num_thread <= 1:
+        return [_pool_run_detail(q) for q in queries]
+    mpctx = mp.get_context('fork')
+    with mpctx.Pool(num_thread) as pool:
+        return pool.map(_pool_run_detail, queries, chunksize=1)
 
 
 # ----------------------------------------------------------------------------------------------------------------

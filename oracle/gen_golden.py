@@ -9,8 +9,14 @@ What is the reference here and what is substituted:
   * `TreeCluster.py` (absent dependency) cannot run, so the cluster TSV is produced by apples_b200.treecluster and
     fed to the reference's own parsing + PoolRepresentativeWorker code (Reference.py:94-107), i.e. a
     ReducedReference instance is assembled without calling its __init__ (which would shell out).
-Floats are stored as float.hex() strings so the vectors are exact.  Inputs that are too large to commit (synthetic
-alignments) are regenerated from seeds by apples_b200.synth in the tests.
+Floats are stored as float.hex() strings so the vectors are exact.
+
+The INPUTS of every case are the committed fixtures under tests/golden/data/ (and tests/golden/c1_clusters*.tsv): the
+script reads them, it does not regenerate them, so the vectors stay pinned whatever apples_b200.synth or
+apples_b200.treecluster become.  `--regen-inputs` rebuilds the synthetic inputs (syn300*, prot_*) and the cluster TSVs
+from their seeds first (only when a fixture is to be replaced on purpose).  `--check` writes nothing: it regenerates
+every vector into a scratch directory and fails if any committed tests/golden/*.json would change
+(tests/test_oracle_golden.py::test_golden_recipe_reproduces_committed_vectors runs it where /root/reference exists).
 """
 import gzip
 import itertools
@@ -49,6 +55,7 @@ from apples_b200.tree import BackboneTree  # noqa: E402
 
 GOLD = os.path.join(ROOT, 'tests', 'golden')
 DATA = os.path.join(GOLD, 'data')
+OUT = GOLD   # --check redirects the vectors to a scratch directory
 REF_DATA = '/root/reference/data'
 ALGS = {'FM': FM, 'OLS': OLS, 'BME': BME, 'BE': BE}
 
@@ -168,7 +175,7 @@ def run_case(name, tree_fp, options, queries, reference=None, prot=False, detail
     assert bt.extended_newick() == ext_newick, name
     for lbl, node in name_to_node.items():
         assert bt.name_to_node[lbl] == node.edge_index and bt.level[node.edge_index] == node.level
-    with open(os.path.join(GOLD, name + '.json'), 'w') as f:
+    with open(os.path.join(OUT, name + '.json'), 'w') as f:
         json.dump(out, f, indent=0, sort_keys=True)
     print('wrote', name, len(out['queries']), 'queries')
     return out
@@ -221,11 +228,57 @@ def cluster_tsv_for(tree_fp, threshold, out_path):
     return bt
 
 
-def main():
-    os.makedirs(GOLD, exist_ok=True)
+def gunzip_to(name, workdir):
+    dst = os.path.join(workdir, name)
+    with gzip.open(os.path.join(DATA, name + '.gz'), 'rb') as fi, open(dst, 'wb') as fo:
+        fo.write(fi.read())
+    return dst
+
+
+def regen_inputs(tmp):
+    """Rebuilds the synthetic inputs and cluster TSVs from their seeds (replaces committed fixtures: on purpose only)."""
     copy_data()
+    tree_fp = os.path.join(REF_DATA, 'backbone.nwk')
+    cluster_tsv_for(tree_fp, 0.2, os.path.join(GOLD, 'c1_clusters.tsv'))
+    cluster_tsv_for(tree_fp, 0.45, os.path.join(GOLD, 'c1_clusters_f045.tsv'))
+    nwk = synth.random_tree(300, seed=11, polytomy_frac=0.15, zero_frac=0.05, neg_frac=0.03)
+    tfp = os.path.join(tmp, 'syn300.nwk')
+    open(tfp, 'w').write(nwk + '\n')
+    bt = BackboneTree.from_newick(tfp)
+    srefs, leaf_states = synth.evolve_alignment(bt, 600, seed=12)
+    sq, _ = synth.make_queries(bt, leaf_states, 40, seed=13)
+    cluster_tsv_for(tfp, 0.2, os.path.join(tmp, 'syn300.tsv'))
+    synth.write_fasta(srefs, os.path.join(tmp, 'syn300_ref.fa'))
+    synth.write_fasta(sq, os.path.join(tmp, 'syn300_query.fa'))
+    ptree = os.path.join(REF_DATA, 'prot', 'backbone.nwk')
+    pbt = BackboneTree.from_newick(ptree)
+    prefs, pstates = synth.evolve_alignment(pbt, 400, seed=21, protein=True)
+    pq, _ = synth.make_queries(pbt, pstates, 12, seed=22, protein=True)
+    cluster_tsv_for(ptree, 0.6, os.path.join(tmp, 'prot.tsv'))
+    synth.write_fasta(prefs, os.path.join(tmp, 'prot_ref.fa'))
+    synth.write_fasta(pq, os.path.join(tmp, 'prot_query.fa'))
+    for fn in ['syn300.nwk', 'syn300.tsv', 'syn300_ref.fa', 'syn300_query.fa', 'prot.tsv', 'prot_ref.fa', 'prot_query.fa']:
+        save_gz(os.path.join(tmp, fn), fn)
+
+
+def main(argv=None):
+    global OUT
+    argv = sys.argv[1:] if argv is None else argv
+    check = '--check' in argv
     tmp = '/tmp/apples_golden'
     os.makedirs(tmp, exist_ok=True)
+    if '--regen-inputs' in argv:
+        if check:
+            raise SystemExit('--check and --regen-inputs exclude each other')
+        regen_inputs(tmp)
+    if check:
+        OUT = os.path.join(tmp, 'check')
+        shutil.rmtree(OUT, ignore_errors=True)
+        os.makedirs(OUT)
+    # the reference's own example files must still be what the fixtures hold
+    for rel in ['ref.fa', 'query.fa', 'backbone.nwk', 'dist.mat', 'small_backbone.nwk', 'small_dist.mat', 'prot/backbone.nwk']:
+        with open(os.path.join(REF_DATA, rel), 'rb') as fi, gzip.open(os.path.join(DATA, rel.replace('/', '_') + '.gz'), 'rb') as fg:
+            assert fi.read() == fg.read(), 'fixture %s differs from the reference file' % rel
 
     # ---------------- small 5-leaf case: every method x criterion x negative (SURVEY 8c item 3)
     small_tree = os.path.join(REF_DATA, 'small_backbone.nwk')
@@ -244,11 +297,10 @@ def main():
     run_case('c2_matrix_BME_ME_b5', tree_fp, make_options(tree_fp, 'BME', 'ME', baseobs=5, filt=0.05), rows, detail_n=1)
     run_case('c2_matrix_BE_MLSE_neg', tree_fp, make_options(tree_fp, 'BE', 'MLSE', negative=True), rows, detail_n=1)
 
-    # ---------------- config 1: data/ref.fa + query.fa, clusters from the in-repo clustering
+    # ---------------- config 1: data/ref.fa + query.fa, clusters from the committed TSV (TreeCluster.py is absent)
     refs = ref_fasta2dic(os.path.join(REF_DATA, 'ref.fa'), False, False)
     queries = ref_fasta2dic(os.path.join(REF_DATA, 'query.fa'), False, False)
     tsv = os.path.join(GOLD, 'c1_clusters.tsv')
-    cluster_tsv_for(tree_fp, 0.2, tsv)
     rr = reference_reduced(refs, False, tsv, 0.2, 25)
     qlist = [(k, v, None) for k, v in queries.items()]
     # raw counts for every query x reference pair (distance.py:733-737) -- pins kernel (a) bit-exactly
@@ -267,7 +319,6 @@ def main():
     run_case('c1_align_BME_HYBRID', tree_fp, make_options(tree_fp, 'BME', 'HYBRID'), qlist, rr, detail_n=1)
     run_case('c1_align_BE_ME', tree_fp, make_options(tree_fp, 'BE', 'ME'), qlist, rr, detail_n=1)
     tsv45 = os.path.join(GOLD, 'c1_clusters_f045.tsv')
-    cluster_tsv_for(tree_fp, 0.45, tsv45)
     rr45 = reference_reduced(refs, False, tsv45, 0.45, 5)
     run_case('c1_align_FM_MLSE_f045_b5', tree_fp, make_options(tree_fp, baseobs=5, filt=0.45), qlist, rr45, detail_n=1)
     # a reference sequence used as a query under its own name (PoolQueryWorker.py:63-70) and a copy under a new name
@@ -282,20 +333,12 @@ def main():
     run_case('c1_align_special', tree_fp, make_options(tree_fp), special, rr, detail_n=4)
     run_case('c1_align_special_exclude', tree_fp, make_options(tree_fp, exclude=True), special + qlist[:3], rr, detail_n=0)
 
-    # ---------------- synthetic nucleotide with polytomies, zero and negative edges
-    nwk = synth.random_tree(300, seed=11, polytomy_frac=0.15, zero_frac=0.05, neg_frac=0.03)
-    tfp = os.path.join(tmp, 'syn300.nwk')
-    open(tfp, 'w').write(nwk + '\n')
-    bt = BackboneTree.from_newick(tfp)
-    srefs, leaf_states = synth.evolve_alignment(bt, 600, seed=12)
-    sq, _ = synth.make_queries(bt, leaf_states, 40, seed=13)
-    stsv = os.path.join(tmp, 'syn300.tsv')
-    cluster_tsv_for(tfp, 0.2, stsv)
+    # ---------------- synthetic nucleotide with polytomies, zero and negative edges (committed fixture inputs)
+    tfp = gunzip_to('syn300.nwk', tmp)
+    srefs = ref_fasta2dic(gunzip_to('syn300_ref.fa', tmp), False, False)
+    sq = ref_fasta2dic(gunzip_to('syn300_query.fa', tmp), False, False)
+    stsv = gunzip_to('syn300.tsv', tmp)
     sql = [(k, v, None) for k, v in sq.items()]
-    synth.write_fasta(srefs, os.path.join(tmp, 'syn300_ref.fa'))
-    synth.write_fasta(sq, os.path.join(tmp, 'syn300_query.fa'))
-    for fn in ['syn300.nwk', 'syn300.tsv', 'syn300_ref.fa', 'syn300_query.fa']:
-        save_gz(os.path.join(tmp, fn), fn)
     gen = {'generator': {'tree': dict(n_leaves=300, seed=11, polytomy_frac=0.15, zero_frac=0.05, neg_frac=0.03),
                          'L': 600, 'aln_seed': 12, 'n_queries': 40, 'q_seed': 13, 'cluster_threshold': 0.2}}
     for m in ['FM', 'OLS', 'BME', 'BE']:
@@ -307,24 +350,31 @@ def main():
 
     # ---------------- protein: the reference's real 4038-leaf tree (polytomies, negative edges), synthetic alignment
     ptree = os.path.join(REF_DATA, 'prot', 'backbone.nwk')
-    pbt = BackboneTree.from_newick(ptree)
-    prefs, pstates = synth.evolve_alignment(pbt, 400, seed=21, protein=True)
-    pq, _ = synth.make_queries(pbt, pstates, 12, seed=22, protein=True)
-    ptsv = os.path.join(tmp, 'prot.tsv')
-    cluster_tsv_for(ptree, 0.6, ptsv)
+    prefs = ref_fasta2dic(gunzip_to('prot_ref.fa', tmp), True, False)
+    pq = ref_fasta2dic(gunzip_to('prot_query.fa', tmp), True, False)
+    ptsv = gunzip_to('prot.tsv', tmp)
     pgen = {'generator': {'L': 400, 'aln_seed': 21, 'n_queries': 12, 'q_seed': 22, 'cluster_threshold': 0.6}}
     prr = reference_reduced(prefs, True, ptsv, 0.6, 25)
     pql = [(k, v, None) for k, v in pq.items()]
-    synth.write_fasta(prefs, os.path.join(tmp, 'prot_ref.fa'))
-    synth.write_fasta(pq, os.path.join(tmp, 'prot_query.fa'))
-    for fn in ['prot.tsv', 'prot_ref.fa', 'prot_query.fa']:
-        save_gz(os.path.join(tmp, fn), fn)
     # scoredist values for query 0 against the first 64 references (1e-9 parity target, BLAS summation order)
     pn = list(prefs.keys())[:64]
     sd = [hx(ref_distance.scoredist(pql[0][1], prefs[n], 0.001)) for n in pn]
     pgen['scoredist_q0'] = {'refs': pn, 'd': sd}
     run_case('c3_prot_FM_MLSE', ptree, make_options(ptree, filt=0.6), pql, prr, prot=True, detail_n=1, extra=pgen)
     run_case('c3_prot_OLS_MLSE', ptree, make_options(ptree, 'OLS', filt=0.6), pql, prr, prot=True, detail_n=1, extra=pgen)
+
+    if check:
+        committed = sorted(f for f in os.listdir(GOLD) if f.endswith('.json'))
+        made = sorted(os.listdir(OUT))
+        bad = [f for f in committed if f not in made]
+        bad += [f for f in made if f not in committed]
+        for f in made:
+            if f in committed and open(os.path.join(OUT, f), 'rb').read() != open(os.path.join(GOLD, f), 'rb').read():
+                bad.append(f)
+        if bad:
+            print('golden vectors that would change:', ' '.join(sorted(set(bad))))
+            raise SystemExit(1)
+        print('check ok: %d committed golden vectors are reproduced byte for byte by the unmodified reference' % len(made))
 
 
 if __name__ == '__main__':

@@ -5,6 +5,7 @@ Same options, inputs and jplace output as the reference's run_apples.py; the one
 `pool.starmap(queryworker.runquery, queries)` (reference run_apples.py:94-102) -> apples_b200.placer.place_batch.
 """
 import logging
+import os
 import pickle
 import re
 import sys
@@ -13,7 +14,7 @@ import time
 from apples_b200 import jplace
 from apples_b200.fasta import fasta2dic
 from apples_b200.options import options_config_run
-from apples_b200.placer import place_batch
+from apples_b200.placer import place_batch, visible_devices
 from apples_b200.reference import ReducedReference
 from apples_b200.tree import prepare_tree
 
@@ -32,13 +33,39 @@ def main(argv=None):
     logging.info('[%s] Options are parsed.' % time.strftime('%H:%M:%S'))
     tree = name_to_node_map = extended_newick_string = None
     up = fdtb = None
+    # One process per GPU under torchrun (WORLD_SIZE > 1): every rank places its block of queries on its own GPU, the
+    # blocks are exchanged with one NCCL all-gather and rank 0 writes the output.  Otherwise the queries are sharded
+    # over --gpus devices inside this process (0 = all visible: the analogue of upstream's -T 0 = all cores).
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = 0
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get('LOCAL_RANK', '0'))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group('nccl', device_id=torch.device('cuda:%d' % local))
+        else:
+            dist.init_process_group('gloo')
+        rank = dist.get_rank()
+        devices = [local]
+    else:
+        devices = visible_devices(options.device, options.num_gpus)
     if options.database_fp:
         start = time.time()
         fdtb = open(options.database_fp, 'rb')
         up = pickle.Unpickler(fdtb)
-        tree = up.load()
-        name_to_node_map = up.load()
-        extended_newick_string = up.load()
+        try:
+            tree = up.load()
+            name_to_node_map = up.load()
+            extended_newick_string = up.load()
+        except (ModuleNotFoundError, AttributeError) as e:
+            # upstream databases pickle treeswift.Tree / apples.Reference objects, which this build does not contain
+            raise SystemExit('%s is not a database written by this build\'s build_applesdtb.py (%s); databases pickled '
+                             'by upstream APPLES hold treeswift / apples.* objects and cannot be loaded here: rebuild it '
+                             'with build_applesdtb.py' % (options.database_fp, e))
+        if not hasattr(tree, 'parent') or not hasattr(tree, 'first'):
+            raise SystemExit('%s does not hold a tree written by this build\'s build_applesdtb.py' % options.database_fp)
         logging.info('[%s] Tree is loaded from APPLES database in %.3f seconds.' % (time.strftime('%H:%M:%S'),
                                                                                    time.time() - start))
     if options.tree_fp:
@@ -57,7 +84,11 @@ def main(argv=None):
             logging.info('[%s] Reduced reference is computed in %.3f seconds.' % (time.strftime('%H:%M:%S'),
                                                                                   time.time() - start))
         else:
-            reference = up.load()
+            try:
+                reference = up.load()
+            except (ModuleNotFoundError, AttributeError) as e:
+                raise SystemExit('%s: the reduced reference was not pickled by this build (%s); rebuild the database with '
+                                 'build_applesdtb.py' % (options.database_fp, e))
             fdtb.close()
             logging.info('[%s] Reduced reference is loaded from APPLES database in %.3f seconds.'
                          % (time.strftime('%H:%M:%S'), time.time() - start))
@@ -72,11 +103,16 @@ def main(argv=None):
     logging.info('[%s] Query sequences are prepared in %.3f seconds.' % (time.strftime('%H:%M:%S'), time.time() - start))
 
     startq = time.time()
-    results = place_batch(reference, options, name_to_node_map, queries, tree=tree, device=options.device)
-    logging.info('[%s] Processed all queries in %.3f seconds.' % (time.strftime('%H:%M:%S'), time.time() - startq))
-
-    jplace.write(jplace.assemble(results, extended_newick_string), options.output_fp)
-    logging.warning('[%s] APPLES finished in %.3f seconds.' % (time.strftime('%H:%M:%S'), time.time() - startb))
+    results = place_batch(reference, options, name_to_node_map, queries, tree=tree, devices=devices)
+    logging.info('[%s] Processed all queries in %.3f seconds on %d GPU(s).' % (time.strftime('%H:%M:%S'),
+                                                                               time.time() - startq, max(world, len(devices))))
+    if rank == 0:
+        jplace.write(jplace.assemble(results, extended_newick_string), options.output_fp)
+        logging.warning('[%s] APPLES finished in %.3f seconds.' % (time.strftime('%H:%M:%S'), time.time() - startb))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -76,3 +76,82 @@ def test_cli_protein(workdir):
     out = os.path.join(workdir, 'c3.jplace')
     run_apples.main(['-s', ref, '-q', qry, '-t', tree, '-p', '-f', '0.6', '-b', '25', '-D', '--clusters', tsv, '-o', out])
     _check_jplace(out, 'c3_prot_FM_MLSE', workdir, 'prot_backbone.nwk')
+
+
+def test_database_threshold_comes_from_the_database(workdir):
+    """with `-a database` the cluster-expansion threshold is the one stored in the reference object at build
+    time (Reference.py:146 uses self.threshold), whatever -f the run is given: a database built with -f 0.45 and run
+    with the default -f reproduces the reference's `-f 0.45` observed sets."""
+    import run_apples
+    import build_applesdtb
+    ref, qry, tree = (util.gunzip_to(n, workdir) for n in ('ref.fa', 'query.fa', 'backbone.nwk'))
+    tsv45 = os.path.join(util.GOLD, 'c1_clusters_f045.tsv')
+    dtb = os.path.join(workdir, 'apples_f045.dtb')
+    build_applesdtb.main(['-s', ref, '-t', tree, '-D', '-f', '0.45', '--clusters', tsv45, '-o', dtb])
+    out = os.path.join(workdir, 'c1_f045.jplace')
+    run_apples.main(['-a', dtb, '-q', qry, '-b', '5', '-o', out])          # run-time -f left at its default 0.2
+    _check_jplace(out, 'c1_align_FM_MLSE_f045_b5', workdir, 'backbone.nwk')
+    # a pickle that is not one of this build's databases is refused with a clear message
+    bogus = os.path.join(workdir, 'bogus.dtb')
+    with open(bogus, 'wb') as f:
+        pickle.dump({'not': 'a tree'}, f)
+    with pytest.raises(SystemExit):
+        run_apples.main(['-a', bogus, '-q', qry, '-o', out])
+
+
+def _n_gpus():
+    from apples_b200 import _lib
+    return _lib.device_count()
+
+
+def test_multi_gpu_result_is_byte_identical(workdir):
+    """queries sharded over N GPUs (one context and one host thread per GPU, in-process) give result
+    arrays BYTE-IDENTICAL to the single-GPU arrays for the same queries; same for the jplace dicts of place_batch."""
+    import types
+    import numpy as np
+    from apples_b200 import _lib, fasta
+    from apples_b200.placer import GpuPlacer, MultiGpuPlacer, place_batch
+    from tests.test_gpu_parity import _synthetic
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    nwk, tree, refs, ref, queries, _ = _synthetic(4000, 1500, 9001, 700, workdir)
+    ref.set_baseobs(25)
+    names = list(queries.keys())
+    mat = fasta.as_byte_matrix([queries[k] for k in names], 1500)
+    params = _lib.make_params('FM', 'MLSE')
+    one = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+    a = one.place_bytes(mat, None, params)
+    one.close()
+    for g in sorted({2, n}):
+        multi = MultiGpuPlacer(tree, ref, tree.name_to_node, devices=list(range(g)))
+        b = multi.place_bytes(mat, None, params)
+        multi.close()
+        for x, y in zip(a, b):
+            assert x.tobytes() == y.tobytes(), g
+    opt = types.SimpleNamespace(method_name='OLS', criterion_name='MLSE', negative_branch=False,
+                                base_observation_threshold=25, filt_threshold=0.2, minimum_alignment_overlap=0.001,
+                                exclude_intplace=False)
+    qlist = [(k, queries[k], None) for k in names[:777]]
+    r1 = place_batch(ref, opt, tree.name_to_node, qlist, tree=tree, device=0)
+    r2 = place_batch(ref, opt, tree.name_to_node, qlist, tree=tree, devices=list(range(n)))
+    assert json.dumps(r1) == json.dumps(r2)
+
+
+def test_torchrun_cli_equals_single_process(workdir):
+    """run_apples.py under torchrun (one process per GPU, NCCL all-gather of 32-byte records, rank 0 writes) produces
+    the same jplace file as the single-process run."""
+    import subprocess
+    import sys
+    if _n_gpus() < 2:
+        pytest.skip('needs at least 2 GPUs')
+    ref, qry, tree = (util.gunzip_to(n, workdir) for n in ('ref.fa', 'query.fa', 'backbone.nwk'))
+    tsv = os.path.join(util.GOLD, 'c1_clusters.tsv')
+    out1, out2 = os.path.join(workdir, 'tr1.jplace'), os.path.join(workdir, 'tr2.jplace')
+    base = ['-s', ref, '-q', qry, '-t', tree, '-D', '--clusters', tsv]
+    subprocess.run([sys.executable, os.path.join(util.ROOT, 'run_apples.py')] + base + ['-o', out1, '--gpus', '1'], check=True)
+    subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                    '127.0.0.1', '--master-port', '29733', os.path.join(util.ROOT, 'run_apples.py')] + base + ['-o', out2],
+                   check=True, timeout=600)
+    assert open(out1).read() == open(out2).read()
+    _check_jplace(out2, 'c1_align_FM_MLSE', workdir, 'backbone.nwk')

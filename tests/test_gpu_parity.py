@@ -577,7 +577,7 @@ def test_randomized_differential_matrix_mode(workdir):
     from oracle import apples_oracle as orc
     from apples_b200.placer import place_batch
     rng = np.random.default_rng(20240917)
-    n_checked = 0
+    n_checked = n_degenerate = 0
     for case in range(300):
         tfp, tree, queries = _random_matrix_case(rng, workdir, case)
         method = str(rng.choice(['FM', 'OLS', 'BME', 'BE']))
@@ -588,15 +588,31 @@ def test_randomized_differential_matrix_mode(workdir):
         opt = types.SimpleNamespace(method_name=method, criterion_name=criterion, negative_branch=neg,
                                     base_observation_threshold=b, filt_threshold=f, minimum_alignment_overlap=0.001,
                                     exclude_intplace=bool(rng.random() < 0.3))
-        res = place_batch(None, opt, tree.name_to_node, queries, tree=tree, device=0)
         otree, onames = orc.load_tree(tfp)
         octx = orc.OracleContext(otree, onames, method=method, criterion=criterion, negative_branch=neg,
                                  filt_threshold=f, baseobs=b, exclude_intplace=opt.exclude_intplace)
+        # singular 2x2 systems: the reference raises in util.solve2_2 (util.py:26-27) and the run dies; place_batch
+        # raises ZeroDivisionError exactly for the batches in which the reference does (APPLES_FLAG_DEGENERATE)
+        ref_raises = False
+        for q in queries:
+            try:
+                octx.runquery(q[0], None, dict(q[2]))
+            except (ZeroDivisionError, AssertionError):
+                ref_raises = True
+            except (FloatingPointError, OverflowError):
+                pass
+        try:
+            res = place_batch(None, opt, tree.name_to_node, queries, tree=tree, device=0)
+            assert not ref_raises, ('the reference raises on a singular system, place_batch did not', case)
+        except ZeroDivisionError:
+            assert ref_raises, ('place_batch raised on a system the reference solves', case)
+            n_degenerate += 1
+            continue
         for q, r in zip(queries, res):
             try:
                 exp, st = octx.runquery(q[0], None, dict(q[2]))
-            except (ZeroDivisionError, FloatingPointError, OverflowError):
-                continue  # the reference itself raises here (1 / 0.0 in util.solve2_2): nothing to compare
+            except (FloatingPointError, OverflowError):
+                continue  # Python-level overflow in the reference: nothing to compare
             g, e = r['placements'][0]['p'][0], exp['placements'][0]['p'][0]
             ctx = (case, q[0], method, criterion, neg, b, f, g, e)
             assert r['placements'][0]['n'] == exp['placements'][0]['n'], ctx
@@ -664,7 +680,7 @@ def test_randomized_differential_alignment_mode(workdir):
         packed = pl.pack_queries([q[1] for q in queries])
         out = pl.place_packed(packed, sn, params)
         count, node, dist = pl.observed_sets(params, packed=packed, self_node=sn, cap=256)
-        res = results_to_jplace(qn, [x in tree.name_to_node for x in qn], out, log=False)
+        res = results_to_jplace(qn, [x in tree.name_to_node for x in qn], out, log=False, degenerate='keep')
         pl.close()
         otree, onames = orc.load_tree(tfp)
         octx = orc.OracleContext(otree, onames, refs=refs, representatives=orc.representatives_from_tsv(tsv, refs, protein),
@@ -673,11 +689,15 @@ def test_randomized_differential_alignment_mode(workdir):
                                  overlap=opt.minimum_alignment_overlap)
         for qi, (q, r) in enumerate(zip(queries, res)):
             det = {}
+            ctx = (case, q[0], protein, vars(opt))
             try:
                 exp, st = octx.runquery(q[0], q[1], None, detail=det)
-            except (ZeroDivisionError, FloatingPointError, OverflowError):
+            except (ZeroDivisionError, AssertionError):
+                assert int(out[4][qi]) & 0x200, ('the reference raises on a singular system, no APPLES_FLAG_DEGENERATE', ctx)
                 continue
-            ctx = (case, q[0], protein, vars(opt))
+            except (FloatingPointError, OverflowError):
+                continue
+            assert not (int(out[4][qi]) & 0x200), ('APPLES_FLAG_DEGENERATE on a system the reference solves', ctx)
             eobs = {tree.name_to_node[k]: v for k, v in det['observed']}
             assert int(count[qi]) == len(eobs), ctx
             if st in (0, 3):
@@ -693,3 +713,58 @@ def test_randomized_differential_alignment_mode(workdir):
                 ties += 1
             checked += 1
     assert checked > 500 and ties <= 5, (checked, ties)
+
+
+def test_config5_parity_including_overflow_reruns(workdir):
+    """BASELINE.json config 5 at full reference size (the bench workload: 200 000-leaf backbone, 5000 sites, 21 924
+    representatives, FM + MLSE, -f 0.2 -b 25): 20 480 queries through apples_place_batch_bytes, then a seeded sample of
+    64 ordinary queries plus 16 queries from the OVERFLOW set (observed set larger than the 256-entry slot: stash of the
+    key row, gather, rerun selection with the larger slot, rerun placement) against the oracle: status, edge, error,
+    distal, pendant, the observed set (leaves identical, distances 1e-9) and the number of valid nodes V
+    (Reference.py:143-154, PoolQueryWorker.py:101-120)."""
+    import bench
+    from oracle import apples_oracle as orc
+    from apples_b200 import _lib
+    from apples_b200.placer import GpuPlacer
+    args = bench.parse([])
+    args.queries_per_gpu = 20480
+    tree, arrays, packed_q, q_bytes, info, host = bench.build_workload(args, 'cuda:0', 0, True)
+    nq = args.queries_per_gpu
+    pl = GpuPlacer(tree, None, tree.name_to_node, device=0)
+    pl.set_reference_arrays(**arrays)
+    params = _lib.make_params('FM', 'MLSE')
+    q_host = q_bytes.cpu().numpy()
+    packed_host = packed_q.cpu().numpy().view(np.uint32)
+    edge, error, distal, pendant, status = pl.place_bytes(q_host, None, params)
+    K, V, over = pl.last_counts(nq)
+    assert over.sum() >= 16, 'the workload is expected to hold ~1 %% overflow queries, saw %d' % over.sum()
+    assert (K[over == 1] > 256).all() and (K[over == 0] <= 256).all()
+    rng = np.random.default_rng(5)
+    sample = np.concatenate([rng.choice(np.flatnonzero(over == 0), 64, replace=False),
+                             rng.choice(np.flatnonzero(over == 1), 16, replace=False)])
+    # the sample's observed sets through the same pipeline (slot capacity 256: the 16 are rerun here as well)
+    count, node, dist = pl.observed_sets(params, packed=np.ascontiguousarray(packed_host[sample]), cap=4096)
+    K2, V2, over2 = pl.last_counts(len(sample))
+    assert (over2 == over[sample]).all() and (K2 == K[sample]).all() and (V2 == V[sample]).all() and (count == K2).all()
+    octx = bench.cpu_context(args, tree, host)
+    queries = [('Q%07d' % i, q_host[i].view('S1'), None) for i in sample.tolist()]
+    exp = orc.run_pool_detail(octx, queries, os.cpu_count() or 1)
+    ties = 0
+    for j, (i, q, (res, st, det)) in enumerate(zip(sample.tolist(), queries, exp)):
+        assert (int(status[i]) & 0xff) == st, (i, status[i], st)
+        eobs = {tree.name_to_node[k]: v for k, v in det['observed']}
+        assert int(K[i]) == len(eobs), (i, K[i], len(eobs))
+        p = res['placements'][0]['p'][0]
+        if st in (1, 2):
+            assert st != 1 or int(edge[i]) == p[0]
+            continue
+        k = int(count[j])
+        assert node[j, :k].tolist() == sorted(eobs), i
+        for u, d in zip(node[j, :k].tolist(), dist[j, :k].tolist()):
+            assert util.close(d, eobs[u], REL, 0.0), (i, u, d, eobs[u])
+        assert int(V[i]) == det['num_nodes'], (i, V[i], det['num_nodes'])
+        got = [int(edge[i]), float(error[i]), 1, float(distal[i]), 0 if status[i] & 0x100 else float(pendant[i])]
+        if _check_p('c5', q[0], got, p, False, octx, q) == 'tie':
+            ties += 1
+    assert ties <= 2
+    pl.close()

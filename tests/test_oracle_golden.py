@@ -99,3 +99,18 @@ def test_alignment_and_matrix_agree():
     b = util.load_golden('c2_matrix_FM_MLSE')
     # (scores differ slightly: the observed sets are cut at different ties, SURVEY.md section 7 "hard parts")
     assert [q['p'][0] for q in a['queries']] == [q['p'][0] for q in b['queries']]
+
+
+def test_golden_recipe_reproduces_committed_vectors():
+    """oracle/gen_golden.py --check: the committed recipe, fed with the committed input fixtures and run against the
+    UNMODIFIED reference, regenerates every tests/golden/*.json byte for byte (and asserts oracle == reference bit for
+    bit on the way).  Catches drift between recipe, fixtures and oracle; runs only where /root/reference exists."""
+    import os
+    import subprocess
+    import sys
+    if not os.path.isdir('/root/reference/apples'):
+        pytest.skip('/root/reference is not present on this box')
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, 'oracle', 'gen_golden.py'), '--check'],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert 'check ok' in r.stdout

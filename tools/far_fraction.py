@@ -7,7 +7,7 @@ import bench
 from apples_b200 import _lib
 from apples_b200.placer import GpuPlacer
 
-args = bench.parse()
+args = bench.parse(sys.argv[1:])
 args.queries_per_gpu = 4096
 tree, arrays, packed_q, q_bytes, info, host = bench.build_workload(args, 'cuda:0', 0, False)
 pl = GpuPlacer(tree, None, tree.name_to_node, device=0)
