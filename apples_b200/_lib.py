@@ -25,6 +25,9 @@ SYMBOLS = [
     'apples_ctx_stream', 'apples_ctx_set_limits', 'apples_set_tree', 'apples_set_reference', 'apples_set_matrix_columns', 'apples_place_batch',
     'apples_place_batch_matrix', 'apples_set_reference_bytes', 'apples_place_batch_bytes', 'apples_queries_upload', 'apples_place_resident', 'apples_results_download', 'apples_results_to_device',
     'apples_distance_counts', 'apples_observed_sets', 'apples_edge_solutions', 'apples_get_timings', 'apples_last_counts',
+    'apples_fasta_open', 'apples_fasta_close', 'apples_fasta_count', 'apples_fasta_max_len', 'apples_fasta_stride',
+    'apples_fasta_uniform', 'apples_fasta_pinned', 'apples_fasta_matrix', 'apples_fasta_lengths', 'apples_fasta_names',
+    'apples_fasta_name_offsets', 'apples_jplace_write',
 ]
 
 
@@ -76,6 +79,20 @@ def load():
     lib.apples_edge_solutions.argtypes = [vp, vp, vp, i32, C.POINTER(Params), vp, vp, vp, vp]
     lib.apples_get_timings.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.apples_last_counts.argtypes = [vp, i64, vp, vp, vp]
+    lib.apples_fasta_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]
+    lib.apples_fasta_close.argtypes = [vp]
+    lib.apples_fasta_close.restype = None
+    for fn in ('count', 'max_len', 'stride'):
+        getattr(lib, 'apples_fasta_' + fn).argtypes = [vp]
+        getattr(lib, 'apples_fasta_' + fn).restype = i64
+    for fn in ('uniform', 'pinned'):
+        getattr(lib, 'apples_fasta_' + fn).argtypes = [vp]
+        getattr(lib, 'apples_fasta_' + fn).restype = C.c_int
+    for fn in ('matrix', 'lengths', 'names', 'name_offsets'):
+        getattr(lib, 'apples_fasta_' + fn).argtypes = [vp]
+        getattr(lib, 'apples_fasta_' + fn).restype = vp
+    lib.apples_jplace_write.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
+                                        C.c_int, C.POINTER(i64), C.c_char_p, C.c_int]
     _lib = lib
     return lib
 

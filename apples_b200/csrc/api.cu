@@ -49,7 +49,7 @@ struct apples_ctx {
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
     DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
-    DevBuf obs_node2, obs_dist2, qlist, rec_off, stack_off, recs, stacks;
+    DevBuf obs_node2, obs_dist2, qlist, pl_lists, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
     // resident queries
@@ -70,6 +70,8 @@ struct apples_ctx {
     std::vector<int> h_first;      // host copy of first[]: node u is a leaf iff first[u] == u
     std::vector<int> h_ref_node, h_col_node;  // re-validated when the tree changes
     std::vector<long long> h_rec_off, h_stack_off;
+    std::vector<int> h_pl_lists;
+    double n_place_class[PLACE_NCLASS] = {0, 0, 0, 0, 0};
     std::vector<char> h_gather;
     int slot_cap = 256;
 };
@@ -289,8 +291,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         ensure(ctx, ctx->o_distal, (size_t)n * 8) || ensure(ctx, ctx->o_pendant, (size_t)n * 8) ||
         ensure(ctx, ctx->o_status, (size_t)n * 4))
         return -1;
-    if (ensure(ctx, ctx->rec_off, (size_t)n * 8) || ensure(ctx, ctx->stack_off, (size_t)n * 8) ||
-        ensure(ctx, ctx->qlist, (size_t)std::max(n, 1) * 4))
+    if (ensure(ctx, ctx->rec_off, (size_t)(n + 1) * 8) || ensure(ctx, ctx->stack_off, (size_t)(n + 1) * 8) ||
+        ensure(ctx, ctx->qlist, (size_t)std::max(n, 1) * 4) || ensure(ctx, ctx->pl_lists, (size_t)std::max(n, 1) * 8))
         return -1;
     CK(cudaMemsetAsync(ctx->pair_counter.p, 0, 8, s));
     const bool dbg = io.dbg_x1 != nullptr;
@@ -318,7 +320,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     std::vector<int>& hK = ctx->hK; std::vector<int>& hV = ctx->hV; std::vector<int>& hS = ctx->hS;
     hK.resize(n); hV.resize(n); hS.resize(n);
     std::vector<long long>& h_rec_off = ctx->h_rec_off; std::vector<long long>& h_stack_off = ctx->h_stack_off;
-    h_rec_off.resize(n); h_stack_off.resize(n);
+    h_rec_off.resize(n + 1); h_stack_off.resize(n + 1);
     const NucGate gate = make_gate(ctx->L, prm->filt_threshold, prm->overlap_frac);
 
     SelectArgs sa{};
@@ -495,58 +497,94 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     pa.dbg_err = (double*)ctx->dbg_err.p;
     pa.dbg_valid = (unsigned char*)ctx->dbg_valid.p;
 
-    // placement of `cnt` launch entries (entry i -> query id(i)); chunks bounded by the scratch pool
-    auto place_entries = [&](int cnt, auto id, auto active, const int* d_qlist, int capx, const int* on, const double* od,
+    // placement of `cnt` candidate entries (entry i -> query id(i), observed lists in row slot(i) of the given buffers;
+    // slot == nullptr: row = query id).  The PLACE-status queries are sorted into launch classes by their node count:
+    // four shared-memory launches (V + 1 <= 64 / 128 / 256 / 512) and one block-per-query launch with global scratch, chunked
+    // if the scratch pool would be exceeded.
+    auto place_entries = [&](int cnt, auto id, auto active, bool entry_slots, int capx, const int* on, const double* od,
                              const int* ol) -> int {
-        int i0 = 0;
-        while (i0 < cnt) {
+        std::vector<int>& L = ctx->h_pl_lists;
+        L.clear();
+        int begin[PLACE_NCLASS + 1];
+        // pass 1: class sizes; pass 2: fill (query ids first, then the slot rows in the second half of the buffer)
+        int sizes[PLACE_NCLASS] = {0, 0, 0, 0, 0};
+        auto cls_of = [&](int qi) {
+            const int v = hV[qi] + 1;  // + 1: pseudo record of the subtree root
+            return v <= 64 ? PLACE_CLASS_64 : v <= 128 ? PLACE_CLASS_128 : v <= 256 ? PLACE_CLASS_256 : v <= 512 ? PLACE_CLASS_512 : PLACE_CLASS_BLOCK;
+        };
+        for (int i = 0; i < cnt; ++i) {
+            const int qi = id(i);
+            if (hS[qi] == ST_PLACE && active(qi)) sizes[cls_of(qi)]++;
+        }
+        begin[0] = 0;
+        for (int c = 0; c < PLACE_NCLASS; ++c) begin[c + 1] = begin[c] + sizes[c];
+        const int total = begin[PLACE_NCLASS];
+        if (total == 0) return 0;
+        L.resize((size_t)2 * total);
+        int fill[PLACE_NCLASS];
+        for (int c = 0; c < PLACE_NCLASS; ++c) fill[c] = begin[c];
+        for (int i = 0; i < cnt; ++i) {
+            const int qi = id(i);
+            if (hS[qi] != ST_PLACE || !active(qi)) continue;
+            const int pos = fill[cls_of(qi)]++;
+            L[pos] = qi;
+            L[(size_t)total + pos] = i;
+        }
+        if (ensure(ctx, ctx->pl_lists, (size_t)2 * total * 4)) return -1;
+        CK(cudaMemcpyAsync(ctx->pl_lists.p, L.data(), (size_t)(entry_slots ? 2 : 1) * total * 4, cudaMemcpyHostToDevice, s));
+        const int* d_q = (const int*)ctx->pl_lists.p;
+        const int* d_slot = entry_slots ? d_q + total : nullptr;
+        pa.cap = capx;
+        pa.obs_node = on;
+        pa.obs_dist = od;
+        pa.obs_len = ol;
+        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
+            if (!sizes[c]) continue;
+            pa.n = sizes[c];
+            pa.qlist = d_q + begin[c];
+            pa.slot_list = d_slot ? d_slot + begin[c] : nullptr;
+            Span sp(ctx, T_PLACE);
+            CK(launch_place(prm->method, c, pa, s));
+            ctx->n_launch += 1;
+            ctx->n_place_class[c] += sizes[c];
+        }
+        // block-per-query class: exact scratch regions, chunked by the pool limit
+        int i0 = begin[PLACE_CLASS_BLOCK];
+        const int iend = begin[PLACE_NCLASS];
+        ctx->n_place_class[PLACE_CLASS_BLOCK] += iend - i0;
+        while (i0 < iend) {
             long long recs = 0, stk = 0;
             int i1 = i0;
-            while (i1 < cnt) {
-                const int qi = id(i1);
-                const bool act = hS[qi] == ST_PLACE && active(qi);
-                const long long v = act ? hV[qi] + 1 : 0, k = act ? hK[qi] : 0;  // + 1: pseudo record of the subtree root
-                if (i1 > i0 && (size_t)(recs + v) * sizeof(NodeRec) > ctx->scratch_limit) break;
-                // -1: observed set lives in the other pass's buffers (the kernel skips the entry)
-                h_rec_off[i1] = (hS[qi] == ST_PLACE && !act) ? -1 : recs;
-                h_stack_off[i1] = stk;
+            while (i1 < iend) {
+                const int qi = L[i1];
+                const long long v = hV[qi] + 1, k = hK[qi];
+                if (i1 > i0 && (size_t)(recs + v) * PLACE_NODE_SLOT_BYTES > ctx->scratch_limit) break;
+                h_rec_off[i1 - i0] = recs;
+                h_stack_off[i1 - i0] = stk;
                 recs += v;
                 stk += k;
                 ++i1;
             }
-            if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * sizeof(NodeRec))) return -1;
-            if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * sizeof(StackEnt))) return -1;
-            CK(cudaMemcpyAsync((long long*)ctx->rec_off.p + i0, h_rec_off.data() + i0, (size_t)(i1 - i0) * 8,
-                               cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync((long long*)ctx->stack_off.p + i0, h_stack_off.data() + i0, (size_t)(i1 - i0) * 8,
-                               cudaMemcpyHostToDevice, s));
+            h_rec_off[i1 - i0] = recs;
+            h_stack_off[i1 - i0] = stk;
+            if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * PLACE_NODE_SLOT_BYTES)) return -1;
+            if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * PLACE_CHAIN_SLOT_BYTES)) return -1;
+            CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
             pa.n = i1 - i0;
-            pa.rec_off = (const long long*)ctx->rec_off.p + i0;
-            pa.stack_off = (const long long*)ctx->stack_off.p + i0;
-            pa.recs = (NodeRec*)ctx->recs.p;
-            pa.stacks = (StackEnt*)ctx->stacks.p;
-            pa.cap = capx;
-            if (d_qlist) {
-                pa.qlist = d_qlist + i0;
-                pa.q_begin = 0;
-                pa.obs_node = on + (size_t)i0 * capx;
-                pa.obs_dist = od + (size_t)i0 * capx;
-                pa.obs_len = ol + (size_t)i0 * capx;
-            } else {
-                pa.qlist = nullptr;
-                pa.q_begin = i0;
-                pa.obs_node = on;
-                pa.obs_dist = od;
-                pa.obs_len = ol;
-            }
+            pa.qlist = d_q + i0;
+            pa.slot_list = d_slot ? d_slot + i0 : nullptr;
+            pa.rec_off = (const long long*)ctx->rec_off.p;
+            pa.stack_off = (const long long*)ctx->stack_off.p;
+            pa.recs = ctx->recs.p;
+            pa.stacks = ctx->stacks.p;
             {
                 Span sp(ctx, T_PLACE);
-                launch_place(prm->method, pa, s);
+                CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, s));
                 ctx->n_launch += 1;
             }
-            CK(cudaGetLastError());
             i0 = i1;
-            if (i0 < cnt) CK(cudaStreamSynchronize(s));  // the scratch pool is reused by the next chunk
+            if (i0 < iend) CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused by the next chunk
         }
         return 0;
     };
@@ -635,7 +673,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             }
             if (!io.stop_after_select) {
                 const int* ov = over.data() + o0;
-                if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, (const int*)ctx->qlist.p, cap2,
+                if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, true, cap2,
                                   (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
                     return -1;
                 CK(cudaStreamSynchronize(s));
@@ -672,9 +710,15 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
     if (!io.stop_after_select) {
         // ---------------- phase 3 ----------------
-        if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, nullptr, cap,
+        if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, false, cap,
                           (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p, (const int*)ctx->obs_len.p))
             return -1;
+        {   // zero-distance shortcut / too-few-distances records of the whole batch
+            Span sp(ctx, T_PLACE);
+            pa.n = n;
+            CK(launch_place_finalize(pa, s));
+            ctx->n_launch += 1;
+        }
         // ---------------- phase 4 ----------------
         {
             Span sp(ctx, T_D2H);
@@ -777,7 +821,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -1168,13 +1212,15 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
     if (!ctx || !out) return -1;
-    double v[15] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+    double v[20] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
                     ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid,
-                    ctx->n_over, ctx->max_K, ctx->max_V, ctx->dense_mhz};
-    for (int i = 0; i < n && i < 15; ++i) out[i] = v[i];
+                    ctx->n_over, ctx->max_K, ctx->max_V, ctx->dense_mhz, ctx->n_place_class[0], ctx->n_place_class[1],
+                    ctx->n_place_class[2], ctx->n_place_class[3], ctx->n_place_class[4]};
+    for (int i = 0; i < n && i < 20; ++i) out[i] = v[i];
     if (reset) {
         for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
         ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = ctx->n_over = ctx->max_K = ctx->max_V = 0;
+        for (int c = 0; c < PLACE_NCLASS; ++c) ctx->n_place_class[c] = 0;
     }
     return 0;
 }

@@ -126,41 +126,27 @@ struct SelectArgs {
     TreeDev tree;
 };
 
-struct alignas(16) NodeRec {
-    double S[6];
-    double R[6];
-    double len;
-    int orig;
-    int fchild;
-    int rsib;
-    int nchild;
-    int par;   // compact index of the parent (V = the subtree root)
-    int pad_;
-};
-static_assert(sizeof(NodeRec) == 128, "NodeRec must be 128 bytes");
-
-struct StackEnt {
-    int A;
-    int first;
-    int last;
-    int n;
-};
+// placement launch classes: working set in shared memory for up to 64 / 128 / 256 / 512 node slots (V + 1), else one
+// block per query with the working set in the global scratch pool
+enum { PLACE_CLASS_64 = 0, PLACE_CLASS_128 = 1, PLACE_CLASS_256 = 2, PLACE_CLASS_512 = 3, PLACE_CLASS_BLOCK = 4, PLACE_NCLASS = 5 };
+constexpr int PLACE_NODE_SLOT_BYTES = 128;   // global scratch per node slot (13 doubles + 5 ints = 124 bytes used)
+constexpr int PLACE_CHAIN_SLOT_BYTES = 16;   // global scratch per chain (4 ints)
 
 struct PlaceArgs {
-    int n;                 // entries in this launch
-    const int* qlist;      // slot -> query index (NULL = identity) for obs buffers
-    int q_begin;           // first query index of the launch when qlist == NULL
-    int cap;
+    int n;                 // entries in this launch (finalize: queries of the batch)
+    const int* qlist;      // launch entry -> query index inside the batch
+    const int* slot_list;  // launch entry -> row of the observed-list buffers (NULL: the query index)
+    int cap;               // slots per row of the observed-list buffers
     const int* obs_node;
     const double* obs_dist;
     const int* obs_len;
     const int* K;
     const int* status;
     const int* zero_edge;
-    const long long* rec_off;    // per launch entry: first NodeRec of the query's scratch
-    const long long* stack_off;  // per launch entry: first StackEnt
-    NodeRec* recs;
-    StackEnt* stacks;
+    const long long* rec_off;    // PLACE_CLASS_BLOCK: n + 1 offsets into the node-slot pool
+    const long long* stack_off;  // PLACE_CLASS_BLOCK: n + 1 offsets into the chain-slot pool
+    void* recs;
+    void* stacks;
     int criterion;
     int negative_branch;
     TreeDev tree;
@@ -169,7 +155,7 @@ struct PlaceArgs {
     double* out_distal;
     double* out_pendant;
     int* out_status;
-    // optional per-edge export for one query (index inside the sub-batch), arrays of M
+    // optional per-edge export for one query (index inside the batch), arrays of M
     int dbg_query;
     double* dbg_x1;
     double* dbg_x2;
@@ -190,7 +176,8 @@ void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad
 void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
                      int64_t ldd, uint32_t* valid_out, cudaStream_t s);
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
-void launch_place(int method, const PlaceArgs& a, cudaStream_t s);
+cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s);
+cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s);
 cudaError_t dense_nuc_configure();
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad, cudaStream_t s);
 cudaError_t launch_gather_rows(const void* src, const int* idx, void* dst, int n, size_t row_bytes, cudaStream_t s);

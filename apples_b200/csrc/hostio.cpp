@@ -1,0 +1,442 @@
+// Host side of SURVEY.md section 8 (f1) and (f3) in native code, behind the C ABI (include/apples_b200.h):
+//
+//   apples_fasta_*   FASTA / FASTQ -> one byte matrix [n][stride] (pinned host memory when a CUDA device is there), with
+//                    the record semantics and alphabet normalisation of apples/fasta2dic.py:4-72 (readfq + fasta2dic):
+//                    name = header up to the first blank, multi-line sequences, optional '+' quality block, sequences
+//                    upper-cased (or lower-case masked to '-' with -X), letters outside the alphabet -> '-'.
+//                    The matrix is what apples_place_batch_bytes / apples_set_reference_bytes take.
+//   apples_jplace_write   result arrays -> the jplace text `json.dumps(result, sort_keys=True, indent=4)` writes for the
+//                    joined per-query records (run_apples.py:106-118, jutil.py:1-19), byte for byte: Python float repr,
+//                    ensure_ascii string escapes, the "first record is kept even when unplaceable" quirk of join_jplace.
+//
+// Both are multi-threaded (std::thread): at config 5 the queries are 5 GB of text and a million records.  No CUDA kernel
+// is involved; cudaHostAlloc is used only to make the matrix directly DMA-able.
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cuda_runtime.h>
+
+#include "../../include/apples_b200.h"
+
+struct apples_fasta {
+    int64_t n = 0, max_len = 0, stride = 0;
+    bool uniform = true;
+    bool pinned = false;
+    uint8_t* matrix = nullptr;
+    std::vector<int64_t> lengths;
+    std::string names;               // NUL-terminated names, concatenated
+    std::vector<int64_t> name_off;   // n + 1 offsets into `names`
+    std::string err;
+};
+
+namespace {
+
+struct Rec {
+    const char* name;   // header text after '>' / '@'
+    int64_t name_len;
+    const char* seq;    // first sequence line
+    const char* seq_end;  // end of the sequence block (start of the next header / '+' line / EOF)
+    int64_t len = 0;    // residues (line breaks removed)
+};
+
+inline const char* line_end(const char* p, const char* end) {
+    const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+    return q ? q : end;
+}
+
+// strip the line terminator the way the Python twin does (rstrip('\r\n'))
+inline const char* rstrip_crlf(const char* b, const char* e) {
+    while (e > b && (e[-1] == '\n' || e[-1] == '\r')) --e;
+    return e;
+}
+
+void set_err(char* err, int errlen, const std::string& msg) {
+    if (err && errlen > 0) {
+        snprintf(err, (size_t)errlen, "%s", msg.c_str());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int apples_fasta_open(const char* path, int prot_flag, int mask_flag, int n_threads, int want_pinned, apples_fasta** out,
+                      char* err, int errlen) {
+    if (!out || !path) return -1;
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) {
+        set_err(err, errlen, std::string("cannot open ") + path);
+        return -2;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+        close(fd);
+        set_err(err, errlen, "fstat failed");
+        return -2;
+    }
+    const size_t size = (size_t)st.st_size;
+    const char* data = nullptr;
+    if (size) {
+        data = (const char*)mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (data == MAP_FAILED) {
+            close(fd);
+            set_err(err, errlen, "mmap failed");
+            return -2;
+        }
+        madvise((void*)data, size, MADV_SEQUENTIAL);
+    }
+    close(fd);
+    const char* end = data + size;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = std::min(n_threads, 64);
+
+    // ---- pass 1 (sequential over LINES' first characters, cheap): record boundaries with readfq's state machine
+    // (fasta2dic.py:4-39): a header is a line starting with '>' or '@' where a header is expected; inside a sequence
+    // block a line starting with '@', '+' or '>' ends it; a '+' line starts a quality block that is skipped until it is
+    // at least as long as the sequence.
+    std::vector<Rec> recs;
+    {
+        const char* p = data;
+        // state: looking for a header
+        while (p < end) {
+            const char* le = line_end(p, end);
+            if (le > p && (*p == '>' || *p == '@')) {
+                Rec r;
+                const char* hb = p + 1;
+                const char* he = rstrip_crlf(hb, le);
+                const char* sp = (const char*)memchr(hb, ' ', (size_t)(he - hb));
+                r.name = hb;
+                r.name_len = (sp ? sp : he) - hb;
+                p = le < end ? le + 1 : end;
+                r.seq = p;
+                // sequence lines until a line starting with '@', '+' or '>'
+                int64_t len = 0;
+                bool plus = false;
+                while (p < end) {
+                    const char* e2 = line_end(p, end);
+                    if (e2 > p && (*p == '>' || *p == '@' || *p == '+')) {
+                        plus = *p == '+';
+                        break;
+                    }
+                    len += rstrip_crlf(p, e2) - p;
+                    p = e2 < end ? e2 + 1 : end;
+                }
+                r.seq_end = p;
+                r.len = len;
+                recs.push_back(r);
+                if (plus) {
+                    // quality block: skip the '+' line, then lines until their total length reaches the sequence length
+                    const char* e2 = line_end(p, end);
+                    p = e2 < end ? e2 + 1 : end;
+                    int64_t got = 0;
+                    while (p < end && got < len) {
+                        const char* e3 = line_end(p, end);
+                        got += rstrip_crlf(p, e3) - p;
+                        p = e3 < end ? e3 + 1 : end;
+                    }
+                }
+            } else {
+                p = le < end ? le + 1 : end;   // text before the first header / between records is ignored
+            }
+        }
+    }
+
+    apples_fasta* f = new apples_fasta();
+    f->n = (int64_t)recs.size();
+    f->lengths.resize(recs.size());
+    f->name_off.resize(recs.size() + 1);
+    int64_t max_len = 0, min_len = INT64_MAX, name_bytes = 0;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        f->lengths[i] = recs[i].len;
+        max_len = std::max(max_len, recs[i].len);
+        min_len = std::min(min_len, recs[i].len);
+        f->name_off[i] = name_bytes;
+        name_bytes += recs[i].name_len + 1;
+    }
+    f->name_off[recs.size()] = name_bytes;
+    f->names.resize((size_t)name_bytes);
+    for (size_t i = 0; i < recs.size(); ++i) {
+        memcpy(&f->names[(size_t)f->name_off[i]], recs[i].name, (size_t)recs[i].name_len);
+        f->names[(size_t)f->name_off[i] + (size_t)recs[i].name_len] = '\0';
+    }
+    f->max_len = max_len;
+    f->uniform = recs.empty() || min_len == max_len;
+    f->stride = (max_len + 15) / 16 * 16;
+    const size_t bytes = std::max<size_t>((size_t)f->n * (size_t)f->stride, 16);
+    if (want_pinned && cudaHostAlloc((void**)&f->matrix, bytes, cudaHostAllocDefault) == cudaSuccess) {
+        f->pinned = true;
+    } else {
+        cudaGetLastError();   // no device / no driver: plain memory
+        f->matrix = (uint8_t*)malloc(bytes);
+        if (!f->matrix) {
+            delete f;
+            if (size) munmap((void*)data, size);
+            set_err(err, errlen, "out of memory");
+            return -3;
+        }
+    }
+
+    // ---- pass 2 (parallel): normalise and copy.  fasta2dic.py:52-72: upper() or lower-case -> '-' (mask), then the
+    // letters outside the alphabet -> '-'.  Every other byte is kept as it is.
+    uint8_t tab[256];
+    for (int c = 0; c < 256; ++c) tab[c] = (uint8_t)c;
+    for (int c = 'a'; c <= 'z'; ++c) tab[c] = mask_flag ? (uint8_t)'-' : (uint8_t)(c - 32);
+    const char* invalid = prot_flag ? "BJOUXZ" : "BDEFHIJKLMNOPQRSUVWXYZ";
+    for (const char* q = invalid; *q; ++q) {
+        tab[(unsigned char)*q] = '-';
+        if (!mask_flag) tab[(unsigned char)(*q + 32)] = '-';   // upper() first, then the translation
+    }
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        const size_t chunk = 256;
+        for (;;) {
+            const size_t b = next.fetch_add(chunk);
+            if (b >= recs.size()) break;
+            const size_t e = std::min(recs.size(), b + chunk);
+            for (size_t i = b; i < e; ++i) {
+                uint8_t* dst = f->matrix + i * (size_t)f->stride;
+                int64_t k = 0;
+                const char* p = recs[i].seq;
+                const char* se = recs[i].seq_end;
+                while (p < se) {
+                    const char* le = line_end(p, se);
+                    const char* te = rstrip_crlf(p, le);
+                    for (const char* c = p; c < te; ++c) dst[k++] = tab[(unsigned char)*c];
+                    p = le < se ? le + 1 : se;
+                }
+                for (; k < f->stride; ++k) dst[k] = '-';
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    if (size) munmap((void*)data, size);
+    *out = f;
+    return 0;
+}
+
+void apples_fasta_close(apples_fasta* f) {
+    if (!f) return;
+    if (f->matrix) {
+        if (f->pinned) cudaFreeHost(f->matrix); else free(f->matrix);
+    }
+    delete f;
+}
+
+int64_t apples_fasta_count(const apples_fasta* f) { return f ? f->n : 0; }
+int64_t apples_fasta_max_len(const apples_fasta* f) { return f ? f->max_len : 0; }
+int64_t apples_fasta_stride(const apples_fasta* f) { return f ? f->stride : 0; }
+int apples_fasta_uniform(const apples_fasta* f) { return f && f->uniform ? 1 : 0; }
+int apples_fasta_pinned(const apples_fasta* f) { return f && f->pinned ? 1 : 0; }
+const uint8_t* apples_fasta_matrix(const apples_fasta* f) { return f ? f->matrix : nullptr; }
+const int64_t* apples_fasta_lengths(const apples_fasta* f) { return f ? f->lengths.data() : nullptr; }
+const char* apples_fasta_names(const apples_fasta* f) { return f ? f->names.data() : nullptr; }
+const int64_t* apples_fasta_name_offsets(const apples_fasta* f) { return f ? f->name_off.data() : nullptr; }
+
+}  // extern "C"
+
+// =================================================================================================================
+// jplace writer
+// =================================================================================================================
+namespace {
+
+// float.__repr__ (Python 3: shortest round-trip digits; fixed notation for 1e-4 <= |x| < 1e16, else exponent with at
+// least two exponent digits; ".0" appended to integral values in fixed notation)
+void py_float_repr(double x, std::string& out) {
+    if (std::isnan(x)) { out += "NaN"; return; }            // json.dumps spelling
+    if (std::isinf(x)) { out += x > 0 ? "Infinity" : "-Infinity"; return; }
+    if (x == 0.0) { out += std::signbit(x) ? "-0.0" : "0.0"; return; }
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, x, std::chars_format::scientific);   // shortest: d[.ddd]e[+-]XX
+    const char* p = buf;
+    if (*p == '-') { out += '-'; ++p; }
+    char digits[32];
+    int nd = 0;
+    const char* e = p;
+    while (e < r.ptr && *e != 'e') {
+        if (*e != '.') digits[nd++] = *e;
+        ++e;
+    }
+    int exp10 = 0;
+    std::from_chars(e + 1 + (e[1] == '+' ? 1 : 0), r.ptr, exp10);
+    const int decpt = exp10 + 1;   // position of the decimal point relative to the first digit
+    if (decpt > 16 || decpt < -3) {
+        out += digits[0];
+        if (nd > 1) {
+            out += '.';
+            out.append(digits + 1, (size_t)(nd - 1));
+        }
+        out += 'e';
+        const int ex = decpt - 1;
+        out += ex < 0 ? '-' : '+';
+        const int ax = ex < 0 ? -ex : ex;
+        if (ax < 10) out += '0';
+        out += std::to_string(ax);
+    } else if (decpt <= 0) {
+        out += "0.";
+        out.append((size_t)(-decpt), '0');
+        out.append(digits, (size_t)nd);
+    } else if (decpt >= nd) {
+        out.append(digits, (size_t)nd);
+        out.append((size_t)(decpt - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, (size_t)decpt);
+        out += '.';
+        out.append(digits + decpt, (size_t)(nd - decpt));
+    }
+}
+
+// json.encoder.encode_basestring_ascii of a UTF-8 string (quotes included); returns false on invalid UTF-8
+bool json_escape_ascii(const char* s, size_t n, const char* suffix, std::string& out) {
+    static const char* hex = "0123456789abcdef";
+    auto put_u = [&](unsigned cp) {
+        out += "\\u";
+        out += hex[(cp >> 12) & 15]; out += hex[(cp >> 8) & 15]; out += hex[(cp >> 4) & 15]; out += hex[cp & 15];
+    };
+    out += '"';
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char c = (unsigned char)s[i];
+        if (c < 0x80) {
+            switch (c) {
+                case '"': out += "\\\""; break;
+                case '\\': out += "\\\\"; break;
+                case '\n': out += "\\n"; break;
+                case '\r': out += "\\r"; break;
+                case '\t': out += "\\t"; break;
+                case '\b': out += "\\b"; break;
+                case '\f': out += "\\f"; break;
+                default:
+                    if (c < 0x20 || c == 0x7f) put_u(c); else out += (char)c;
+            }
+            ++i;
+            continue;
+        }
+        const int extra = (c & 0xe0) == 0xc0 ? 1 : (c & 0xf0) == 0xe0 ? 2 : (c & 0xf8) == 0xf0 ? 3 : -1;
+        if (extra < 0 || i + (size_t)extra >= n) return false;
+        unsigned cp = extra == 1 ? (c & 0x1fu) : extra == 2 ? (c & 0x0fu) : (c & 0x07u);
+        for (int k = 1; k <= extra; ++k) {
+            const unsigned char cc = (unsigned char)s[i + (size_t)k];
+            if ((cc & 0xc0) != 0x80) return false;
+            cp = (cp << 6) | (cc & 0x3fu);
+        }
+        i += (size_t)extra + 1;
+        if (cp >= 0x10000) {
+            cp -= 0x10000;
+            put_u(0xd800 + (cp >> 10));
+            put_u(0xdc00 + (cp & 0x3ff));
+        } else {
+            put_u(cp);
+        }
+    }
+    for (const char* q = suffix; q && *q; ++q) out += *q;
+    out += '"';
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apples_jplace_write(const char* path, const char* prefix, const char* suffix, int64_t n, const char* names,
+                        const int64_t* name_off, const uint8_t* in_backbone, const int32_t* edge, const double* error,
+                        const double* distal, const double* pendant, const int32_t* status, int exclude_intplace,
+                        int n_threads, int64_t* n_written, char* err, int errlen) {
+    if (!path || !prefix || !suffix || n < 0 || (n > 0 && (!names || !name_off || !edge || !error || !distal || !pendant || !status)))
+        return -1;
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(n_threads, 64), (n + 4095) / 4096));
+    // which records are written (jutil.py:11-19): a single result is dropped when its edge is -1; of several, the first
+    // is always kept and later ones with edge -1 are dropped
+    auto final_edge = [&](int64_t i) -> int32_t {
+        const int code = status[i] & APPLES_STATUS_CODE_MASK;
+        if (code == APPLES_TOO_FEW_DISTANCES) return -1;
+        if (code == APPLES_PLACED_MISPLACEMENT_FLAG && exclude_intplace) return -1;
+        return edge[i];
+    };
+    std::vector<std::string> parts((size_t)n_threads);
+    std::vector<int64_t> counts((size_t)n_threads, 0);
+    std::atomic<int> bad(0);
+    const int64_t per = (n + n_threads - 1) / std::max(n_threads, 1);
+    auto work = [&](int t) {
+        std::string& out = parts[(size_t)t];
+        const int64_t b = (int64_t)t * per, e = std::min<int64_t>(n, b + per);
+        out.reserve((size_t)std::max<int64_t>(0, e - b) * 330);
+        for (int64_t i = b; i < e; ++i) {
+            const int32_t fe = final_edge(i);
+            if (fe == -1 && (n == 1 || i > 0)) continue;
+            const int code = status[i] & APPLES_STATUS_CODE_MASK;
+            out += counts[(size_t)t] || t > 0 ? ",\n" : "";
+            out += "        {\n            \"n\": [\n                ";
+            const char* nm = names + name_off[i];
+            if (!json_escape_ascii(nm, strlen(nm), (in_backbone && in_backbone[i]) ? "-query" : nullptr, out)) bad.store(1);
+            out += "\n            ],\n            \"p\": [\n                [\n                    ";
+            out += std::to_string(fe);
+            out += ",\n                    ";
+            const bool plain = code == APPLES_ZERO_DIST_LEAF || code == APPLES_TOO_FEW_DISTANCES;
+            if (plain) out += '0'; else py_float_repr(error[i], out);
+            out += ",\n                    1,\n                    ";
+            if (plain) out += '0'; else py_float_repr(distal[i], out);
+            out += ",\n                    ";
+            if (plain || (status[i] & APPLES_FLAG_PENDANT_INT0)) out += '0'; else py_float_repr(pendant[i], out);
+            out += "\n                ]\n            ]\n        }";
+            counts[(size_t)t]++;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < n_threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& t : th) t.join();
+    if (bad.load()) {
+        set_err(err, errlen, "a query name is not valid UTF-8");
+        return -4;
+    }
+    // chunks other than the first started with ",\n" unconditionally: drop it where nothing precedes
+    int64_t total = 0;
+    FILE* fp = fopen(path, "wb");
+    if (!fp) {
+        set_err(err, errlen, std::string("cannot open ") + path + " for writing");
+        return -2;
+    }
+    bool ok = fwrite(prefix, 1, strlen(prefix), fp) == strlen(prefix);
+    int64_t kept = 0;
+    for (int t = 0; t < n_threads; ++t) kept += counts[(size_t)t];
+    if (ok) ok = fputs(kept ? "[\n" : "[", fp) >= 0;   // json.dumps(indent=4): an empty list is "[]"
+    bool any = false;
+    for (int t = 0; t < n_threads && ok; ++t) {
+        const std::string& s = parts[(size_t)t];
+        if (s.empty()) continue;
+        size_t skip = (!any && t > 0 && s.size() >= 2 && s[0] == ',' && s[1] == '\n') ? 2 : 0;
+        ok = fwrite(s.data() + skip, 1, s.size() - skip, fp) == s.size() - skip;
+        any = true;
+        total += counts[(size_t)t];
+    }
+    if (ok) ok = fputs(kept ? "\n    ]" : "]", fp) >= 0;
+    if (ok) ok = fwrite(suffix, 1, strlen(suffix), fp) == strlen(suffix);
+    if (fclose(fp) != 0) ok = false;
+    if (!ok) {
+        set_err(err, errlen, "write failed");
+        return -2;
+    }
+    if (n_written) *n_written = total;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,4 +1,4 @@
-// Kernel (b): least-squares placement over every edge of the query's restricted backbone, one WARP per query.
+// Kernel (b): least-squares placement over every edge of the query's restricted backbone.
 //
 // Replaces, per query: Subtree (apples/Subtree.py:23-70), Algorithm.dp_frag (apples/Algorithm.py:16-21) with
 // FM/OLS/BME/BE all_S_values + all_R_values (FM.py:6-76, OLS.py:12-80, BME.py:6-60, BE.py:6-57),
@@ -12,9 +12,18 @@
 // index, and the attach level of a chain (level of the node above its top) describes the whole topology:
 //   * the node a chain hangs from lives on the next chain to the right with a strictly smaller attach level,
 //   * chains hanging from the same node are consecutive "next smaller-or-equal" neighbours, in child order.
-// Lanes work on chains / nodes in parallel: chain discovery and linking, then the S moments level by level from the
-// deepest level up, the R moments level by level down, then every edge is solved in closed form and the criterion
-// argmin is a warp-shuffle reduction (first minimum in post-order wins, like Python's min()).
+// A cooperating group of threads works on chains / nodes in parallel: chain discovery and linking, then the S moments
+// bucket by bucket from the deepest attach level up, the R moments from the shallowest down, then every edge is solved
+// in closed form and the criterion argmin is a reduction (first minimum in post-order wins, like Python's min()).
+//
+// Two instantiations of the same code:
+//   * WARP + SHARED MEMORY (queries with V + 1 <= 64 / 128 / 256 / 512 node slots, 99 % of a batch): one warp per query, the
+//     per-node records (S[6], R[6], edge length, links) and the chain table live in SHARED memory as structure-of-arrays,
+//     sized by the class of the launch -- nothing but the observed list is read from and nothing but the 32-byte
+//     result is written to global memory (round 1 kept 128-byte records in a global scratch pool: 12x the algorithmic
+//     traffic and a DRAM round trip on every dependent step);
+//   * BLOCK + GLOBAL MEMORY (the few queries with hundreds to thousands of observed leaves): one 256-thread block per
+//     query, records in a global scratch region sized exactly from the counts the selection kernel returned.
 //
 // One template for the four weightings: moment vector m[6] = sums over leaves of
 //   [w, w d, w d^2, w D, w D d, w D^2]      d = path length, D = observed distance,
@@ -25,13 +34,8 @@
 #include "common.cuh"
 
 #define FULLMASK 0xffffffffu
-#ifndef PL_HIST_V
-#define PL_HIST_V 512
-#endif
-#ifndef PL_MINBLOCKS
-#define PL_MINBLOCKS 1
-#endif
-constexpr int PL_HIST = PL_HIST_V;  // attach-level buckets per warp in shared memory
+constexpr int PL_HIST = 256;          // attach-level buckets per query in shared memory (deeper: level-sweep fallback)
+constexpr int PL_BLOCK_THREADS = 256; // threads per query of the global-memory instantiation
 
 __device__ __forceinline__ void leaf_moments(int method, double D, double* m) {
     m[1] = 0.0; m[2] = 0.0; m[4] = 0.0;
@@ -116,232 +120,354 @@ __device__ __forceinline__ EdgeSol solve_edge(const double* S, const double* R, 
     return e;
 }
 
-// lexicographic (value, index) minimum over the warp; lanes without a candidate pass idx = INT_MAX
-__device__ __forceinline__ void warp_argmin(double& val, int& idx) {
+// ---------------------------------------------------------------------------------------------------------------
+// cooperation policies: a warp (shuffles) or a whole block (shared-memory scratch + __syncthreads)
+// ---------------------------------------------------------------------------------------------------------------
+struct WarpCoop {
+    static constexpr int G = 32;
+    __device__ static int lane() { return threadIdx.x & 31; }
+    __device__ static void sync() { __syncwarp(); }
+    // inclusive prefix sum over the group; `total` = sum over the group
+    __device__ static int scan(int v, int& total) {
+        const int l = lane();
+        int incl = v;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(FULLMASK, val, o);
-        const int oi = __shfl_xor_sync(FULLMASK, idx, o);
-        const bool take = (oi != 0x7fffffff) && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx));
-        if (take) { val = ov; idx = oi; }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULLMASK, incl, o);
+            if (l >= o) incl += t;
+        }
+        total = __shfl_sync(FULLMASK, incl, 31);
+        return incl;
     }
+    __device__ static int max_all(int v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULLMASK, v, o));
+        return v;
+    }
+    __device__ static bool any(bool p) { return __any_sync(FULLMASK, p) != 0; }
+    // lexicographic (value, index) minimum; members without a candidate pass idx = INT_MAX
+    __device__ static void argmin(double& val, int& idx) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULLMASK, val, o);
+            const int oi = __shfl_xor_sync(FULLMASK, idx, o);
+            const bool take = (oi != 0x7fffffff) && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx));
+            if (take) { val = ov; idx = oi; }
+        }
+    }
+};
+
+struct BlockCoop {
+    static constexpr int G = PL_BLOCK_THREADS;
+    __device__ static int lane() { return threadIdx.x; }
+    __device__ static void sync() { __syncthreads(); }
+    __device__ static int* scratch_i() { __shared__ int s[PL_BLOCK_THREADS / 32 + 1]; return s; }
+    __device__ static double* scratch_d() { __shared__ double s[PL_BLOCK_THREADS / 32]; return s; }
+    __device__ static int scan(int v, int& total) {
+        int* s = scratch_i();
+        const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int wt;
+        const int incl = WarpCoop::scan(v, wt);
+        __syncthreads();
+        if (l == 31) s[w] = wt;
+        __syncthreads();
+        int before = 0, tot = 0;
+#pragma unroll
+        for (int i = 0; i < PL_BLOCK_THREADS / 32; ++i) {
+            const int x = s[i];
+            if (i < w) before += x;
+            tot += x;
+        }
+        total = tot;
+        return incl + before;
+    }
+    __device__ static int max_all(int v) {
+        int* s = scratch_i();
+        v = WarpCoop::max_all(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int m = s[0];
+#pragma unroll
+        for (int i = 1; i < PL_BLOCK_THREADS / 32; ++i) m = max(m, s[i]);
+        return m;
+    }
+    __device__ static bool any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+    __device__ static void argmin(double& val, int& idx) {
+        int* si = scratch_i();
+        double* sd = scratch_d();
+        WarpCoop::argmin(val, idx);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { si[threadIdx.x >> 5] = idx; sd[threadIdx.x >> 5] = val; }
+        __syncthreads();
+        val = sd[0];
+        idx = si[0];
+#pragma unroll
+        for (int i = 1; i < PL_BLOCK_THREADS / 32; ++i) {
+            const double ov = sd[i];
+            const int oi = si[i];
+            const bool take = (oi != 0x7fffffff) && (idx == 0x7fffffff || ov < val || (ov == val && oi < idx));
+            if (take) { val = ov; idx = oi; }
+        }
+    }
+};
+
+// per-query working set as structure-of-arrays over `cap` node slots (V valid nodes + 1 pseudo record for the subtree
+// root, the MRCA) and `kcap` chain slots; lives in shared memory (warp instantiation) or in a global scratch region
+struct Work {
+    double* S;      // [6][cap]
+    double* R;      // [6][cap]
+    double* len;    // [cap]
+    int* orig;      // [cap] tree node id
+    int* fchild;    // [cap] compact index of the first valid child (-1: none)
+    int* rsib;      // [cap] next valid child of the same parent (-1: none)
+    int* nchild;    // [cap] valid children
+    int* par;       // [cap] compact index of the parent (V = the subtree root)
+    int* cA;        // [kcap] chain: attach level (level of the node above the chain's top)
+    int* cfirst;    // [kcap] compact index of the chain's leaf
+    int* clast;     // [kcap] level of the chain's leaf
+    int* corder;    // [kcap] chains sorted by attach level
+    int cap;
+};
+
+__host__ __device__ constexpr size_t work_bytes(int cap, int kcap) {
+    return (size_t)cap * (13 * 8 + 5 * 4) + (size_t)kcap * 16;
 }
 
-template <int METHOD>
-__global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArgs a) {
+__device__ __forceinline__ Work carve(unsigned char* base, int cap, int kcap) {
+    Work w;
+    w.cap = cap;
+    w.S = reinterpret_cast<double*>(base);
+    w.R = w.S + 6 * (size_t)cap;
+    w.len = w.R + 6 * (size_t)cap;
+    w.orig = reinterpret_cast<int*>(w.len + cap);
+    w.fchild = w.orig + cap;
+    w.rsib = w.fchild + cap;
+    w.nchild = w.rsib + cap;
+    w.par = w.nchild + cap;
+    w.cA = w.par + cap;
+    w.cfirst = w.cA + kcap;
+    w.clast = w.cfirst + kcap;
+    w.corder = w.clast + kcap;
+    return w;
+}
+
+template <int METHOD, class Coop>
+__device__ __forceinline__ void place_query(const PlaceArgs& a, const int q, const int slot, const Work w, int* hist) {
     constexpr bool BME = METHOD == APPLES_BME;
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= a.n) return;
-    const int q = a.qlist ? a.qlist[t] : a.q_begin + t;
-    const int slot = a.qlist ? t : q;
-    const int st = a.status[q];
-    if (st != ST_PLACE) {
-        if (st == ST_OVERFLOW || lane != 0) return;  // overflow: handled by a later launch
-        a.out_edge[q] = (st == ST_ZERO) ? a.zero_edge[q] : -1;
-        a.out_error[q] = 0.0;
-        a.out_distal[q] = 0.0;
-        a.out_pendant[q] = 0.0;
-        a.out_status[q] = (st == ST_ZERO) ? APPLES_ZERO_DIST_LEAF : APPLES_TOO_FEW_DISTANCES;
-        return;
-    }
-    if (a.rec_off[t] < 0) return;  // belongs to the other pass (overflow rerun buffers)
+    constexpr int G = Coop::G;
+    const int lane = Coop::lane();
     const int K = a.K[q];
+    const int cap = w.cap;
     const int* __restrict__ onode = a.obs_node + (size_t)slot * a.cap;
     const double* __restrict__ odist = a.obs_dist + (size_t)slot * a.cap;
     const int* __restrict__ olen = a.obs_len + (size_t)slot * a.cap;
-    NodeRec* rec = a.recs + a.rec_off[t];       // V valid nodes + 1 pseudo record for the subtree root (the MRCA)
-    StackEnt* ch = a.stacks + a.stack_off[t];   // K chains: A = attach level, first = compact offset, last = leaf level
     const int* __restrict__ parent = a.tree.parent;
     const int* __restrict__ level = a.tree.level;
     const double* __restrict__ elen = a.tree.elen;
 
     // ---------------- chains: attach level, leaf level, compact offsets (prefix sum over chain lengths) ----------------
     int carry = 0, maxlev = 0;
-    for (int i0 = 0; i0 < K; i0 += 32) {
+    for (int i0 = 0; i0 < K; i0 += G) {
         const int i = i0 + lane;
         int len = 0, ll = 0;
         if (i < K) {
             len = olen[i];
             ll = level[onode[i]];
         }
-        int incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULLMASK, incl, o);
-            if (lane >= o) incl += v;
-        }
+        int tot;
+        const int incl = Coop::scan(len, tot);
         if (i < K) {
-            ch[i].A = ll - len;
-            ch[i].first = carry + incl - len;
-            ch[i].last = ll;
+            w.cA[i] = ll - len;
+            w.cfirst[i] = carry + incl - len;
+            w.clast[i] = ll;
         }
-        carry += __shfl_sync(FULLMASK, incl, 31);
+        carry += tot;
         maxlev = max(maxlev, ll);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxlev = max(maxlev, __shfl_xor_sync(FULLMASK, maxlev, o));
+    maxlev = Coop::max_all(maxlev);
     const int V = carry;
-    __syncwarp();
-    const int rootlev = ch[K - 1].A;  // the last chain stops below the MRCA
+    Coop::sync();
+    const int rootlev = w.cA[K - 1];  // the last chain stops below the MRCA
 
-    // ---------------- node records: one lane walks one chain ----------------
-    for (int i = lane; i < K; i += 32) {
+    // ---------------- node records: one thread walks one chain ----------------
+    for (int i = lane; i < K; i += G) {
         int u = onode[i];
-        const int off = ch[i].first, len = ch[i].last - ch[i].A;
+        const int off = w.cfirst[i], len = w.clast[i] - w.cA[i];
         for (int s = 0; s < len; ++s) {
-            NodeRec& r = rec[off + s];
-            r.len = elen[u];
-            r.orig = u;
-            r.fchild = s ? off + s - 1 : -1;
-            r.rsib = -1;
-            r.nchild = s ? 1 : 0;
-            r.par = off + s + 1;  // the top of the chain is re-linked below
-            if (s == 0) leaf_moments(METHOD, odist[i], r.S);
+            const int p = off + s;
+            w.len[p] = elen[u];
+            w.orig[p] = u;
+            w.fchild[p] = s ? p - 1 : -1;
+            w.rsib[p] = -1;
+            w.nchild[p] = s ? 1 : 0;
+            w.par[p] = p + 1;  // the top of the chain is re-linked below
+            if (s == 0) {
+                double m[6];
+                leaf_moments(METHOD, odist[i], m);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w.S[k * cap + p] = m[k];
+            }
             u = parent[u];
         }
     }
     if (lane == 0) {
-        rec[V].fchild = -1;
-        rec[V].nchild = 0;
+        w.fchild[V] = -1;
+        w.nchild[V] = 0;
     }
-    __syncwarp();
+    Coop::sync();
 
     // ---------------- link every chain top to the node it hangs from ----------------
-    for (int j = lane; j < K; j += 32) {
-        const int alj = ch[j].A;
-        const int top = ch[j].first + (ch[j].last - alj) - 1;
+    for (int j = lane; j < K; j += G) {
+        const int alj = w.cA[j];
+        const int top = w.cfirst[j] + (w.clast[j] - alj) - 1;
         // next chain to the right with attach level <= mine (next sibling or my owner), then < mine (my owner)
         int nse = j + 1;
-        while (nse < K && ch[nse].A > alj) ++nse;
+        while (nse < K && w.cA[nse] > alj) ++nse;
         int own = nse;
-        while (own < K && ch[own].A >= alj) ++own;
-        const int P = (own < K) ? ch[own].first + (ch[own].last - alj) : V;   // compact index of the node I hang from
-        rec[top].par = P;
-        if (nse < K && ch[nse].A == alj)
-            rec[top].rsib = ch[nse].first + (ch[nse].last - alj) - 1;          // next attached chain of the same node
+        while (own < K && w.cA[own] >= alj) ++own;
+        const int P = (own < K) ? w.cfirst[own] + (w.clast[own] - alj) : V;   // compact index of the node I hang from
+        w.par[top] = P;
+        if (nse < K && w.cA[nse] == alj)
+            w.rsib[top] = w.cfirst[nse] + (w.clast[nse] - alj) - 1;          // next attached chain of the same node
         else if (own < K)
-            rec[top].rsib = P - 1;                                            // the owner chain's own child comes last
+            w.rsib[top] = P - 1;                                            // the owner chain's own child comes last
         // am I the first child?  (no chain to the left hangs from the same node)
         int pse = j - 1;
-        while (pse >= 0 && ch[pse].A > alj) --pse;
-        if (pse < 0 || ch[pse].A < alj) rec[P].fchild = top;
-        atomicAdd(&rec[P].nchild, 1);
+        while (pse >= 0 && w.cA[pse] > alj) --pse;
+        if (pse < 0 || w.cA[pse] < alj) w.fchild[P] = top;
+        atomicAdd(&w.nchild[P], 1);
     }
-    __syncwarp();
+    Coop::sync();
 
     // ---------------- S and R moments ----------------
     // A chain only depends on chains with a DEEPER attach level (the chains hanging from its nodes) for S, and on the
     // one chain with a shallower attach level that owns the node it hangs from for R.  So chains are bucketed by attach
-    // level (counting sort in shared memory); S walks the buckets from the deepest level up, R from the shallowest
-    // down, and inside a bucket every lane owns whole chains (sequential along the chain, which is what the recursion
-    // is anyway).  Work is O(V + K) instead of O(levels x K).  Trees deeper than PL_HIST levels below the MRCA fall
-    // back to a level-by-level sweep.
+    // level (counting sort); S walks the buckets from the deepest level up, R from the shallowest down, and inside a
+    // bucket every thread owns whole chains (sequential along the chain, which is what the recursion is anyway).
+    // Work is O(V + K) instead of O(levels x K).  Trees deeper than PL_HIST levels below the MRCA fall back to a
+    // level-by-level sweep.
     auto s_node = [&](int p) {
-        NodeRec& r = rec[p];
-        const double coef = BME ? 1.0 / (double)r.nchild : 1.0;   // BME.py:19
+        const double coef = BME ? 1.0 / (double)w.nchild[p] : 1.0;   // BME.py:19
         double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int c = r.fchild; c >= 0; c = rec[c].rsib) accumulate<BME>(acc, rec[c].S, rec[c].len, coef);
+        for (int c = w.fchild[p]; c >= 0; c = w.rsib[c]) {
+            double m[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) r.S[k] = acc[k];
+            for (int k = 0; k < 6; ++k) m[k] = w.S[k * cap + c];
+            accumulate<BME>(acc, m, w.len[c], coef);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w.S[k * cap + p] = acc[k];
     };
     // all_R_values: siblings in child order, then the parent's R shifted by the parent's edge unless the parent is
     // the subtree root (FM.py:53-76); BME: coefficient 1 / (nonroot + #valid siblings) (BME.py:36-37)
     auto r_node = [&](int p) {
-        NodeRec& r = rec[p];
-        const int P = r.par;
+        const int P = w.par[p];
         const bool nonroot = P < V;
-        const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + rec[P].nchild - 1) : 1.0;
+        const double coef = BME ? 1.0 / (double)((nonroot ? 1 : 0) + w.nchild[P] - 1) : 1.0;
         double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int sb = rec[P].fchild; sb >= 0; sb = rec[sb].rsib)
-            if (sb != p) accumulate<BME>(acc, rec[sb].S, rec[sb].len, coef);
-        if (nonroot) accumulate<BME>(acc, rec[P].R, rec[P].len, coef);
+        for (int sb = w.fchild[P]; sb >= 0; sb = w.rsib[sb])
+            if (sb != p) {
+                double m[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) r.R[k] = acc[k];
+                for (int k = 0; k < 6; ++k) m[k] = w.S[k * cap + sb];
+                accumulate<BME>(acc, m, w.len[sb], coef);
+            }
+        if (nonroot) {
+            double m[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) m[k] = w.R[k * cap + P];
+            accumulate<BME>(acc, m, w.len[P], coef);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) w.R[k * cap + p] = acc[k];
     };
     const int range = maxlev - rootlev;  // attach levels lie in [rootlev, maxlev - 1]
     if (range <= PL_HIST) {
-        __shared__ int s_hist[4][PL_HIST + 1];
-        int* h = s_hist[threadIdx.x >> 5];
-        for (int x = lane; x <= range; x += 32) h[x] = 0;
-        __syncwarp();
-        for (int i = lane; i < K; i += 32) atomicAdd(&h[ch[i].A - rootlev], 1);
-        __syncwarp();
-        {   // exclusive prefix sum over h[0 .. range): every lane owns a contiguous segment
-            const int seg = (range + 31) / 32, b = min(range, lane * seg), e = min(range, b + seg);
-            int sum = 0;
-            for (int x = b; x < e; ++x) sum += h[x];
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULLMASK, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int run = incl - sum;
-            for (int x = b; x < e; ++x) {
-                const int c = h[x];
-                h[x] = run;
-                run += c;
+        int* h = hist;
+        for (int x = lane; x <= range; x += G) h[x] = 0;
+        Coop::sync();
+        for (int i = lane; i < K; i += G) atomicAdd(&h[w.cA[i] - rootlev], 1);
+        Coop::sync();
+        // exclusive prefix sum over h[0 .. range): at most PL_HIST entries, one pass of the group's scan per G entries
+        {
+            int run = 0;
+            for (int x0 = 0; x0 < range; x0 += G) {
+                const int x = x0 + lane;
+                const int c = x < range ? h[x] : 0;
+                int tot;
+                const int incl = Coop::scan(c, tot);
+                if (x < range) h[x] = run + incl - c;
+                run += tot;
             }
         }
-        __syncwarp();
-        for (int i = lane; i < K; i += 32) ch[atomicAdd(&h[ch[i].A - rootlev], 1)].n = i;  // h[x] becomes the bucket END
-        __syncwarp();
+        Coop::sync();
+        for (int i = lane; i < K; i += G) w.corder[atomicAdd(&h[w.cA[i] - rootlev], 1)] = i;  // h[x] becomes the bucket END
+        Coop::sync();
         for (int x = range - 1; x >= 0; --x) {          // S: deepest attach level first
             const int b = x ? h[x - 1] : 0, e = h[x];
-            for (int k = b + lane; k < e; k += 32) {
-                const int i = ch[k].n;
-                const int off = ch[i].first, len = ch[i].last - ch[i].A;
+            for (int k = b + lane; k < e; k += G) {
+                const int i = w.corder[k];
+                const int off = w.cfirst[i], len = w.clast[i] - w.cA[i];
                 for (int sdx = 1; sdx < len; ++sdx) s_node(off + sdx);
             }
-            if (b != e) __syncwarp();
+            if (b != e) Coop::sync();
         }
         for (int x = 0; x < range; ++x) {               // R: shallowest attach level first, each chain top-down
             const int b = x ? h[x - 1] : 0, e = h[x];
-            for (int k = b + lane; k < e; k += 32) {
-                const int i = ch[k].n;
-                const int off = ch[i].first, len = ch[i].last - ch[i].A;
+            for (int k = b + lane; k < e; k += G) {
+                const int i = w.corder[k];
+                const int off = w.cfirst[i], len = w.clast[i] - w.cA[i];
                 for (int sdx = len - 1; sdx >= 0; --sdx) r_node(off + sdx);
             }
-            if (b != e) __syncwarp();
+            if (b != e) Coop::sync();
         }
     } else {
         for (int lv = maxlev - 1; lv > rootlev; --lv) {  // S: level by level upwards
-            for (int i = lane; i < K; i += 32) {
-                const int al = ch[i].A, ll = ch[i].last;
-                if (al < lv && lv < ll) s_node(ch[i].first + (ll - lv));
+            for (int i = lane; i < K; i += G) {
+                const int al = w.cA[i], ll = w.clast[i];
+                if (al < lv && lv < ll) s_node(w.cfirst[i] + (ll - lv));
             }
-            __syncwarp();
+            Coop::sync();
         }
         for (int lv = rootlev + 1; lv <= maxlev; ++lv) {  // R: level by level downwards
-            for (int i = lane; i < K; i += 32) {
-                const int al = ch[i].A, ll = ch[i].last;
-                if (al < lv && lv <= ll) r_node(ch[i].first + (ll - lv));
+            for (int i = lane; i < K; i += G) {
+                const int al = w.cA[i], ll = w.clast[i];
+                if (al < lv && lv <= ll) r_node(w.cfirst[i] + (ll - lv));
             }
-            __syncwarp();
+            Coop::sync();
         }
     }
 
     // ---------------- per-edge closed-form solve + criterion selection (first minimum in post-order) ----------------
+    auto solve_at = [&](int p) {
+        double S[6], R[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            S[k] = w.S[k * cap + p];
+            R[k] = w.R[k * cap + p];
+        }
+        return solve_edge(S, R, w.len[p], a.negative_branch);
+    };
     const bool dbg = a.dbg_x1 != nullptr && q == a.dbg_query;
     double bval = 0.0;
     int bidx = 0x7fffffff;
     bool degenerate = false;
-    for (int p = lane; p < V; p += 32) {
-        NodeRec& r = rec[p];
-        const EdgeSol e = solve_edge(r.S, r.R, r.len, a.negative_branch);
+    for (int p = lane; p < V; p += G) {
+        const EdgeSol e = solve_at(p);
         degenerate |= e.deg;
         if (dbg) {
-            a.dbg_x1[r.orig] = e.x1;
-            a.dbg_x2[r.orig] = e.x2;
-            a.dbg_err[r.orig] = e.err;
-            a.dbg_valid[r.orig] = 1;
+            const int u = w.orig[p];
+            a.dbg_x1[u] = e.x1;
+            a.dbg_x2[u] = e.x2;
+            a.dbg_err[u] = e.err;
+            a.dbg_valid[u] = 1;
         }
         const double key = (a.criterion == APPLES_ME) ? e.x1 : e.err;
-        if (bidx == 0x7fffffff || key < bval) { bval = key; bidx = p; }  // ascending p per lane: first minimum kept
+        if (bidx == 0x7fffffff || key < bval) { bval = key; bidx = p; }  // ascending p per thread: first minimum kept
     }
-    warp_argmin(bval, bidx);
-    degenerate = __any_sync(FULLMASK, degenerate);
+    Coop::argmin(bval, bidx);
+    degenerate = Coop::any(degenerate);
     int best = bidx;
     if (a.criterion == APPLES_HYBRID) {
         // heapq.nsmallest(floor(log2 V), key=error) in (error, order) order, then the first minimum of x_1 among
@@ -353,43 +479,124 @@ __global__ void __launch_bounds__(128, PL_MINBLOCKS) place_kernel(const PlaceArg
         for (int rd = 0; rd < rounds; ++rd) {
             double v = 0.0;
             int ix = 0x7fffffff;
-            for (int p = lane; p < V; p += 32) {
-                const NodeRec& r = rec[p];
-                const double e = solve_edge(r.S, r.R, r.len, a.negative_branch).err;
+            for (int p = lane; p < V; p += G) {
+                const double e = solve_at(p).err;
                 const bool after = last_p < 0 || e > last_e || (e == last_e && p > last_p);
                 if (after && (ix == 0x7fffffff || e < v)) { v = e; ix = p; }
             }
-            warp_argmin(v, ix);
+            Coop::argmin(v, ix);
             if (ix == 0x7fffffff) break;
-            const NodeRec& r = rec[ix];
-            const double x1 = solve_edge(r.S, r.R, r.len, a.negative_branch).x1;
+            const double x1 = solve_at(ix).x1;
             if (best < 0 || x1 < best_x1) { best = ix; best_x1 = x1; }
             last_e = v;
             last_p = ix;
         }
     }
     if (lane == 0) {
-        const NodeRec& rb = rec[best];
-        const EdgeSol bs = solve_edge(rb.S, rb.R, rb.len, a.negative_branch);
+        const EdgeSol bs = solve_at(best);
+        const double blen = w.len[best];
         // Algorithm.py:93-99
-        const bool flag = bs.x1 == 0.0 && bs.err > 0.0 && (bs.x2 == 0.0 || bs.x2 == rb.len);
-        a.out_edge[q] = rb.orig;
+        const bool flag = bs.x1 == 0.0 && bs.err > 0.0 && (bs.x2 == 0.0 || bs.x2 == blen);
+        a.out_edge[q] = w.orig[best];
         a.out_error[q] = bs.err;
-        a.out_distal[q] = rb.len - bs.x2;
+        a.out_distal[q] = blen - bs.x2;
         a.out_pendant[q] = bs.x1;
         a.out_status[q] = (flag ? APPLES_PLACED_MISPLACEMENT_FLAG : APPLES_PLACED) | (bs.int0 ? APPLES_FLAG_PENDANT_INT0 : 0) |
                           (degenerate ? APPLES_FLAG_DEGENERATE : 0);
     }
 }
 
-void launch_place(int method, const PlaceArgs& a, cudaStream_t s) {
-    if (a.n <= 0) return;
-    const int warps = 4;
-    dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
+// one warp per query, working set in shared memory (VCAP node slots per query), WARPS queries per block
+template <int VCAP>
+struct SmemClass {
+    static constexpr int WARPS = 1;   // 10 / 19 / 37 / 73 KB per block: 22 / 11 / 6 / 3 queries in flight per SM
+    static constexpr size_t PER_WARP = work_bytes(VCAP, VCAP) + (PL_HIST + 1) * 4 + 12;   // multiple of 16
+    static constexpr size_t BYTES = WARPS * PER_WARP;
+};
+
+template <int METHOD, int VCAP>
+__global__ void __launch_bounds__(SmemClass<VCAP>::WARPS * 32) place_smem_kernel(const PlaceArgs a) {
+    extern __shared__ __align__(16) unsigned char pl_smem[];
+    using C = SmemClass<VCAP>;
+    static_assert(C::PER_WARP % 16 == 0, "per-warp region must keep the doubles aligned");
+    const int wib = threadIdx.x >> 5;
+    const int t = blockIdx.x * C::WARPS + wib;
+    if (t >= a.n) return;
+    unsigned char* base = pl_smem + (size_t)wib * C::PER_WARP;
+    const Work w = carve(base, VCAP, VCAP);
+    int* hist = reinterpret_cast<int*>(base + work_bytes(VCAP, VCAP));
+    const int q = a.qlist[t];
+    place_query<METHOD, WarpCoop>(a, q, a.slot_list ? a.slot_list[t] : q, w, hist);
+}
+
+// one block per query, working set in a global scratch region (rec_off / stack_off in node / chain slots)
+template <int METHOD>
+__global__ void __launch_bounds__(PL_BLOCK_THREADS) place_block_kernel(const PlaceArgs a) {
+    __shared__ int hist[PL_HIST + 1];
+    const int t = blockIdx.x;
+    const int q = a.qlist[t];
+    const int K = a.K[q];
+    // the host sized the region: rec_off[t] .. rec_off[t + 1] node slots of 128 bytes, stack_off likewise in 16-byte slots
+    const int cap = (int)(a.rec_off[t + 1] - a.rec_off[t]);
+    unsigned char* nodes = reinterpret_cast<unsigned char*>(a.recs) + (size_t)a.rec_off[t] * 128;
+    Work w = carve(nodes, cap, 0);
+    int* chains = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(a.stacks) + (size_t)a.stack_off[t] * 16);
+    w.cA = chains;
+    w.cfirst = chains + K;
+    w.clast = chains + 2 * (size_t)K;
+    w.corder = chains + 3 * (size_t)K;
+    place_query<METHOD, BlockCoop>(a, q, a.slot_list ? a.slot_list[t] : q, w, hist);
+}
+
+// queries that are not placed by least squares: zero-distance shortcut and "<= 2 observed distances"
+// (PoolQueryWorker.py:72-75, 97-98); one thread per query of the batch
+__global__ void finalize_kernel(const PlaceArgs a) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.n) return;
+    const int st = a.status[q];
+    if (st != ST_ZERO && st != ST_TOO_FEW) return;
+    a.out_edge[q] = (st == ST_ZERO) ? a.zero_edge[q] : -1;
+    a.out_error[q] = 0.0;
+    a.out_distal[q] = 0.0;
+    a.out_pendant[q] = 0.0;
+    a.out_status[q] = (st == ST_ZERO) ? APPLES_ZERO_DIST_LEAF : APPLES_TOO_FEW_DISTANCES;
+}
+
+cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
+    finalize_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int METHOD, int VCAP>
+static cudaError_t launch_smem(const PlaceArgs& a, cudaStream_t s) {
+    using C = SmemClass<VCAP>;
+    const dim3 grid((a.n + C::WARPS - 1) / C::WARPS), block(C::WARPS * 32);
+    cudaError_t e = cudaFuncSetAttribute(place_smem_kernel<METHOD, VCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+    if (e != cudaSuccess) return e;
+    place_smem_kernel<METHOD, VCAP><<<grid, block, C::BYTES, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <int METHOD>
+static cudaError_t launch_place_method(int vclass, const PlaceArgs& a, cudaStream_t s) {
+    switch (vclass) {
+        case PLACE_CLASS_64: return launch_smem<METHOD, 64>(a, s);
+        case PLACE_CLASS_128: return launch_smem<METHOD, 128>(a, s);
+        case PLACE_CLASS_256: return launch_smem<METHOD, 256>(a, s);
+        case PLACE_CLASS_512: return launch_smem<METHOD, 512>(a, s);
+        default:
+            place_block_kernel<METHOD><<<a.n, PL_BLOCK_THREADS, 0, s>>>(a);
+            return cudaGetLastError();
+    }
+}
+
+cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s) {
+    if (a.n <= 0) return cudaSuccess;
     switch (method) {
-        case APPLES_FM: place_kernel<APPLES_FM><<<grid, block, 0, s>>>(a); break;
-        case APPLES_BME: place_kernel<APPLES_BME><<<grid, block, 0, s>>>(a); break;
-        case APPLES_BE: place_kernel<APPLES_BE><<<grid, block, 0, s>>>(a); break;
-        default: place_kernel<APPLES_OLS><<<grid, block, 0, s>>>(a); break;
+        case APPLES_FM: return launch_place_method<APPLES_FM>(vclass, a, s);
+        case APPLES_BME: return launch_place_method<APPLES_BME>(vclass, a, s);
+        case APPLES_BE: return launch_place_method<APPLES_BE>(vclass, a, s);
+        default: return launch_place_method<APPLES_OLS>(vclass, a, s);
     }
 }

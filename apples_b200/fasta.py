@@ -69,6 +69,64 @@ def fasta2dic(ref_fp, prot_flag, mask_flag):
     return refs
 
 
+class FastaMatrix:
+    """An alignment file read by the native reader (libapples_b200: apples_fasta_open, the C++ twin of fasta2dic above):
+    `names` (list of str, file order) and `matrix` (uint8 [n, L] view of the reader's buffer -- pinned host memory when a
+    CUDA device is usable, so the placement call DMAs straight from it).  Keep the object alive while `matrix` is used."""
+
+    def __init__(self, path, prot_flag=False, mask_flag=False, threads=0, pinned=True):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self._lib.apples_fasta_open(str(path).encode(), 1 if prot_flag else 0, 1 if mask_flag else 0, int(threads),
+                                         1 if pinned else 0, C.byref(h), err, 512)
+        if rc != 0:
+            raise OSError('reading %s failed: %s' % (path, err.value.decode(errors='replace')))
+        self._h = h
+        lib = self._lib
+        self.n = int(lib.apples_fasta_count(h))
+        self.L = int(lib.apples_fasta_max_len(h))
+        self.stride = int(lib.apples_fasta_stride(h))
+        self.uniform = bool(lib.apples_fasta_uniform(h))
+        self.pinned = bool(lib.apples_fasta_pinned(h))
+        n = self.n
+        self.lengths = np.ctypeslib.as_array(C.cast(lib.apples_fasta_lengths(h), C.POINTER(C.c_int64)), shape=(n,)) if n else np.zeros(0, np.int64)
+        self._name_off = np.ctypeslib.as_array(C.cast(lib.apples_fasta_name_offsets(h), C.POINTER(C.c_int64)), shape=(n + 1,))
+        self._name_bytes = C.string_at(lib.apples_fasta_names(h), int(self._name_off[n])) if n else b''
+        full = np.ctypeslib.as_array(C.cast(lib.apples_fasta_matrix(h), C.POINTER(C.c_uint8)), shape=(max(n, 1), max(self.stride, 1)))
+        self.full = full[:n]                 # [n, stride], rows padded with '-'
+        self.matrix = self.full[:, :self.L]  # [n, L] (row stride = self.stride)
+        self._names = None
+
+    @property
+    def names(self):
+        if self._names is None:
+            # text files are read as UTF-8 by the Python twin (open() default); invalid bytes raise like there
+            self._names = self._name_bytes.decode('utf-8').split('\0')[:-1] if self.n else []
+        return self._names
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self.matrix = self.full = self.lengths = self._name_off = None
+            self._lib.apples_fasta_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def as_dict(self):
+        """{name: 'S1' row} like fasta2dic (copies; later duplicates overwrite earlier ones in place, like a dict)."""
+        out = {}
+        for i, nm in enumerate(self.names):
+            out[nm] = self.matrix[i, :int(self.lengths[i])].copy().view('S1')
+        return out
+
+
 def words_per_row(L):
     """uint32 words per bit-plane row, padded to a multiple of 4 words (16 bytes) so rows can be moved with
     16-byte bulk copies."""

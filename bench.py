@@ -245,22 +245,24 @@ def main():
     del packed_q
     pl.upload_queries(packed_host)
     stream = torch.cuda.ExternalStream(pl.stream, device=device)
-    # send / receive buffers of the final gather of placements
+    # device buffers of the final gather of placements: the five result arrays are packed into 32-byte records and
+    # exchanged with ONE all-gather (apples_b200.parallel, the same code the product path uses under torchrun)
+    from apples_b200 import parallel
     send = (torch.empty(nq, dtype=torch.int32, device=device), torch.empty(nq, dtype=torch.float64, device=device),
             torch.empty(nq, dtype=torch.float64, device=device), torch.empty(nq, dtype=torch.float64, device=device),
             torch.empty(nq, dtype=torch.int32, device=device))
-    recv = [torch.empty(nq * world, dtype=t.dtype, device=device) for t in send] if world > 1 else None
+    recv = torch.empty((nq * world, 4), dtype=torch.int64, device=device) if world > 1 else None
+    gathered = [None]
 
     def step_resident():
         pl.place_resident(params)
         if world > 1:
             pl.results_to_device(*send)
-            for r, t in zip(recv, send):
-                dist.all_gather_into_tensor(r, t)
+            gathered[0] = parallel.gather_records(parallel.pack_records(*send), nq * world, out=recv)
             # the gathered placements are this step's result: wait for them before the next step starts.  Left
             # asynchronous, the NCCL kernels of a rank that is ahead spin on its SMs while its next dense kernel (one
             # persistent CTA per SM, statically striped tiles) starts, and the CTAs that start late set the kernel time
-            # (+12 % on every rank at 8 GPUs)
+            # (+12 % on every rank at 8 GPUs; handing tiles out dynamically instead costs 4.5 % at 1 GPU)
             torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -319,6 +321,9 @@ def main():
         t0 = time.time()
         for _ in range(args.steps):
             out = pl.place_bytes(bytes_np, self_node, params)
+            if world > 1:
+                # the product's multi-process path ends here: every rank holds all placements (placer.place_arrays)
+                out_all = parallel.gather_placements(out, nq * world, device=device)
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
@@ -327,10 +332,26 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
         e2e = {'value': nq * world * args.steps / (ems / 1e3), 'unit': 'queries/s',
-               'h2d_bytes_per_step': int(bytes_host.numel()), 'd2h_bytes_per_step': int(nq * 32),
+               'h2d_bytes_per_step': (int(bytes_host.numel()) + (32 * nq if world > 1 else 0)) * world,
+               'd2h_bytes_per_step': (32 * nq + (32 * nq * world if world > 1 else 0)) * world,
                'input': 'alignment bytes (uint8 per site) in pinned host memory, packed on the device',
                'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps}
         pl.timings(reset=True)
+
+    # sha1 of every rank's block of result records (block r = the queries generated from seed 1000 + r): block 0 of an
+    # N-GPU run must carry the hash the 1-GPU run prints, block 1 the hash the 2-GPU run prints for it, and so on
+    import hashlib
+    if world > 1:
+        rec_all = gathered[0]
+    else:
+        pl.results_to_device(*send)
+        rec_all = parallel.pack_records(*send)
+    rec_np = rec_all.cpu().numpy()
+    block_hashes = [hashlib.sha1(rec_np[r * nq:(r + 1) * nq].tobytes()).hexdigest()[:16] for r in range(world)]
+    if world > 1 and e2e is not None:
+        # the end-to-end (host buffers + gather) result must be the same records
+        e2e_rec = parallel.pack_records(*[torch.from_numpy(np.ascontiguousarray(a)) for a in out_all]).numpy()
+        e2e['result_equals_resident_path'] = bool((e2e_rec == rec_np).all())
 
     if rank != 0:
         if world > 1:
@@ -421,8 +442,9 @@ def main():
             'distance_gcell_sites_per_s': (tm['pairs'] / args.steps) * args.sites / (step_ms * 1e-3) / 1e9 * world,
             'stage_ms_per_step': stages, 'rep_distance_sm_mhz': tm.get('rep_distance_sm_mhz'), 'per_rank': per_rank, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
             'observed_per_query': tm['observed'] / (nq * args.steps), 'valid_nodes_per_query': tm['valid_nodes'] / (nq * args.steps),
-            'overflow_queries_per_step': tm['overflow_queries'] / args.steps, 'max_observed': tm['max_observed'],
-            'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_select': roofline_select,
+            'overflow_queries_per_step': tm['overflow_queries'] / args.steps,
+            'placement_classes_per_step': {k: tm[k] / args.steps for k in ('placed_smem64', 'placed_smem128', 'placed_smem256', 'placed_smem512', 'placed_block')}, 'max_observed': tm['max_observed'],
+            'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'result_sha1_per_block': block_hashes, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_select': roofline_select,
             'roofline_place': roofline_place, 'setup': info}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----

@@ -157,8 +157,42 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
  * [0] h2d  [1] transpose  [2] rep distance  [3] selection  [4] placement  [5] d2h  [6] launches (count)
  * [7] rep-distance launches (count) [8] query-representative pairs evaluated [9] observed leaves [10] valid nodes
  * [11] overflow reruns (queries) [12] largest observed set [13] largest restricted subtree
- * [14] effective SM clock in MHz during the last representative-distance launch (clock64 / globaltimer, in-kernel) */
+ * [14] effective SM clock in MHz during the last representative-distance launch (clock64 / globaltimer, in-kernel)
+ * [15..19] queries placed by the shared-memory placement launches of 64 / 128 / 256 / 512 node slots and by the
+ * block-per-query launch (global scratch) */
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset);
+
+/* ---- host side of SURVEY.md section 8 (f1) / (f3) in native code (no CUDA kernel involved) ---- */
+
+/* FASTA / FASTQ file -> byte matrix, replacing apples/fasta2dic.py:4-72 (readfq + fasta2dic): records in file order,
+ * name = header up to the first blank, sequences upper-cased (mask_flag: lower case -> '-'), letters outside the
+ * alphabet (nucleotide: everything but A,C,G,T; protein: B,J,O,U,X,Z) -> '-', every other byte kept.  The matrix is
+ * uint8[n][stride], stride = max length rounded up to 16, rows padded with '-'; it is pinned host memory when
+ * want_pinned != 0 and a CUDA device is usable, so apples_place_batch_bytes can DMA straight from it.
+ * n_threads <= 0: all cores.  err (may be NULL) receives a message on failure. */
+typedef struct apples_fasta apples_fasta;
+int apples_fasta_open(const char* path, int prot_flag, int mask_flag, int n_threads, int want_pinned, apples_fasta** out,
+                      char* err, int errlen);
+void apples_fasta_close(apples_fasta* f);
+int64_t apples_fasta_count(const apples_fasta* f);
+int64_t apples_fasta_max_len(const apples_fasta* f);
+int64_t apples_fasta_stride(const apples_fasta* f);
+int apples_fasta_uniform(const apples_fasta* f);            /* 1 when every sequence has the same length (an alignment) */
+int apples_fasta_pinned(const apples_fasta* f);
+const uint8_t* apples_fasta_matrix(const apples_fasta* f);
+const int64_t* apples_fasta_lengths(const apples_fasta* f); /* n */
+const char* apples_fasta_names(const apples_fasta* f);      /* NUL-terminated names, concatenated */
+const int64_t* apples_fasta_name_offsets(const apples_fasta* f); /* n + 1 */
+
+/* Result arrays -> jplace file, replacing join_jplace + json.dumps(result, sort_keys=True, indent=4) for the
+ * "placements" list (jutil.py:1-19, run_apples.py:106-118): writes `prefix`, the list, `suffix`.  prefix / suffix are
+ * the JSON text before / after the list (the caller renders the small rest of the document).  Records are the ones
+ * PoolQueryWorker.runquery returns for the given status codes (names of queries found in the backbone get "-query");
+ * numbers are written as Python's float repr, names as json.dumps' ASCII escapes.  n_written = records kept. */
+int apples_jplace_write(const char* path, const char* prefix, const char* suffix, int64_t n, const char* names,
+                        const int64_t* name_off, const uint8_t* in_backbone, const int32_t* edge, const double* error,
+                        const double* distal, const double* pendant, const int32_t* status, int exclude_intplace,
+                        int n_threads, int64_t* n_written, char* err, int errlen);
 
 #ifdef __cplusplus
 }

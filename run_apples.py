@@ -59,7 +59,7 @@ def main(argv=None):
             tree = up.load()
             name_to_node_map = up.load()
             extended_newick_string = up.load()
-        except (ModuleNotFoundError, AttributeError) as e:
+        except (ModuleNotFoundError, AttributeError, EOFError, pickle.UnpicklingError) as e:
             # upstream databases pickle treeswift.Tree / apples.Reference objects, which this build does not contain
             raise SystemExit('%s is not a database written by this build\'s build_applesdtb.py (%s); databases pickled '
                              'by upstream APPLES hold treeswift / apples.* objects and cannot be loaded here: rebuild it '
@@ -86,7 +86,7 @@ def main(argv=None):
         else:
             try:
                 reference = up.load()
-            except (ModuleNotFoundError, AttributeError) as e:
+            except (ModuleNotFoundError, AttributeError, EOFError, pickle.UnpicklingError) as e:
                 raise SystemExit('%s: the reduced reference was not pickled by this build (%s); rebuild the database with '
                                  'build_applesdtb.py' % (options.database_fp, e))
             fdtb.close()

@@ -374,7 +374,8 @@ def test_tiny_tree_and_all_singletons(workdir):
     tsv = os.path.join(workdir, 'tiny.tsv')
     with open(tsv, 'w') as f:
         f.write('SequenceName\tClusterNumber\n' + ''.join('%s\t-1\n' % n for n in 'ABCDE'))
-    ref = ReducedReference(None, False, tfp, 0.2, 1, cluster_tsv=tsv, tree=tree, refs=refs)
+    # the reference object carries the expansion threshold (Reference.py:146), as upstream builds it from the run's -f
+    ref = ReducedReference(None, False, tfp, 0.01, 1, cluster_tsv=tsv, tree=tree, refs=refs)
     for method, crit, b in [('FM', 'MLSE', 25), ('OLS', 'ME', 2), ('BME', 'HYBRID', 100)]:
         opt = types.SimpleNamespace(method_name=method, criterion_name=crit, negative_branch=False,
                                     base_observation_threshold=b, filt_threshold=0.01, minimum_alignment_overlap=0.001,
