@@ -104,14 +104,87 @@ int apples_fasta_open(const char* path, int prot_flag, int mask_flag, int n_thre
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     n_threads = std::min(n_threads, 64);
 
-    // ---- pass 1 (sequential over LINES' first characters, cheap): record boundaries with readfq's state machine
-    // (fasta2dic.py:4-39): a header is a line starting with '>' or '@' where a header is expected; inside a sequence
-    // block a line starting with '@', '+' or '>' ends it; a '+' line starts a quality block that is skipped until it is
-    // at least as long as the sequence.
+    // ---- pass 1: record boundaries.  Parallel scan for the lines that start with '>', '@' or '+'.  A file without '@' and
+    // '+' lines is plain FASTA: every '>' line starts a record, so the boundaries are known without a sequential state
+    // machine (5 GB of queries at config 5).  Anything else (FASTQ) takes readfq's sequential state machine below.
     std::vector<Rec> recs;
+    bool plain_fasta = true;
     {
+        std::vector<std::vector<const char*>> heads((size_t)n_threads);
+        std::vector<char> other((size_t)n_threads, 0);
+        auto scan = [&](int t) {
+            const size_t b = size * (size_t)t / (size_t)n_threads, e = size * (size_t)(t + 1) / (size_t)n_threads;
+            const char* p = data + b;
+            const char* pe = data + e;
+            if (b > 0) {   // first line start at or after b
+                const char* q = (const char*)memchr(p - 1, '\n', (size_t)(end - (p - 1)));
+                p = q ? q + 1 : end;
+            }
+            while (p < pe) {
+                const char c = *p;
+                if (c == '>') heads[(size_t)t].push_back(p);
+                else if (c == '@' || c == '+') other[(size_t)t] = 1;
+                const char* q = (const char*)memchr(p, '\n', (size_t)(end - p));
+                p = q ? q + 1 : end;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_threads; ++t) th.emplace_back(scan, t);
+        scan(0);
+        for (auto& t : th) t.join();
+        for (int t = 0; t < n_threads; ++t) plain_fasta = plain_fasta && !other[(size_t)t];
+        if (plain_fasta) {
+            size_t total = 0;
+            for (auto& h : heads) total += h.size();
+            recs.resize(total);
+            size_t k = 0;
+            for (auto& h : heads)
+                for (const char* p : h) recs[k++].name = p;   // header position for now
+            // names, sequence ranges and lengths in parallel
+            std::atomic<size_t> nx(0);
+            // header positions (the next record's header ends this record's sequence block)
+            std::vector<const char*> hp(recs.size());
+            for (size_t i = 0; i < recs.size(); ++i) hp[i] = recs[i].name;
+            auto fill2 = [&]() {
+                for (;;) {
+                    const size_t b = nx.fetch_add(1024);
+                    if (b >= recs.size()) break;
+                    const size_t e = std::min(recs.size(), b + 1024);
+                    for (size_t i = b; i < e; ++i) {
+                        const char* p = hp[i];
+                        const char* stop = i + 1 < hp.size() ? hp[i + 1] : end;
+                        const char* le = line_end(p, end);
+                        const char* hb = p + 1;
+                        const char* he = rstrip_crlf(hb, le);
+                        const char* sp = (const char*)memchr(hb, ' ', (size_t)(he - hb));
+                        Rec r;
+                        r.name = hb;
+                        r.name_len = (sp ? sp : he) - hb;
+                        r.seq = le < end ? le + 1 : end;
+                        if (r.seq > stop) r.seq = stop;
+                        r.seq_end = stop;
+                        int64_t len = 0;
+                        for (const char* q = r.seq; q < stop;) {
+                            const char* e2 = line_end(q, stop);
+                            len += rstrip_crlf(q, e2) - q;
+                            q = e2 < stop ? e2 + 1 : stop;
+                        }
+                        r.len = len;
+                        recs[i] = r;
+                    }
+                }
+            };
+            std::vector<std::thread> th2;
+            for (int t = 1; t < n_threads; ++t) th2.emplace_back(fill2);
+            fill2();
+            for (auto& t : th2) t.join();
+        }
+    }
+    if (!plain_fasta) {
+        // readfq's state machine (fasta2dic.py:4-39): a header is a line starting with '>' or '@' where a header is
+        // expected; inside a sequence block a line starting with '@', '+' or '>' ends it; a '+' line starts a quality
+        // block that is skipped until it is at least as long as the sequence.
         const char* p = data;
-        // state: looking for a header
         while (p < end) {
             const char* le = line_end(p, end);
             if (le > p && (*p == '>' || *p == '@')) {
@@ -123,7 +196,6 @@ int apples_fasta_open(const char* path, int prot_flag, int mask_flag, int n_thre
                 r.name_len = (sp ? sp : he) - hb;
                 p = le < end ? le + 1 : end;
                 r.seq = p;
-                // sequence lines until a line starting with '@', '+' or '>'
                 int64_t len = 0;
                 bool plus = false;
                 while (p < end) {
@@ -139,7 +211,6 @@ int apples_fasta_open(const char* path, int prot_flag, int mask_flag, int n_thre
                 r.len = len;
                 recs.push_back(r);
                 if (plus) {
-                    // quality block: skip the '+' line, then lines until their total length reaches the sequence length
                     const char* e2 = line_end(p, end);
                     p = e2 < end ? e2 + 1 : end;
                     int64_t got = 0;

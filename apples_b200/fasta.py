@@ -119,12 +119,20 @@ class FastaMatrix:
         except Exception:
             pass
 
-    def as_dict(self):
-        """{name: 'S1' row} like fasta2dic (copies; later duplicates overwrite earlier ones in place, like a dict)."""
+    def as_dict(self, copy=True):
+        """{name: 'S1' row} like fasta2dic (later duplicates overwrite earlier ones in place, like a dict).  copy=False
+        returns views into the reader's buffer: keep this object alive as long as the dict is used."""
         out = {}
+        lens = self.lengths.tolist()
         for i, nm in enumerate(self.names):
-            out[nm] = self.matrix[i, :int(self.lengths[i])].copy().view('S1')
+            row = self.matrix[i, :lens[i]]
+            out[nm] = (row.copy() if copy else row).view('S1')
         return out
+
+
+def read_alignment(path, prot_flag=False, mask_flag=False, threads=0, pinned=True):
+    """Product-path reader: the native C++ twin of fasta2dic (apples_fasta_open).  Fails loudly without the library."""
+    return FastaMatrix(path, prot_flag, mask_flag, threads, pinned)
 
 
 def words_per_row(L):

@@ -93,6 +93,45 @@ def dumps(result):
             gc.enable()
 
 
+def write_arrays(output_fp, names, in_backbone, out, extended_newick_string, exclude_intplace=False, argv=None, threads=0,
+                 name_blob=None, name_off=None):
+    """The fast path of run_apples.py's tail (join_jplace + json.dumps + write, run_apples.py:106-118) straight from the
+    device result arrays, without a million per-query dicts: the native writer (apples_jplace_write, hostio.cpp) renders
+    the "placements" list, Python renders the few lines around it.  Output is byte-identical to
+    `write(assemble(results_to_jplace(...)))`.  `names` is a list of str, or pass the reader's NUL-separated UTF-8 blob
+    and offsets (FastaMatrix) as name_blob / name_off.  Returns the number of records written."""
+    import ctypes as C
+    import numpy as np
+    from . import _lib
+    lib = _lib.load()
+    edge, error, distal, pendant, status = [np.ascontiguousarray(a) for a in out]
+    n = int(edge.shape[0])
+    if name_blob is None:
+        enc = [s.encode('utf-8') for s in names]
+        name_off = np.zeros(n + 1, np.int64)
+        if n:
+            np.cumsum([len(b) + 1 for b in enc], out=name_off[1:])
+        name_blob = b'\0'.join(enc) + b'\0'
+    name_off = np.ascontiguousarray(name_off, dtype=np.int64)
+    inb = np.ascontiguousarray(np.asarray(in_backbone, dtype=np.uint8))
+    marker = '@@APPLES_B200_PLACEMENTS@@'
+    shell = {'placements': marker, 'tree': extended_newick_string,
+             'metadata': {'invocation': ' '.join(sys.argv if argv is None else argv)},
+             'fields': ['edge_num', 'likelihood', 'like_weight_ratio', 'distal_length', 'pendant_length'], 'version': 3}
+    text = json.dumps(shell, sort_keys=True, indent=4)
+    head, _, tail = text.partition('"' + marker + '"')
+    err = C.create_string_buffer(512)
+    nw = C.c_int64(0)
+    blob = C.create_string_buffer(name_blob, len(name_blob)) if not isinstance(name_blob, C.Array) else name_blob
+    rc = lib.apples_jplace_write(str(output_fp).encode(), head.encode(), (tail + '\n').encode(), n,
+                                 C.cast(blob, C.c_void_p), _lib.ptr(name_off), _lib.ptr(inb), _lib.ptr(edge), _lib.ptr(error),
+                                 _lib.ptr(distal), _lib.ptr(pendant), _lib.ptr(status), 1 if exclude_intplace else 0,
+                                 int(threads), C.byref(nw), err, 512)
+    if rc != 0:
+        raise OSError('writing %s failed: %s' % (output_fp, err.value.decode(errors='replace')))
+    return int(nw.value)
+
+
 def write(result, output_fp=None):
     """run_apples.py:112-118"""
     f = open(output_fp, 'w') if output_fp else sys.stdout

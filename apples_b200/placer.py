@@ -138,13 +138,15 @@ class GpuPlacer:
 
     def place_bytes(self, mat, self_node, params, out=None):
         """alignment bytes uint8 [nq, L] (host) -> result arrays; packing happens on the device."""
-        mat = np.ascontiguousarray(mat, dtype=np.uint8)
         if mat.shape[1] != self.L:
             raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], self.L))
+        if not (mat.dtype == np.uint8 and mat.ndim == 2 and mat.strides[1] == 1 and mat.strides[0] >= mat.shape[1]):
+            mat = np.ascontiguousarray(mat, dtype=np.uint8)
         nq = int(mat.shape[0])
         out = out if out is not None else self._outputs(nq)
-        self._check(self.lib.apples_place_batch_bytes(self.h, nq, _lib.ptr(mat), mat.shape[1], _lib.ptr(self_node),
-                                                      _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
+        # rows may be padded (the native reader's matrix: row stride = L rounded up to 16): the stride is passed on
+        self._check(self.lib.apples_place_batch_bytes(self.h, nq, mat.ctypes.data, mat.strides[0] if nq else self.L,
+                                                      _lib.ptr(self_node), _lib.C.byref(params), *[_lib.ptr(o) for o in out]))
         return out
 
     def place_rows(self, rows, self_node, params, out=None):
@@ -334,7 +336,8 @@ class MultiGpuPlacer:
         return out
 
     def place_bytes(self, mat, self_node, params):
-        mat = np.ascontiguousarray(mat, dtype=np.uint8)
+        if not (mat.dtype == np.uint8 and mat.ndim == 2 and mat.strides[1] == 1):
+            mat = np.ascontiguousarray(mat, dtype=np.uint8)
         return self._sharded('place_bytes', mat, self_node, params)
 
     def place_rows(self, rows, self_node, params):
@@ -423,6 +426,72 @@ def place_arrays(reference, options, name_to_node_map, queries, tree=None, place
             from .parallel import gather_placements
             out = gather_placements(out, len(queries))
         return names, in_backbone, out
+    finally:
+        if own:
+            placer.close()
+
+
+def log_messages(names, in_backbone, out, exclude_intplace=False):
+    """The warnings / stderr lines PoolQueryWorker.runquery emits (PoolQueryWorker.py:63-70, 97-98, 121-130), from the
+    result arrays: only the special records are visited.  Raises on degenerate systems like results_to_jplace."""
+    st_arr = np.asarray(out[4])
+    bad = np.flatnonzero(st_arr & _lib.FLAG_DEGENERATE)
+    if bad.size:
+        raise ZeroDivisionError('float division by zero: the least-squares system of query %s is singular on at least '
+                                'one edge (the reference raises in util.solve2_2 as well)' % names[int(bad[0])])
+    code = st_arr & _lib.STATUS_CODE_MASK
+    inb = np.asarray(in_backbone, dtype=bool)
+    for i in np.flatnonzero(inb | (code == _lib.TOO_FEW_DISTANCES) | (code == _lib.PLACED_MISPLACEMENT_FLAG)).tolist():
+        name = names[i]
+        if inb[i]:
+            logging.warning('The query named %s exists in the backbone. Changing its name to %s-query.' % (name, name))
+            name = name + '-query'
+        if code[i] == _lib.TOO_FEW_DISTANCES:
+            sys.stderr.write('Taxon {} cannot be placed. At least three non-infinity distances '
+                             'should be observed to place a taxon. '
+                             'Consequently, this taxon is ignored (no output).\n'.format(name))
+        elif code[i] == _lib.PLACED_MISPLACEMENT_FLAG:
+            ignored = ' Consequently, this sequence is ignored (no output).' if exclude_intplace else ''
+            logging.warning('Best placement for query sequence %s has zero pendant edge length and placed at '
+                            'an internal node with a non-zero least squares error. This is a potential '
+                            'misplacement.%s' % (name, ignored))
+
+
+def place_alignment(reference, options, name_to_node_map, names, mat, tree=None, placer=None, device=0, devices=None):
+    """Array-level twin of place_batch for alignment input: `names` (list of str) and `mat` (uint8 [n, L] alignment bytes
+    as fasta2dic / the native reader leave them, e.g. FastaMatrix.matrix).  Returns (in_backbone, (edge, error, distal,
+    pendant, status)) for all queries in input order -- no per-query Python objects, so a million queries cost
+    milliseconds of host time.  Sharding over `devices` / torch.distributed ranks as in place_arrays."""
+    rank, world = _distributed_world()
+    n = len(names)
+    lo, hi = 0, n
+    if world > 1:
+        from .parallel import shard_bounds
+        lo, hi = shard_bounds(n, world)[rank]
+    own = placer is None
+    if placer is None:
+        if tree is None:
+            raise ValueError('place_alignment needs the BackboneTree (tree=) or a GpuPlacer (placer=)')
+        devs = [int(d) for d in devices] if devices else [int(device)]
+        devs = devs[:max(1, min(len(devs), hi - lo))]
+        if len(devs) > 1:
+            placer = MultiGpuPlacer(tree, reference, name_to_node_map, devices=devs)
+        else:
+            placer = GpuPlacer(tree, reference, name_to_node_map, device=devs[0])
+    try:
+        n2n = placer.name_to_node
+        in_backbone = np.fromiter((nm in n2n for nm in names), dtype=bool, count=n)
+        self_node = np.full(hi - lo, -1, np.int32)
+        for i in np.flatnonzero(in_backbone[lo:hi]).tolist():
+            self_node[i] = n2n[names[lo + i]]
+        params = placer.params_from_options(options, reference)
+        if mat.shape[1] != placer.L:
+            raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], placer.L))
+        out = placer.place_bytes(mat[lo:hi], self_node, params) if hi > lo else placer._outputs(0)
+        if world > 1:
+            from .parallel import gather_placements
+            out = gather_placements(out, n)
+        return in_backbone, out
     finally:
         if own:
             placer.close()

@@ -38,7 +38,12 @@ class ReducedReference:
         tree        -- an already parsed BackboneTree for `tree_file`;
         refs        -- an already loaded {name: 'S1' row} dict (skips reading ref_fp).
         """
-        self.refs = refs if refs is not None else _fasta.fasta2dic(ref_fp, prot_flag, False)
+        self._fm = None
+        if refs is None:
+            # native reader (hostio.cpp): one byte matrix for the whole alignment, `refs` holds views into it
+            self._fm = _fasta.read_alignment(ref_fp, prot_flag, False, pinned=False)
+            refs = self._fm.as_dict(copy=False)
+        self.refs = refs
         self.prot_flag = bool(prot_flag)
         self.threshold = threshold
         self.baseobs = None
@@ -103,6 +108,20 @@ class ReducedReference:
     def set_baseobs(self, baseobs):
         self.baseobs = baseobs
 
+    def __getstate__(self):
+        # the pickled database owns its sequences (the reader's buffer is not part of it)
+        d = dict(self.__dict__)
+        if d.get('_fm') is not None:
+            d['refs'] = {k: v.copy() for k, v in self.refs.items()}
+            d['_fm'] = None
+        return d
+
+    def _byte_matrix(self, names, L):
+        fm = getattr(self, '_fm', None)
+        if fm is not None and fm.uniform and fm.n == len(names) and fm.names == names:
+            return np.ascontiguousarray(fm.matrix)   # one strided copy instead of a Python loop over 200 000 rows
+        return _fasta.as_byte_matrix([self.refs[n] for n in names], L)
+
     def get_obs_dist(self, query_seq, query_tag, overlap_frac):
         raise RuntimeError('ReducedReference.get_obs_dist is computed on the GPU by apples_b200.placer.place_batch; '
                            'there is no CPU path in this package')
@@ -119,7 +138,7 @@ class ReducedReference:
             members.extend(row_of[g] for g in group)
             offs[i + 1] = len(members)
         return dict(kind=_fasta.AA if self.prot_flag else _fasta.NUC, L=L, ref_names=names,
-                    ref_bytes=_fasta.as_byte_matrix([self.refs[n] for n in names], L),
+                    ref_bytes=self._byte_matrix(names, L),
                     ref_node=np.array([name_to_node.get(n, -1) for n in names], dtype=np.int32),
                     group_offsets=offs, group_members=np.asarray(members, dtype=np.int32))
 
@@ -134,7 +153,7 @@ class ReducedReference:
         row_of = {n: i for i, n in enumerate(names)}
         kind = _fasta.AA if self.prot_flag else _fasta.NUC
         L = len(self.refs[names[0]]) if names else 0
-        mat = _fasta.as_byte_matrix([self.refs[n] for n in names], L)
+        mat = self._byte_matrix(names, L)
         rep_mat = _fasta.as_byte_matrix([r[0] for r in self.representatives], L)
         offs = np.zeros(len(self.representatives) + 1, dtype=np.int32)
         members = []

@@ -43,6 +43,7 @@ def parse(argv=None):
     ap.add_argument('--cpu-sample', type=int, default=0, help='queries in the CPU-baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cli', action='store_true', help='skip the run_apples.py command-line measurement (cli_e2e)')
     ap.add_argument('--slot-cap', type=int, default=0, help='observed-list slots per query before a rerun (0 = library default)')
     ap.add_argument('--sub-batch', type=int, default=0, help='queries per dense/selection launch (0 = library default)')
     return ap.parse_args(argv)
@@ -142,7 +143,7 @@ def build_workload(args, device, rank, want_host_refs):
     info = {'setup_s': round(time.time() - t0, 1), 'n_rep': len(ordered), 'max_level': int(tree.level.max())}
     host = None
     if want_host_refs:
-        host = dict(nwk=nwk, ref_host=ref_host, reps=reps, ordered=ordered, leaf_row=leaf_row, q_bytes=q_bytes)
+        host = dict(nwk=nwk, ref_host=ref_host, reps=reps, ordered=ordered, clusters=clusters, leaf_row=leaf_row, q_bytes=q_bytes)
     return tree, arrays, packed_q, q_bytes, info, host
 
 
@@ -171,6 +172,62 @@ def cpu_baseline(ctx, q_host, threads):
     res = orc.run_pool(ctx, queries, threads)
     dt = time.time() - t0
     return len(queries) / dt, dt, res
+
+
+def write_fasta(path, names, mat):
+    """uint8 [n, L] rows + fixed-width names -> FASTA text, vectorised (setup, untimed)."""
+    n, L = mat.shape
+    w = max(len(x) for x in names)
+    assert all(len(x) == w for x in names)
+    out = np.empty((n, w + 2 + L + 1), dtype=np.uint8)
+    out[:, 0] = ord('>')
+    out[:, 1:1 + w] = np.frombuffer(''.join(names).encode(), dtype=np.uint8).reshape(n, w)
+    out[:, 1 + w] = ord('\n')
+    out[:, 2 + w:2 + w + L] = mat
+    out[:, -1] = ord('\n')
+    with open(path, 'wb') as f:
+        f.write(out.tobytes())
+
+
+def cli_e2e(args, tree, host, q_bytes, device):
+    """run_apples.py as a user runs it: reference FASTA + tree + cluster TSV + query FASTA on disk in, jplace on disk out.
+    The files are written first (untimed); everything run_apples.main does is timed, stage by stage (its own timers)."""
+    import shutil
+    import tempfile
+    import run_apples
+    from apples_b200 import treecluster
+    wd = tempfile.mkdtemp(prefix='apples_cli_')
+    try:
+        names = [tree.label[u] for u in tree.leaf_ids.tolist()]
+        write_fasta(os.path.join(wd, 'ref.fa'), names, host['ref_host'])
+        q_host = q_bytes.cpu().numpy()
+        write_fasta(os.path.join(wd, 'query.fa'), ['Q%07d' % i for i in range(q_host.shape[0])], q_host)
+        with open(os.path.join(wd, 'backbone.nwk'), 'w') as f:
+            f.write(host['nwk'])
+        treecluster.write_cluster_tsv(tree, host['clusters'], os.path.join(wd, 'clusters.tsv'))
+        out = os.path.join(wd, 'out.jplace')
+        argv = ['-s', os.path.join(wd, 'ref.fa'), '-q', os.path.join(wd, 'query.fa'), '-t', os.path.join(wd, 'backbone.nwk'),
+                '--clusters', os.path.join(wd, 'clusters.tsv'), '-D', '-m', args.method, '-c', args.criterion, '-o', out,
+                '--device', str(device), '--gpus', '1']
+        import logging
+        lvl = logging.getLogger().level
+        logging.getLogger().setLevel(logging.ERROR)
+        t0 = time.time()
+        run_apples.main(argv)
+        wall = time.time() - t0
+        logging.getLogger().setLevel(lvl)
+        t = dict(run_apples.LAST_TIMINGS)
+        nq = int(t.get('queries', 0))
+        qpath = t.get('read_queries_s', 0.0) + t.get('place_s', 0.0) + t.get('write_s', 0.0)
+        return {'queries': nq, 'wall_s': wall, 'queries_per_s': nq / wall,
+                'query_path_s': qpath, 'query_path_queries_per_s': nq / qpath if qpath else None,
+                'stages_s': {k: round(v, 3) for k, v in t.items() if k.endswith('_s')},
+                'jplace_bytes': os.path.getsize(out),
+                'note': 'setup_s = tree parsing, reference FASTA, clustering file, options (once per run); query path = '
+                        'native FASTA reader -> apples_place_batch_bytes (context creation + reference upload included) -> '
+                        'native jplace writer'}
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
 
 
 def main():
@@ -232,7 +289,7 @@ def main():
     device = 'cuda:%d' % local_rank
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device(device))
-    want_host = (rank == 0 and not args.no_cpu_baseline)
+    want_host = rank == 0 and world == 1 and not (args.no_cpu_baseline and args.no_cli)
     tree, arrays, packed_q, q_bytes, info, host = build_workload(args, device, rank, want_host)
     nq = args.queries_per_gpu
     pl = GpuPlacer(tree, None, tree.name_to_node, device=local_rank)
@@ -446,6 +503,10 @@ def main():
             'placement_classes_per_step': {k: tm[k] / args.steps for k in ('placed_smem64', 'placed_smem128', 'placed_smem256', 'placed_smem512', 'placed_block')}, 'max_observed': tm['max_observed'],
             'max_valid_nodes': tm['max_valid_nodes'], 'gpu_launches': int(tm['launches']), 'result_sha1_per_block': block_hashes, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_select': roofline_select,
             'roofline_place': roofline_place, 'setup': info}
+
+    # ---- the command line end to end (rank 0, N = 1): FASTA text on disk -> run_apples.py -> jplace on disk ----
+    if not args.no_cli and world == 1 and host is not None:
+        line['cli_e2e'] = cli_e2e(args, tree, host, q_bytes, local_rank)
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same queries ----
     if not args.no_cpu_baseline and world == 1:

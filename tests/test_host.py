@@ -235,3 +235,72 @@ def test_results_to_jplace_fast_path_equals_per_record_logic():
             exp = {'placements': [{'p': [p], 'n': [name]}]}
             assert got[i] == exp, i
             assert [type(x) for x in got[i]['placements'][0]['p'][0]] == [type(x) for x in p], i
+
+
+def test_native_fasta_reader_equals_python_twin(tmp_path, workdir):
+    """hostio.cpp apples_fasta_open (C++ twin of fasta2dic) gives the same names and bytes as the Python
+    fasta2dic on the fixtures and on a file with multi-line records, FASTQ records, CRLF, blank lines, lower case, letters
+    outside the alphabet and non-letter symbols; nucleotide / protein x mask on / off."""
+    from apples_b200 import fasta
+    files = [(util.gunzip_to('ref.fa', workdir), False), (util.gunzip_to('query.fa', workdir), False),
+             (util.gunzip_to('prot_query.fa', workdir), True)]
+    edge = tmp_path / 'edge.fa'
+    with open(edge, 'w', newline='') as f:
+        f.write('junk before\n>a desc here\nacgtNn-\r\nAC.GT\n\n>b\nACGTacgtXYZ\n@fq1 x\nACGTN\n+\nIIIII\n@fq2\nAC\nGT\n+fq2\nII\nII\n'
+                '>dup\nAAAA\n>dup\nCCCC\n>last\nACGT*?')
+    files += [(str(edge), False), (str(edge), True)]
+    for fp, prot in files:
+        for mask in (False, True):
+            d = fasta.fasta2dic(fp, prot, mask)
+            m = fasta.read_alignment(fp, prot, mask, pinned=False)
+            d2 = m.as_dict()
+            assert list(d) == list(d2), fp
+            for k in d:
+                assert d[k].tobytes() == d2[k].tobytes(), (fp, k, mask)
+            assert m.n >= len(d) and m.stride % 16 == 0 and m.stride >= m.L
+            if m.uniform and m.n:
+                assert (m.full[:, m.L:] == ord('-')).all()
+            m.close()
+    with pytest.raises(OSError):
+        fasta.read_alignment(str(tmp_path / 'missing.fa'))
+
+
+def test_native_jplace_writer_equals_python_writer(tmp_path):
+    """hostio.cpp apples_jplace_write writes, from the result arrays, the bytes that
+    json.dumps(join_jplace(per-query dicts), sort_keys=True, indent=4) gives (run_apples.py:106-118, jutil.py:1-19):
+    Python float repr (exponent thresholds, -0.0, denormals, nan/inf spellings), int 0 where the reference has ints,
+    ASCII escapes of names incl. non-BMP characters, '-query' names, --exclude, the first-record quirk, empty lists."""
+    import json
+    from apples_b200 import jplace
+    from apples_b200.placer import results_to_jplace
+    vals = [0.0, -0.0, 1e-5, 1e-4, 0.0001234, 1e15, 1e16, 1.5e-7, 123456789.123, float('nan'), float('inf'), -float('inf'),
+            5e-324, 1.7976931348623157e308, 0.1, 1 / 3, 2.0, 100.0, 1e22, 1e21, 123456789012345680.0, 9999999999999998.0]
+
+    def case(n, first_bad, seed):
+        rng = np.random.default_rng(seed)
+        names = ['q%d' % i for i in range(n)]
+        if n > 3:
+            names[1], names[2], names[3] = 'na\u00efve "q"\\t\u2603', '\U0001F600x', 'tab\there\x7f'
+        edge = rng.integers(0, 1000, n).astype(np.int32)
+
+        def col():
+            a = rng.random(n) * rng.choice([1e-18, 1e-9, 1e-3, 1.0, 1e6], n)
+            k = min(n, len(vals))
+            a[:k] = vals[:k]
+            rng.shuffle(a)
+            return a
+        status = rng.choice([0, 0, 0, 0, 1, 2, 3, 0x100, 0x103], n).astype(np.int32)
+        if first_bad:
+            status[0] = 2
+        return names, rng.random(n) < 0.1, (edge, col(), col(), col(), status)
+    fp = str(tmp_path / 'o.jplace')
+    for n, fb, ex, seed in [(1, False, False, 1), (1, True, False, 2), (2, True, True, 3), (40, False, False, 4),
+                            (40, True, True, 5), (9000, False, True, 6), (3, True, False, 7)]:
+        names, inb, out = case(n, fb, seed)
+        res = results_to_jplace(names, inb.tolist(), out, ex, log=False, degenerate='keep')
+        doc = jplace.assemble(res, '((a,b),c);', argv=['run_apples.py', '-x'])
+        ref = json.dumps(doc, sort_keys=True, indent=4) + '\n'
+        for th in (1, 3, 0):
+            nw = jplace.write_arrays(fp, names, inb, out, '((a,b),c);', ex, argv=['run_apples.py', '-x'], threads=th)
+            assert open(fp, encoding='utf-8').read() == ref, (n, fb, ex, th)
+            assert nw == len(doc['placements'])
