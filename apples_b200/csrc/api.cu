@@ -41,6 +41,9 @@ struct apples_ctx {
     // reference
     int kind = -1, L = 0, W = 0, Wp = 0, Lp = 0, n_ref = 0, n_rep = 0, rep_pad = 0, ref_pad = 0;
     DevBuf refs_rm, reps_rm, reps_wm, refs_wm, reps_nv, refs_nv, q_nv, ref_node, goff, gmem;
+    DevBuf aa_tab, reps_aa_tm, reps_aav, refs_aa_tm, refs_aav, q_aa_tm, q_aav, aa_valid;   // amino-acid dense kernel operands
+    int aa_rep_pad = 0, aa_ref_pad = 0;
+    bool refs_aa_ready = false;
     bool refs_wm_ready = false;
     // matrix mode
     int n_cols = 0;
@@ -201,6 +204,33 @@ int check_leaf_ids(apples_ctx* ctx, const char* what, const int32_t* ids, int n)
     return 0;
 }
 
+const double k_blosum45[441] = {
+#include "blosum45.inc"
+};
+
+inline int aa_chunks(int Lp) { return (Lp + AA_CH - 1) / AA_CH; }
+
+// amino-acid operands of the dense kernel: limb tables (once) and the tile-major copy + valid planes of the representatives
+int aa_prepare_reps(apples_ctx* ctx, cudaStream_t s) {
+    if (!ctx->aa_tab.p) {
+        uint32_t tab[AA_TAB_WORDS];
+        aa_build_tables(k_blosum45, tab);
+        if (ensure(ctx, ctx->aa_tab, sizeof tab)) return -1;
+        CK(cudaMemcpy(ctx->aa_tab.p, tab, sizeof tab, cudaMemcpyHostToDevice));
+    }
+    const int nc = aa_chunks(ctx->Lp);
+    ctx->aa_rep_pad = round_up(ctx->n_rep, AA_TR);
+    ctx->aa_ref_pad = round_up(ctx->n_ref, AA_TR);
+    ctx->refs_aa_ready = false;
+    if (ensure(ctx, ctx->reps_aa_tm, (size_t)ctx->aa_rep_pad * nc * AA_CH) ||
+        ensure(ctx, ctx->reps_aav, (size_t)ctx->aa_rep_pad * nc * (AA_CH / 32) * 4))
+        return -1;
+    launch_aa_layout((const uint8_t*)ctx->reps_rm.p, ctx->n_rep, ctx->Lp, AA_TR, ctx->aa_rep_pad, (uint8_t*)ctx->reps_aa_tm.p,
+                     (uint32_t*)ctx->reps_aav.p, s);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 TreeDev tree_dev(apples_ctx* ctx) {
     TreeDev t;
     t.M = ctx->M;
@@ -278,6 +308,12 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_nv, (size_t)QB * 4)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->clk_probe, 32)) return -1;
+        if (sel_kind == SEL_AA) {
+            const size_t qp = (size_t)round_up(QB, AA_TQ), nc = (size_t)aa_chunks(ctx->Lp);
+            if (ensure(ctx, ctx->q_aa_tm, qp * nc * AA_CH) || ensure(ctx, ctx->q_aav, qp * nc * (AA_CH / 32) * 4) ||
+                ensure(ctx, ctx->aa_valid, (size_t)QB * ldk * 4))
+                return -1;
+        }
     }
     if (ensure(ctx, ctx->self_node, (size_t)n * 4)) return -1;
     if (ensure(ctx, ctx->obs_node, (size_t)n * cap * 4)) return -1;
@@ -384,10 +420,20 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             }
             ctx->n_pairs += (double)nb * ctx->n_rep;
         } else if (sel_kind == SEL_AA) {
+            const int q_pad = round_up(nb, AA_TQ);
+            const int nc = aa_chunks(ctx->Lp);
+            {
+                Span sp(ctx, T_TRANSPOSE);
+                launch_aa_layout((const uint8_t*)d_q, nb, ctx->Lp, AA_TQ, q_pad, (uint8_t*)ctx->q_aa_tm.p, (uint32_t*)ctx->q_aav.p, s);
+                ctx->n_launch += 1;
+            }
+            (void)nc;
             Span sp(ctx, T_DENSE);
-            launch_dense_aa((const uint8_t*)d_q, nb, (const uint8_t*)ctx->reps_rm.p, ctx->n_rep, ctx->Lp, ctx->L,
-                            prm->overlap_frac, (double*)ctx->keys.p, ldk, nullptr, s);
-            ctx->n_launch += 1;
+            launch_dense_aa((const uint8_t*)ctx->q_aa_tm.p, (const uint32_t*)ctx->q_aav.p, q_pad, nb,
+                            (const uint8_t*)ctx->reps_aa_tm.p, (const uint32_t*)ctx->reps_aav.p, ctx->aa_rep_pad, ctx->n_rep,
+                            ctx->Lp, ctx->L, prm->overlap_frac, (const uint32_t*)ctx->aa_tab.p, (uint32_t*)ctx->aa_valid.p, ldk,
+                            (double*)ctx->keys.p, ldk, s);
+            ctx->n_launch += 2;
             ctx->n_dense_launch += 1;
             ctx->n_pairs += (double)nb * ctx->n_rep;
         }
@@ -819,7 +865,8 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
-                     &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
+                     &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->aa_tab, &ctx->reps_aa_tm, &ctx->reps_aav,
+                     &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
@@ -916,6 +963,10 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
     CK(cudaMemcpy(ctx->ref_node.p, ref_node, (size_t)n_ref * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->goff.p, group_offsets, (size_t)(n_rep + 1) * 4, cudaMemcpyHostToDevice));
     if (n_mem) CK(cudaMemcpy(ctx->gmem.p, group_members, (size_t)n_mem * 4, cudaMemcpyHostToDevice));
+    if (kind == APPLES_AA) {
+        if (aa_prepare_reps(ctx, ctx->stream)) return -1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (kind == APPLES_NUC) {
         const size_t wm = (size_t)3 * ctx->Wp * ctx->rep_pad * 4;
         if (ensure(ctx, ctx->reps_wm, wm)) return -1;
@@ -1025,6 +1076,10 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
     if (bad) {
         ctx->kind = -1;
         return fail(ctx, "reference alignment contains bytes the 2-bit nucleotide packing cannot express (only A,C,G,T,-)");
+    }
+    if (kind == APPLES_AA) {
+        if (aa_prepare_reps(ctx, s)) return -1;
+        CK(cudaStreamSynchronize(s));
     }
     if (kind == APPLES_NUC) {
         const size_t wm = (size_t)3 * ctx->Wp * ctx->rep_pad * 4;
@@ -1152,8 +1207,20 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
                               ctx->n_ref, ctx->W, ctx->Wp, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p, (uint32_t*)dv.p,
                               (double*)dd.p, ctx->num_sms, s);
     } else {
-        launch_dense_aa((const uint8_t*)dq.p, (int)nq, (const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, ctx->L,
-                        overlap_frac, (double*)dd.p, ctx->n_ref, (uint32_t*)dv.p, s);
+        const int nc = aa_chunks(ctx->Lp);
+        if (!ctx->refs_aa_ready) {
+            if (ensure(ctx, ctx->refs_aa_tm, (size_t)ctx->aa_ref_pad * nc * AA_CH) ||
+                ensure(ctx, ctx->refs_aav, (size_t)ctx->aa_ref_pad * nc * (AA_CH / 32) * 4)) { cleanup(); return -1; }
+            launch_aa_layout((const uint8_t*)ctx->refs_rm.p, ctx->n_ref, ctx->Lp, AA_TR, ctx->aa_ref_pad,
+                             (uint8_t*)ctx->refs_aa_tm.p, (uint32_t*)ctx->refs_aav.p, s);
+            ctx->refs_aa_ready = true;
+        }
+        const int q_pad = round_up((int)nq, AA_TQ);
+        if (ensure(ctx, qwm, (size_t)q_pad * nc * AA_CH) || ensure(ctx, qnv, (size_t)q_pad * nc * (AA_CH / 32) * 4)) { cleanup(); return -1; }
+        launch_aa_layout((const uint8_t*)dq.p, (int)nq, ctx->Lp, AA_TQ, q_pad, (uint8_t*)qwm.p, (uint32_t*)qnv.p, s);
+        launch_dense_aa((const uint8_t*)qwm.p, (const uint32_t*)qnv.p, q_pad, (int)nq, (const uint8_t*)ctx->refs_aa_tm.p,
+                        (const uint32_t*)ctx->refs_aav.p, ctx->aa_ref_pad, ctx->n_ref, ctx->Lp, ctx->L, overlap_frac,
+                        (const uint32_t*)ctx->aa_tab.p, (uint32_t*)dv.p, ctx->n_ref, (double*)dd.p, ctx->n_ref, s);
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(mism, dm.p, n_out * 4, cudaMemcpyDeviceToHost, s);

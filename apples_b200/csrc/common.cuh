@@ -35,6 +35,16 @@ constexpr int DT_STAGE_WORDS = 3 * DT_WC * (DT_TQ + DT_TR);
 constexpr int DT_STAGE_BYTES = DT_STAGE_WORDS * 4;
 constexpr int DT_SMEM_BYTES = DT_STAGES * DT_STAGE_BYTES + 2 * DT_STAGES * 8 + 16;
 
+// tile shape of the dense amino-acid kernel (distance.cu)
+constexpr int AA_CH = 64;        // sites per pipeline stage
+constexpr int AA_TR = 256;       // references per CTA tile (2 per thread)
+constexpr int AA_TQ = 8;         // queries per CTA tile
+constexpr int AA_THREADS = 128;
+constexpr int AA_TABW = 32;      // table row pitch in words
+constexpr int AA_LIMB = 22;      // bits of the low limb
+constexpr int AA_FRAC = 43;      // fixed-point fraction bits
+constexpr int AA_TAB_WORDS = 2 * 21 * AA_TABW;
+
 // internal per-query status used between the selection and the placement kernel
 constexpr int ST_PLACE = 0;      // observed set ready, go on to placement
 constexpr int ST_ZERO = 1;       // zero-distance shortcut, zero_edge holds the leaf
@@ -173,8 +183,11 @@ void launch_dense_nuc_keys(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad
 void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad, int nq, const uint32_t* r_wm,
                            const uint32_t* r_nv, int r_pad, int n_ref, int W, int Wp, int vmin, uint32_t* mism, uint32_t* valid,
                            double* dist, int num_sms, cudaStream_t s);
-void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
-                     int64_t ldd, uint32_t* valid_out, cudaStream_t s);
+void launch_aa_layout(const uint8_t* codes, int rows, int Lp, int T, int rows_pad, uint8_t* tm, uint32_t* vm, cudaStream_t s);
+void launch_dense_aa(const uint8_t* q_tm, const uint32_t* q_vm, int q_pad, int nq, const uint8_t* r_tm, const uint32_t* r_vm,
+                     int r_pad, int n_r, int Lp, int L, double overlap, const uint32_t* tab, uint32_t* valid, int64_t ldv,
+                     double* dist, int64_t ldd, cudaStream_t s);
+void aa_build_tables(const double* blosum441, uint32_t* out);
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
 cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s);
 cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s);

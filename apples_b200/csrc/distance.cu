@@ -406,71 +406,206 @@ void launch_dense_nuc_full(const uint32_t* q_wm, const uint32_t* q_nv, int q_pad
 
 // ---------------------------------------------------------------------------------------------------------------
 // dense amino-acid kernel: dist[q][r] = scoredist(q, r)  (distance.py:681-715)
-// one thread per reference row, AA_TQ queries per block held in shared memory, BLOSUM45 (21x21, gap row/col = 0)
-// in shared memory.  fp64 table sum per pair; the summation order differs from numpy's BLAS ddot (distance.py:706),
-// parity target 1e-9 relative.
+//
+// Work per (query, reference, site): one BLOSUM45 lookup and one accumulation -- a table-lookup kernel, bound by the
+// shared-memory pipe, not by HBM or the fp64 pipe.  Design:
+//   * codes are one byte per site (0..19 amino acids in a2i order, 20 = gap).  The north star sketches 5-bit packing; with
+//     a lookup per site the code is an ADDRESS, so a byte per site (no shift / mask per lookup) is the faster form of
+//     the same 21-letter alphabet, and the operands are small anyway (1.6 kB per sequence at config 3);
+//   * the table is held in shared memory as 44-bit FIXED POINT split into two 22-bit limbs (two uint32 tables of 21 rows
+//     x 32 columns): value = round(B * 2^43).  The integer sums are exact and order-independent; the quantisation is
+//     2^-44 per site (5e-14 relative on a sum of ~1e3, four orders below the 1e-9 parity tolerance, and below the
+//     summation-order noise of the reference's BLAS ddot).  A row has 21 used columns, so the 32 lanes of a warp -- same
+//     query symbol, 32 different references -- hit 21 distinct banks or broadcast: both lookups are conflict-free
+//     (an fp64 table is 2-way conflicted by construction: 21 entries on 16 eight-byte banks);
+//   * reference tiles (256 references x 64 sites = 16 KB, tile-major in global memory so a stage is one contiguous block)
+//     and query tiles (8 queries x 64 sites) are staged by 1-D TMA bulk copies (cp.async.bulk + mbarrier), two stages;
+//   * a thread owns 2 references x 8 queries: the reference bytes of 8 sites are unpacked once into table column
+//     offsets and reused for the 8 queries; the query codes are expanded once per stage into table row offsets
+//     (broadcast LDS.128), so a lookup costs 1 address add + 2 LDS.32 + 1 accumulation (IADD3 takes two sites);
+//   * 32-bit limb sums are flushed into a 64-bit total every 1024 sites; valid-site counts come from bit-planes
+//     (aa_valid_kernel, popc(qv & rv)) computed beside the codes.
 // ---------------------------------------------------------------------------------------------------------------
-__constant__ double c_blosum45[441] = {
-#include "blosum45.inc"
+// codes [rows][Lp] -> tile-major [rows_pad / T][n_chunks][T][AA_CH] (padding = gap) and valid bit-planes, word-major
+// [Wv][rows_pad] (bit s % 32 of word s / 32 = site s is not a gap); block (32, 8): x = site in a 32-site word
+__global__ void aa_layout_kernel(const uint8_t* __restrict__ codes, int rows, int Lp, int T, int rows_pad, int n_chunks,
+                                 uint8_t* __restrict__ tm, uint32_t* __restrict__ vm) {
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    const int s = blockIdx.x * 32 + threadIdx.x;
+    if (r >= rows_pad) return;
+    uint8_t c = 20;
+    if (r < rows && s < Lp) c = codes[(size_t)r * Lp + s];
+    tm[(((size_t)(r / T) * n_chunks + s / AA_CH) * T + r % T) * AA_CH + s % AA_CH] = c;
+    const uint32_t v = __ballot_sync(0xffffffffu, c != 20);
+    if (threadIdx.x == 0) vm[(size_t)blockIdx.x * rows_pad + r] = v;
+}
+
+void launch_aa_layout(const uint8_t* codes, int rows, int Lp, int T, int rows_pad, uint8_t* tm, uint32_t* vm, cudaStream_t s) {
+    const int n_chunks = (Lp + AA_CH - 1) / AA_CH;
+    dim3 grid(n_chunks * (AA_CH / 32), (rows_pad + 7) / 8), block(32, 8);
+    aa_layout_kernel<<<grid, block, 0, s>>>(codes, rows, Lp, T, rows_pad, n_chunks, tm, vm);
+}
+
+// valid[q][r] = sites where neither sequence has a gap (distance.py:698-699); lanes = consecutive references
+__global__ void aa_valid_kernel(const uint32_t* __restrict__ qv, int q_pad, int nq, const uint32_t* __restrict__ rv, int r_pad,
+                                int n_r, int Wv, uint32_t* __restrict__ valid, int64_t ldv) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q0 = blockIdx.y * 8;
+    if (r >= n_r) return;
+    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int w = 0; w < Wv; ++w) {
+        const uint32_t x = rv[(size_t)w * r_pad + r];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] += __popc(x & qv[(size_t)w * q_pad + min(q0 + k, q_pad - 1)]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (q0 + k < nq) valid[(size_t)(q0 + k) * ldv + r] = c[k];
+}
+
+struct DenseAaArgs {
+    const uint8_t* q_tm;     // [q_pad / AA_TQ][n_chunks][AA_TQ][AA_CH]
+    const uint8_t* r_tm;     // [r_pad / AA_TR][n_chunks][AA_TR][AA_CH]
+    const uint32_t* tab;     // [2][21][AA_TABW] limbs (high, low)
+    const uint32_t* valid;   // [nq][ldv] from aa_valid_kernel
+    int64_t ldv;
+    int nq, n_r, n_chunks, L;
+    double overlap;
+    double* dist;            // [nq][ldd]
+    int64_t ldd;
 };
 
-constexpr int AA_TQ = 4;
-constexpr int AA_THREADS = 128;
-constexpr int AA_CHUNK = 1024;  // sites of the query tile staged per pass
-
-__global__ void __launch_bounds__(AA_THREADS) dense_aa_kernel(const uint8_t* __restrict__ q, int nq,
-                                                               const uint8_t* __restrict__ r, int n_r, int Lp, int L,
-                                                               double overlap, double* __restrict__ dist, int64_t ldd,
-                                                               uint32_t* __restrict__ valid_out) {
-    __shared__ double tab[441];
-    __shared__ __align__(16) uint8_t qs[AA_TQ][AA_CHUNK];
-    for (int i = threadIdx.x; i < 441; i += AA_THREADS) tab[i] = c_blosum45[i];
-    const int q0 = blockIdx.y * AA_TQ;
-    const int row = blockIdx.x * AA_THREADS + threadIdx.x;
-    double sum[AA_TQ];
-    uint32_t val[AA_TQ];
-#pragma unroll
-    for (int k = 0; k < AA_TQ; ++k) { sum[k] = 0.0; val[k] = 0u; }
-    for (int c0 = 0; c0 < Lp; c0 += AA_CHUNK) {
-        const int clen = min(AA_CHUNK, Lp - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < AA_TQ * (clen / 16); i += AA_THREADS) {
-            const int k = i / (clen / 16), x = i % (clen / 16);
-            uint4 v = make_uint4(0x14141414u, 0x14141414u, 0x14141414u, 0x14141414u);  // gaps
-            if (q0 + k < nq) v = *reinterpret_cast<const uint4*>(q + (size_t)(q0 + k) * Lp + c0 + 16 * x);
-            *reinterpret_cast<uint4*>(&qs[k][16 * x]) = v;
-        }
-        __syncthreads();
-        if (row < n_r) {
-            const uint8_t* rr = r + (size_t)row * Lp + c0;
-            for (int x = 0; x < clen; x += 16) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rr + x);
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    const uint32_t rc = (rw[b >> 2] >> (8 * (b & 3))) & 0xffu;
-#pragma unroll
-                    for (int k = 0; k < AA_TQ; ++k) {
-                        const uint32_t qc = qs[k][x + b];
-                        sum[k] += tab[qc * 21 + rc];
-                        val[k] += (qc < 20u && rc < 20u) ? 1u : 0u;
-                    }
-                }
-            }
-        }
+__global__ void __launch_bounds__(AA_THREADS) dense_aa_kernel(const DenseAaArgs a) {
+    constexpr int STAGE_BYTES = (AA_TR + AA_TQ) * AA_CH;
+    __shared__ __align__(128) unsigned char s_stage[2][STAGE_BYTES];
+    __shared__ __align__(16) uint32_t s_qoff[AA_TQ][AA_CH];   // table row offsets (bytes) of the stage's query codes
+    __shared__ uint32_t s_tab[2 * 21 * AA_TABW];
+    __shared__ uint64_t s_bar[2];
+    const int tid = threadIdx.x;
+    const int rt = blockIdx.x, qt = blockIdx.y;
+    for (int i = tid; i < 2 * 21 * AA_TABW; i += AA_THREADS) s_tab[i] = a.tab[i];
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (row < n_r) {
+    __syncthreads();
+    auto issue = [&](int c) {
+        const int st = c & 1;
+        mbar_arrive_expect_tx(&s_bar[st], STAGE_BYTES);
+        tma_bulk_g2s(s_stage[st], a.r_tm + ((size_t)rt * a.n_chunks + c) * (AA_TR * AA_CH), AA_TR * AA_CH, &s_bar[st]);
+        tma_bulk_g2s(s_stage[st] + AA_TR * AA_CH, a.q_tm + ((size_t)qt * a.n_chunks + c) * (AA_TQ * AA_CH), AA_TQ * AA_CH,
+                     &s_bar[st]);
+    };
+    if (tid == 0) issue(0);
+
+    uint32_t ah[AA_TQ][2], al[AA_TQ][2];
+    uint64_t tot[AA_TQ][2];
 #pragma unroll
-        for (int k = 0; k < AA_TQ; ++k)
-            if (q0 + k < nq) {
-                dist[(size_t)(q0 + k) * ldd + row] = scoredist_from_sum(sum[k], val[k], L, overlap);
-                if (valid_out) valid_out[(size_t)(q0 + k) * ldd + row] = val[k];
+    for (int q = 0; q < AA_TQ; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { ah[q][j] = al[q][j] = 0u; tot[q][j] = 0ull; }
+    const uint32_t tab_base = smem_u32(s_tab);
+
+    for (int c = 0; c < a.n_chunks; ++c) {
+        const int st = c & 1;
+        if (tid == 0 && c + 1 < a.n_chunks) issue(c + 1);   // the other buffer was released by the barrier below
+        mbar_wait(&s_bar[st], (c >> 1) & 1);
+        // query codes -> table row offsets, once per stage (AA_TQ * AA_CH = 512 codes, 4 per thread)
+        {
+            const unsigned char* qs = s_stage[st] + AA_TR * AA_CH;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(qs + 4 * tid);
+            uint4 o;
+            o.x = (w & 0xffu) * (AA_TABW * 4);
+            o.y = ((w >> 8) & 0xffu) * (AA_TABW * 4);
+            o.z = ((w >> 16) & 0xffu) * (AA_TABW * 4);
+            o.w = (w >> 24) * (AA_TABW * 4);
+            *reinterpret_cast<uint4*>(&s_qoff[0][0] + 4 * tid) = o;
+        }
+        __syncthreads();
+        const unsigned char* r0 = s_stage[st] + (size_t)tid * AA_CH;
+        const unsigned char* r1 = s_stage[st] + (size_t)(tid + AA_THREADS) * AA_CH;
+#pragma unroll 1
+        for (int g = 0; g < AA_CH / 8; ++g) {
+            const uint2 b0 = *reinterpret_cast<const uint2*>(r0 + 8 * g);
+            const uint2 b1 = *reinterpret_cast<const uint2*>(r1 + 8 * g);
+            uint32_t ro[8][2];   // table column offsets (bytes) of the two references' next 8 sites, + the table base
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t w0 = k < 4 ? b0.x : b0.y, w1 = k < 4 ? b1.x : b1.y;
+                ro[k][0] = tab_base + (((w0 >> (8 * (k & 3))) & 0xffu) << 2);
+                ro[k][1] = tab_base + (((w1 >> (8 * (k & 3))) & 0xffu) << 2);
             }
+#pragma unroll
+            for (int q = 0; q < AA_TQ; ++q) {
+                const uint4 qa = *reinterpret_cast<const uint4*>(&s_qoff[q][8 * g]);       // broadcast
+                const uint4 qb = *reinterpret_cast<const uint4*>(&s_qoff[q][8 * g + 4]);
+                const uint32_t qo[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t addr = qo[k] + ro[k][j];
+                        uint32_t h, l;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(h) : "r"(addr));
+                        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(l) : "r"(addr), "n"(21 * AA_TABW * 4));
+                        ah[q][j] += h;
+                        al[q][j] += l;
+                    }
+            }
+        }
+        if ((c & 15) == 15 || c + 1 == a.n_chunks) {   // 16 stages = 1024 sites: the 22-bit limbs cannot overflow 32 bits
+#pragma unroll
+            for (int q = 0; q < AA_TQ; ++q)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    tot[q][j] += ((uint64_t)ah[q][j] << AA_LIMB) + al[q][j];
+                    ah[q][j] = al[q][j] = 0u;
+                }
+        }
+        __syncthreads();   // every thread is done with this stage's buffers (and with s_qoff)
+    }
+    // ---- epilogue: fixed point -> fp64 (exact: totals are below 2^53), scoredist correction in-register ----
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int r = rt * AA_TR + tid + j * AA_THREADS;
+        if (r >= a.n_r) continue;
+#pragma unroll
+        for (int q = 0; q < AA_TQ; ++q) {
+            const int qi = qt * AA_TQ + q;
+            if (qi >= a.nq) continue;
+            const double sum = (double)tot[q][j] * (1.0 / 8796093022208.0);   // 2^-43
+            const uint32_t v = a.valid[(size_t)qi * a.ldv + r];
+            a.dist[(size_t)qi * a.ldd + r] = scoredist_from_sum(sum, v, a.L, a.overlap);
+        }
     }
 }
 
-void launch_dense_aa(const uint8_t* q, int nq, const uint8_t* r, int n_r, int Lp, int L, double overlap, double* dist,
-                     int64_t ldd, uint32_t* valid_out, cudaStream_t s) {
-    dim3 grid((n_r + AA_THREADS - 1) / AA_THREADS, (nq + AA_TQ - 1) / AA_TQ);
-    dense_aa_kernel<<<grid, AA_THREADS, 0, s>>>(q, nq, r, n_r, Lp, L, overlap, dist, ldd, valid_out);
+// dist[nq][ldd] (and valid[nq][ldv]) from the tile-major operands; `valid` is a scratch / output buffer of nq * ldv words
+void launch_dense_aa(const uint8_t* q_tm, const uint32_t* q_vm, int q_pad, int nq, const uint8_t* r_tm, const uint32_t* r_vm,
+                     int r_pad, int n_r, int Lp, int L, double overlap, const uint32_t* tab, uint32_t* valid, int64_t ldv,
+                     double* dist, int64_t ldd, cudaStream_t s) {
+    const int n_chunks = (Lp + AA_CH - 1) / AA_CH;
+    const int Wv = n_chunks * (AA_CH / 32);
+    {
+        dim3 grid((n_r + 127) / 128, (nq + 7) / 8);
+        aa_valid_kernel<<<grid, 128, 0, s>>>(q_vm, q_pad, nq, r_vm, r_pad, n_r, Wv, valid, ldv);
+    }
+    DenseAaArgs a;
+    a.q_tm = q_tm; a.r_tm = r_tm; a.tab = tab; a.valid = valid; a.ldv = ldv; a.nq = nq; a.n_r = n_r; a.n_chunks = n_chunks;
+    a.L = L; a.overlap = overlap; a.dist = dist; a.ldd = ldd;
+    dim3 grid(r_pad / AA_TR, q_pad / AA_TQ);
+    dense_aa_kernel<<<grid, AA_THREADS, 0, s>>>(a);
+}
+
+// the two limb tables of round(BLOSUM45 * 2^43) (21 x 21 with a zero gap row / column, rows padded to AA_TABW words)
+void aa_build_tables(const double* blosum441, uint32_t* out) {
+    for (int i = 0; i < 2 * 21 * AA_TABW; ++i) out[i] = 0u;
+    for (int a = 0; a < 21; ++a)
+        for (int b = 0; b < 21; ++b) {
+            const double x = blosum441[a * 21 + b];
+            const uint64_t v = (uint64_t)(x * 8796093022208.0 + 0.5);
+            out[a * AA_TABW + b] = (uint32_t)(v >> AA_LIMB);
+            out[21 * AA_TABW + a * AA_TABW + b] = (uint32_t)(v & ((1u << AA_LIMB) - 1));
+        }
 }

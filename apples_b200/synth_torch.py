@@ -10,28 +10,29 @@ import torch
 _GAP = 45  # '-'
 
 
-def _sub_prob(t):
-    return 0.75 * (1.0 - torch.exp(-(4.0 / 3.0) * torch.clamp(t, min=0.0)))
+def _sub_prob(t, ns=4):
+    a = ns / (ns - 1.0)
+    return (1.0 / a) * (1.0 - torch.exp(-a * torch.clamp(t, min=0.0)))
 
 
-def _mutate_rows(states, t, gen, chunk=16384):
-    """states uint8 [n, L] (device), t float32 [n] branch lengths -> mutated copy"""
+def _mutate_rows(states, t, gen, chunk=16384, ns=4):
+    """states uint8 [n, L] (device), t float32 [n] branch lengths -> mutated copy (ns-state symmetric model)"""
     n, L = states.shape
     out = torch.empty_like(states)
     for a in range(0, n, chunk):
         b = min(n, a + chunk)
-        p = _sub_prob(t[a:b]).unsqueeze(1)
+        p = _sub_prob(t[a:b], ns).unsqueeze(1)
         hit = torch.rand((b - a, L), device=states.device, generator=gen) < p
-        shift = torch.randint(1, 4, (b - a, L), device=states.device, generator=gen, dtype=torch.uint8)
+        shift = torch.randint(1, ns, (b - a, L), device=states.device, generator=gen, dtype=torch.uint8)
         s = states[a:b]
-        out[a:b] = torch.where(hit, (s + shift) & 3, s)
+        out[a:b] = torch.where(hit, (s + shift) & 3 if ns == 4 else (s + shift) % ns, s)
     return out
 
 
-def _gapify_rows(states, gen, gap_frac, edge_frac, chunk=16384):
+def _gapify_rows(states, gen, gap_frac, edge_frac, chunk=16384, alphabet=b'ACGT'):
     """states uint8 codes [n, L] -> ASCII bytes with gaps"""
     n, L = states.shape
-    alpha = torch.tensor(list(b'ACGT'), dtype=torch.uint8, device=states.device)
+    alpha = torch.tensor(list(alphabet), dtype=torch.uint8, device=states.device)
     out = torch.empty_like(states)
     col = torch.arange(L, device=states.device).unsqueeze(0)
     for a in range(0, n, chunk):
@@ -45,13 +46,18 @@ def _gapify_rows(states, gen, gap_frac, edge_frac, chunk=16384):
     return out
 
 
-def evolve_alignment(tree, L, seed, device, gap_frac=0.03, edge_frac=0.1):
+AA_ALPHABET = b'ARNDCQEGHILKMFPSTWYV'
+
+
+def evolve_alignment(tree, L, seed, device, gap_frac=0.03, edge_frac=0.1, protein=False):
     """Returns (ref_bytes uint8 [n_leaves, L] on `device`, rows ordered by leaf node id; leaf_states uint8 [n_leaves, L])."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
+    ns = 20 if protein else 4
+    alphabet = AA_ALPHABET if protein else b'ACGT'
     M = tree.num_nodes
     S = torch.empty((M, L), dtype=torch.uint8, device=device)
-    S[M - 1] = torch.randint(0, 4, (L,), device=device, generator=gen, dtype=torch.uint8)
+    S[M - 1] = torch.randint(0, ns, (L,), device=device, generator=gen, dtype=torch.uint8)
     level = tree.level
     order = np.argsort(level, kind='stable')
     lv_sorted = level[order]
@@ -62,14 +68,14 @@ def evolve_alignment(tree, L, seed, device, gap_frac=0.03, edge_frac=0.1):
         idx = torch.from_numpy(order[bounds[k]:bounds[k + 1]].astype(np.int64)).to(device)
         if idx.numel() == 0:
             continue
-        S[idx] = _mutate_rows(S[par[idx]], el[idx], gen)
+        S[idx] = _mutate_rows(S[par[idx]], el[idx], gen, ns=ns)
     leaves = torch.from_numpy(tree.leaf_ids.astype(np.int64)).to(device)
     leaf_states = S[leaves].contiguous()
     del S
-    return _gapify_rows(leaf_states, gen, gap_frac, edge_frac), leaf_states
+    return _gapify_rows(leaf_states, gen, gap_frac, edge_frac, alphabet=alphabet), leaf_states
 
 
-def make_queries(leaf_states, n_queries, seed, device, mean_extra=0.05, gap_frac=0.03, edge_frac=0.1):
+def make_queries(leaf_states, n_queries, seed, device, mean_extra=0.05, gap_frac=0.03, edge_frac=0.1, protein=False):
     """Returns (query_bytes uint8 [n_queries, L] on device, source leaf row index int64 [n_queries])."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -80,8 +86,8 @@ def make_queries(leaf_states, n_queries, seed, device, mean_extra=0.05, gap_frac
     chunk = 16384
     for a in range(0, n_queries, chunk):
         b = min(n_queries, a + chunk)
-        st = _mutate_rows(leaf_states[src[a:b]], extra[a:b].float(), gen)
-        out[a:b] = _gapify_rows(st, gen, gap_frac, edge_frac)
+        st = _mutate_rows(leaf_states[src[a:b]], extra[a:b].float(), gen, ns=20 if protein else 4)
+        out[a:b] = _gapify_rows(st, gen, gap_frac, edge_frac, alphabet=AA_ALPHABET if protein else b'ACGT')
     return out, src
 
 

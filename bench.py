@@ -35,9 +35,13 @@ def parse(argv=None):
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--leaves', type=int, default=200000)
-    ap.add_argument('--sites', type=int, default=5000)
-    ap.add_argument('--queries-per-gpu', type=int, default=125000)
+    ap.add_argument('--workload', default='config5', choices=['config5', 'protein'],
+                    help="config5 = BASELINE.json's metric workload (default); protein = config 3 scaled up (4038-leaf "
+                         "backbone, 1638 amino-acid sites, 100 000 queries, scoredist + BLOSUM45): a side measurement of the "
+                         "amino-acid kernel, not the headline")
+    ap.add_argument('--leaves', type=int, default=None)
+    ap.add_argument('--sites', type=int, default=None)
+    ap.add_argument('--queries-per-gpu', type=int, default=None)
     ap.add_argument('--method', default='FM')
     ap.add_argument('--criterion', default='MLSE')
     ap.add_argument('--cpu-sample', type=int, default=0, help='queries in the CPU-baseline sample (0 = auto)')
@@ -46,7 +50,13 @@ def parse(argv=None):
     ap.add_argument('--no-cli', action='store_true', help='skip the run_apples.py command-line measurement (cli_e2e)')
     ap.add_argument('--slot-cap', type=int, default=0, help='observed-list slots per query before a rerun (0 = library default)')
     ap.add_argument('--sub-batch', type=int, default=0, help='queries per dense/selection launch (0 = library default)')
-    return ap.parse_args(argv)
+    a = ap.parse_args(argv)
+    prot = a.workload == 'protein'
+    a.leaves = a.leaves or (4038 if prot else 200000)
+    a.sites = a.sites or (1638 if prot else 5000)
+    a.queries_per_gpu = a.queries_per_gpu or (100000 if prot else 125000)
+    a.filt = 0.6 if prot else 0.2     # -f of the reference's protein example (README) / default
+    return a
 
 
 class ClockSampler:
@@ -110,17 +120,22 @@ def build_workload(args, device, rank, want_host_refs):
     from apples_b200 import synth, synth_torch, treecluster, fasta
     from apples_b200.tree import BackboneTree
     t0 = time.time()
-    nwk = synth.random_tree(args.leaves, seed=2)
+    prot = getattr(args, 'workload', 'config5') == 'protein'
+    nwk = synth.random_tree(args.leaves, seed=2, mean_edge=0.06 if prot else 0.02)
     tree = BackboneTree.from_newick(nwk)
-    ref_bytes, leaf_states = synth_torch.evolve_alignment(tree, args.sites, 5, device)
-    q_bytes, src = synth_torch.make_queries(leaf_states, args.queries_per_gpu, 1000 + rank, device)
+    ref_bytes, leaf_states = synth_torch.evolve_alignment(tree, args.sites, 5, device, protein=prot)
+    q_bytes, src = synth_torch.make_queries(leaf_states, args.queries_per_gpu, 1000 + rank, device, protein=prot)
     del leaf_states
-    packed_refs = synth_torch.pack_nucleotide(ref_bytes).cpu().numpy().view(np.uint32)
-    packed_q = synth_torch.pack_nucleotide(q_bytes)
     ref_host = ref_bytes.cpu().numpy()
+    if prot:
+        packed_refs = fasta.pack_protein(ref_host)
+        packed_q = torch.from_numpy(fasta.pack_protein(q_bytes.cpu().numpy()))
+    else:
+        packed_refs = synth_torch.pack_nucleotide(ref_bytes).cpu().numpy().view(np.uint32)
+        packed_q = synth_torch.pack_nucleotide(q_bytes)
     del ref_bytes
     # clusters and consensus representatives (Reference.py:85-107 equivalent, build-time)
-    clusters = treecluster.max_diameter_clusters(tree, 0.2 * 1.2)
+    clusters = treecluster.max_diameter_clusters(tree, getattr(args, 'filt', 0.2) * 1.2)
     leaf_row = {int(u): i for i, u in enumerate(tree.leaf_ids.tolist())}
     # the reference orders representatives by the cluster-id STRING with singletons ('-1') first (Reference.py:97)
     multi = [c for c in clusters if len(c) > 1]
@@ -133,11 +148,11 @@ def build_workload(args, device, rank, want_host_refs):
     members = []
     for i, c in enumerate(ordered):
         rows = [leaf_row[u] for u in c]
-        reps[i] = ref_host[rows[0]] if len(rows) == 1 else consensus_rows(ref_host[rows], False)
+        reps[i] = ref_host[rows[0]] if len(rows) == 1 else consensus_rows(ref_host[rows], prot)
         members.extend(rows)
         offs[i + 1] = len(members)
-    packed_reps = fasta.pack_nucleotide(reps)
-    arrays = dict(kind=fasta.NUC, L=args.sites, ref_names=[tree.label[u] for u in tree.leaf_ids.tolist()],
+    packed_reps = fasta.pack(reps, fasta.AA if prot else fasta.NUC)
+    arrays = dict(kind=fasta.AA if prot else fasta.NUC, L=args.sites, ref_names=[tree.label[u] for u in tree.leaf_ids.tolist()],
                   packed_refs=packed_refs, ref_node=tree.leaf_ids.astype(np.int32), packed_reps=packed_reps,
                   group_offsets=offs, group_members=np.asarray(members, dtype=np.int32))
     info = {'setup_s': round(time.time() - t0, 1), 'n_rep': len(ordered), 'max_level': int(tree.level.max())}
@@ -160,7 +175,8 @@ def cpu_context(args, tree, host):
     ref_host = host['ref_host']
     refs = {n: ref_host[i].view('S1') for i, n in enumerate(names)}
     reps = [(host['reps'][i].view('S1'), [names[host['leaf_row'][u]] for u in c]) for i, c in enumerate(host['ordered'])]
-    return orc.OracleContext(otree, onames, refs=refs, representatives=reps, method=args.method, criterion=args.criterion)
+    return orc.OracleContext(otree, onames, refs=refs, representatives=reps, method=args.method, criterion=args.criterion,
+                             protein=getattr(args, 'workload', 'config5') == 'protein', filt_threshold=getattr(args, 'filt', 0.2))
 
 
 def cpu_baseline(ctx, q_host, threads):
@@ -208,7 +224,7 @@ def cli_e2e(args, tree, host, q_bytes, device):
         out = os.path.join(wd, 'out.jplace')
         argv = ['-s', os.path.join(wd, 'ref.fa'), '-q', os.path.join(wd, 'query.fa'), '-t', os.path.join(wd, 'backbone.nwk'),
                 '--clusters', os.path.join(wd, 'clusters.tsv'), '-D', '-m', args.method, '-c', args.criterion, '-o', out,
-                '--device', str(device), '--gpus', '1']
+                '-f', str(args.filt), '--device', str(device), '--gpus', '1'] + (['-p'] if args.workload == 'protein' else [])
         import logging
         lvl = logging.getLogger().level
         logging.getLogger().setLevel(logging.ERROR)
@@ -246,10 +262,13 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     threads = os.cpu_count() or 1
-    workload = ('synthetic %d-leaf Yule backbone, %d-site nucleotide alignment (JC69 + gaps), %d queries per GPU per '
-                'step, APPLES-2 clusters at 1.2x0.2, %s+%s, -f 0.2 -b 25' % (args.leaves, args.sites,
-                                                                           args.queries_per_gpu, args.method,
-                                                                           args.criterion))
+    prot = args.workload == 'protein'
+    workload = ('synthetic %d-leaf Yule backbone, %d-site %s alignment (%s + gaps), %d queries per GPU per '
+                'step, APPLES-2 clusters at 1.2x%g, %s+%s, -f %g -b 25' % (args.leaves, args.sites,
+                                                                          'amino-acid' if prot else 'nucleotide',
+                                                                          '20-state symmetric model' if prot else 'JC69',
+                                                                          args.queries_per_gpu, args.filt, args.method,
+                                                                          args.criterion, args.filt))
     import torch
 
     if args.impl == 'reference':
@@ -296,8 +315,8 @@ def main():
     pl.set_reference_arrays(**arrays)
     if args.slot_cap or args.sub_batch:
         pl.set_limits(max_subbatch=args.sub_batch, slot_cap=args.slot_cap)
-    params = _lib.make_params(args.method, args.criterion)
-    packed_host = torch.empty(packed_q.shape, dtype=torch.int32).pin_memory()
+    params = _lib.make_params(args.method, args.criterion, filt_threshold=args.filt)
+    packed_host = torch.empty(packed_q.shape, dtype=packed_q.dtype).pin_memory()
     packed_host.copy_(packed_q)
     del packed_q
     pl.upload_queries(packed_host)
@@ -467,13 +486,29 @@ def main():
                 'plain_popcount_peak': plain_peak / 1e12, 'frac_of_plain_popcount_peak': cs_rate / plain_peak,
                 'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
                         'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes}}
+    if prot:
+        # amino-acid dense kernel: one BLOSUM45 lookup (two conflict-free 32-bit shared-memory loads) per (query,
+        # representative, site).  Bound by the shared-memory pipe: 32 banks x 4 B per clock per SM = one 32-lane LDS.32
+        # wavefront per clock, two per 32 lookups -> 16 lookups/clk/SM.
+        lookups = q_per_launch * n_rep * args.sites
+        lk_rate = lookups / (dense_ms * 1e-3)
+        lk_peak = 148 * 16 * sm_max * 1e6
+        aa_bytes = (q_per_launch + n_rep) * args.sites + 8.0 * q_per_launch * n_rep
+        roofline = {'kernel': 'dense_aa_kernel (query x representative scoredist, BLOSUM45 in shared memory)', 'bound': 'smem_pipe',
+                    'achieved': lk_rate / 1e12, 'peak': lk_peak / 1e12, 'unit': 'Tlookups/s', 'frac': lk_rate / lk_peak,
+                    'traffic': None, 'avg_launch_ms': dense_ms, 'launches': n_dense,
+                    'peak_model': 'two 32-lane LDS.32 wavefronts per 32 table lookups (44-bit fixed-point BLOSUM45 in two limb '
+                                  'tables, conflict-free by layout): 148 SMs x 16 lookups/clk x %.0f MHz' % sm_max,
+                    'hbm': {'achieved': aa_bytes / (dense_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                            'frac': aa_bytes / (dense_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': peak_src,
+                            'algorithmic_bytes_per_launch': aa_bytes}}
     # selection and placement kernels: per 125k-query step from the stage timers (CUDA events around their launches)
     n_steps = args.steps
     K_avg = tm['observed'] / (nq * n_steps)
     V_avg = tm['valid_nodes'] / (nq * n_steps)
     sel_ms = tm['selection_ms'] / n_steps
     pla_ms = tm['placement_ms'] / n_steps
-    sel_bytes = nq * (4.0 * n_rep + K_avg * 3 * W * 4 + 16.0 * K_avg)     # key row + member rows + observed list
+    sel_bytes = nq * ((8.0 if prot else 4.0) * n_rep + K_avg * (args.sites if prot else 3 * W * 4) + 16.0 * K_avg)   # key row + member rows + observed list
     pla_bytes = nq * (12.0 * K_avg + 20.0 * V_avg + 36.0)
     pla_flops = nq * 110.0 * V_avg
     roofline_select = {'kernel': 'select_kernel<SEL_NUC> (all launches of a step incl. overflow reruns)', 'bound': 'hbm',
@@ -488,13 +523,14 @@ def main():
                       'note': 'bound in practice by the dependency chain over tree levels (DESIGN.md 3b), neither by '
                               'HBM nor by the fp64 pipe'}
     step_ms = ms / args.steps
+    row_bytes = _lib.load().apples_aa_row_bytes(args.sites) if prot else 3 * W * 4
     stages = {k: tm[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms')}
     line = {'metric': 'queries placed/sec', 'value': value, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u32 popcount + f64', 'data': 'synthetic',
+            'dtype': 'u8 codes, 44-bit fixed-point table sums + f64' if prot else 'u32 popcount + f64', 'data': 'synthetic',
             'config': {'workload': workload, 'n_representatives': n_rep, 'queries_per_step': nq * world,
                        'l2': 'inputs larger than L2 (packed queries %.0f MB + packed reference %.0f MB per GPU)'
-                             % (nq * 3 * W * 4 / 1e6, (args.leaves + n_rep) * 3 * W * 4 / 1e6),
+                             % (nq * row_bytes / 1e6, (args.leaves + n_rep) * row_bytes / 1e6),
                        'parallelism': 'queries sharded over %d GPU(s), reference + tree replicated, final NCCL all-gather' % world},
             'distance_gcell_sites_per_s': (tm['pairs'] / args.steps) * args.sites / (step_ms * 1e-3) / 1e9 * world,
             'stage_ms_per_step': stages, 'rep_distance_sm_mhz': tm.get('rep_distance_sm_mhz'), 'per_rank': per_rank, 'pairs_per_query': tm['pairs'] / (nq * args.steps),
