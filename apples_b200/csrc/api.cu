@@ -32,6 +32,8 @@ struct apples_ctx {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;       // host->device staging of the next sub-batch overlaps compute
+    cudaStream_t pl_stream[2] = {nullptr, nullptr};   // the placement launch classes run side by side (partial last waves)
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     std::string err;
 
@@ -44,6 +46,11 @@ struct apples_ctx {
     DevBuf aa_tab, reps_aa_tm, reps_aav, refs_aa_tm, refs_aav, q_aa_tm, q_aav, aa_valid;   // amino-acid dense kernel operands
     int aa_rep_pad = 0, aa_ref_pad = 0;
     bool refs_aa_ready = false;
+    // byte-compare fallback of the nucleotide path (L > 65535 or symbols outside A,C,G,T,-): padded byte rows [n][Lp]
+    bool nuc_slow = false;        // the whole context runs in byte mode
+    bool bytes_ready = false;     // ref_bytes_p / rep_bytes_p hold the reference
+    DevBuf ref_bytes_p, rep_bytes_p, q_bytes_p, q_rowflag, keys_w;
+    double n_slow = 0;            // queries that went through the fallback
     bool refs_wm_ready = false;
     // matrix mode
     int n_cols = 0;
@@ -231,6 +238,18 @@ int aa_prepare_reps(apples_ctx* ctx, cudaStream_t s) {
     return 0;
 }
 
+// padded byte rows of the references and representatives for the byte-compare fallback; a context in fast mode builds
+// them from its bit-planes the first time a query needs the fallback
+int ensure_ref_bytes(apples_ctx* ctx, cudaStream_t s) {
+    if (ctx->bytes_ready) return 0;
+    if (ensure(ctx, ctx->ref_bytes_p, (size_t)ctx->n_ref * ctx->Lp) || ensure(ctx, ctx->rep_bytes_p, (size_t)ctx->n_rep * ctx->Lp))
+        return -1;
+    CK(launch_unpack_nuc((const uint32_t*)ctx->refs_rm.p, ctx->n_ref, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->ref_bytes_p.p, s));
+    CK(launch_unpack_nuc((const uint32_t*)ctx->reps_rm.p, ctx->n_rep, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->rep_bytes_p.p, s));
+    ctx->bytes_ready = true;
+    return 0;
+}
+
 TreeDev tree_dev(apples_ctx* ctx) {
     TreeDev t;
     t.M = ctx->M;
@@ -280,7 +299,9 @@ int check_params(apples_ctx* ctx, const apples_params* p) {
 int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const apples_params* prm) {
     cudaStream_t s = ctx->stream;
     const bool matrix = io.h_rows != nullptr;
-    const int sel_kind = matrix ? SEL_MATRIX : (ctx->kind == APPLES_AA ? SEL_AA : SEL_NUC);
+    const bool nuc = !matrix && ctx->kind == APPLES_NUC;
+    const bool slow_ctx = nuc && ctx->nuc_slow;   // byte-compare fallback for every query of this context
+    const int sel_kind = matrix ? SEL_MATRIX : (ctx->kind == APPLES_AA ? SEL_AA : (slow_ctx ? SEL_NUCW : SEL_NUC));
     const int n_units = matrix ? ctx->n_cols : ctx->n_rep;
     const int64_t ldk = matrix ? ctx->n_cols : ctx->rep_pad;
     const size_t key_bytes = (sel_kind == SEL_NUC) ? 4 : 8;
@@ -301,7 +322,12 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (ensure(ctx, ctx->q_bytes, (size_t)QB * io.byte_stride) || ensure(ctx, ctx->bad_flag, 4)) return -1;
         if (two_bufs && ensure(ctx, ctx->q_bytes2, (size_t)QB * io.byte_stride)) return -1;
         CK(cudaMemsetAsync(ctx->bad_flag.p, 0, 4, s));
+        if (nuc && !slow_ctx) {
+            if (ensure(ctx, ctx->q_rowflag, (size_t)n * 4)) return -1;
+            CK(cudaMemsetAsync(ctx->q_rowflag.p, 0, (size_t)n * 4, s));
+        }
     }
+    if (slow_ctx && ensure(ctx, ctx->q_bytes_p, (size_t)QB * ctx->Lp)) return -1;
     if (io.h_queries && two_bufs && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
@@ -370,6 +396,9 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     sa.refs_nuc = (const uint32_t*)ctx->refs_rm.p;
     sa.W = ctx->W;
     sa.refs_aa = (const uint8_t*)ctx->refs_rm.p;
+    sa.refs_bytes = (const uint8_t*)ctx->ref_bytes_p.p;
+    sa.refs_bstride = ctx->Lp;
+    sa.q_bstride = ctx->Lp;
     sa.Lp = ctx->Lp;
     sa.L = ctx->L;
     sa.col_node = (const int*)ctx->col_node.p;
@@ -398,10 +427,21 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     }
 
     // distances + selection of the `nb` queries whose packed rows / matrix rows are at d_q / ctx->keys
-    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a, bool keys_ready = false) -> int {
+    // `slow`: byte-compare fallback; d_qb = the queries' padded byte rows [nb][Lp], keys go to `kw` (64-bit, row stride ldk)
+    auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a, bool keys_ready = false, bool slow = false,
+                                    const uint8_t* d_qb = nullptr, void* kw = nullptr) -> int {
         const int nb_pad = round_up(nb, DT_TQ);
+        const int kind_now = slow ? SEL_NUCW : sel_kind;
         if (keys_ready) {
             // the key rows are already in a.keys_nuc (stash of the first pass)
+        } else if (slow) {
+            Span sp(ctx, T_DENSE);
+            launch_dense_bytes(d_qb, ctx->Lp, nb, (const uint8_t*)ctx->rep_bytes_p.p, ctx->Lp, ctx->n_rep, ctx->Lp,
+                               (unsigned long long*)kw, ldk, s);
+            ctx->n_launch += 1;
+            ctx->n_dense_launch += 1;
+            ctx->n_pairs += (double)nb * ctx->n_rep;
+            ctx->n_slow += nb;
         } else if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
@@ -441,9 +481,15 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         a.n = nb;
         a.q_nuc = (const uint32_t*)d_q;
         a.q_aa = (const uint8_t*)d_q;
+        if (slow) {
+            a.q_bytes = d_qb;
+            a.refs_bytes = (const uint8_t*)ctx->ref_bytes_p.p;
+            a.keys_f64 = (const double*)kw;
+            a.stash_keys = nullptr;
+        }
         {
             Span sp(ctx, T_SELECT);
-            launch_select(sel_kind, a, s);
+            launch_select(kind_now, a, s);
             ctx->n_launch += 1;
         }
         CK(cudaGetLastError());
@@ -492,9 +538,12 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             }
             CK(cudaEventRecord(ctx->ev_ready[buf], cs));
             CK(cudaStreamWaitEvent(s, ctx->ev_ready[buf], 0));
-            if (io.h_bytes) {
+            if (io.h_bytes && slow_ctx) {
+                CK(launch_repitch_bytes((const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, s));
+                ctx->n_launch += 1;
+            } else if (io.h_bytes) {
                 CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
-                               (int*)ctx->bad_flag.p, s));
+                               (int*)ctx->bad_flag.p, s, (nuc && !slow_ctx) ? (int*)ctx->q_rowflag.p + sb0 : nullptr));
                 ctx->n_launch += 1;
                 d_q = ctx->q_rm.p;
             } else {
@@ -504,8 +553,12 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         } else {
             d_q = (const char*)io.d_queries + (size_t)(base0 + sb0) * qrow;
         }
+        if (slow_ctx && !io.h_bytes) {   // packed planes in, byte rows needed
+            CK(launch_unpack_nuc((const uint32_t*)d_q, nb, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, s));
+            ctx->n_launch += 1;
+        }
         sa.q_begin = sb0;
-        if (distances_and_select(d_q, nb, sa)) return -1;
+        if (distances_and_select(d_q, nb, sa, false, slow_ctx, (const uint8_t*)ctx->q_bytes_p.p, ctx->keys.p)) return -1;
         if (used[buf]) CK(cudaEventRecord(ctx->ev_free[buf], s));
     }
 
@@ -519,10 +572,19 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     };
     if (fetch_counts()) return -1;
     CK(cudaStreamSynchronize(s));
-    if (io.h_bytes) {
+    // queries holding bytes other than A,C,G,T,- (they survive fasta2dic only as non-letters and count as ordinary
+    // characters in jc69, distance.py:733-737): the 2-bit planes cannot carry them, so those queries are recomputed by the
+    // byte-compare fallback below; their first-pass results are discarded
+    std::vector<int> exotic;
+    if (io.h_bytes && nuc && !slow_ctx) {
         int bad = 0;
         CK(cudaMemcpy(&bad, ctx->bad_flag.p, 4, cudaMemcpyDeviceToHost));
-        if (bad) return fail(ctx, "query alignment contains bytes the 2-bit nucleotide packing cannot express (only A,C,G,T,-)");
+        if (bad) {
+            std::vector<int> flags(n);
+            CK(cudaMemcpy(flags.data(), ctx->q_rowflag.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; ++i)
+                if (flags[i]) exotic.push_back(i);
+        }
     }
 
     PlaceArgs pa{};
@@ -584,13 +646,23 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         pa.obs_node = on;
         pa.obs_dist = od;
         pa.obs_len = ol;
-        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
+        // The launch classes are independent: the two large-footprint classes (256 / 512 node slots: 6 / 3 warps per SM) go to
+        // side streams so that their long, thin tails run beside the two big launches instead of after them.
+        Span sp_all(ctx, T_PLACE);
+        CK(cudaEventRecord(ctx->ev_fork, s));
+        bool side_used[2] = {false, false};
+        for (int c = PLACE_CLASS_512; c >= 0; --c) {
             if (!sizes[c]) continue;
+            const int side = c == PLACE_CLASS_512 ? 0 : c == PLACE_CLASS_256 ? 1 : -1;
+            cudaStream_t st = side >= 0 ? ctx->pl_stream[side] : s;
+            if (side >= 0) {
+                CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+                side_used[side] = true;
+            }
             pa.n = sizes[c];
             pa.qlist = d_q + begin[c];
             pa.slot_list = d_slot ? d_slot + begin[c] : nullptr;
-            Span sp(ctx, T_PLACE);
-            CK(launch_place(prm->method, c, pa, s));
+            CK(launch_place(prm->method, c, pa, st));
             ctx->n_launch += 1;
             ctx->n_place_class[c] += sizes[c];
         }
@@ -624,32 +696,35 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             pa.stack_off = (const long long*)ctx->stack_off.p;
             pa.recs = ctx->recs.p;
             pa.stacks = ctx->stacks.p;
-            {
-                Span sp(ctx, T_PLACE);
-                CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, s));
-                ctx->n_launch += 1;
-            }
+            CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, s));
+            ctx->n_launch += 1;
             i0 = i1;
             if (i0 < iend) CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused by the next chunk
         }
+        for (int k = 0; k < 2; ++k)
+            if (side_used[k]) {
+                CK(cudaEventRecord(ctx->ev_join[k], ctx->pl_stream[k]));
+                CK(cudaStreamWaitEvent(s, ctx->ev_join[k], 0));
+            }
         return 0;
     };
 
-    // ---------------- overflow reruns: observed set larger than the slot capacity (rare) ----------------
+    // ---------------- reruns (rare): byte-compare fallback for exotic queries; larger slots for overflowing ones ----------------
     // the selection kernel stops a query as soon as it exceeds its slot; it is rerun with a 16x larger slot (256 ->
     // 4096 -> 65536 -> all leaves) until it fits
     std::vector<char>& is_over = ctx->h_over;
     is_over.assign(n, 0);
+    for (int i : exotic) is_over[i] = 1;
     std::vector<int> over;
     for (int i = 0; i < n; ++i)
-        if (hS[i] == ST_OVERFLOW) {
+        if (hS[i] == ST_OVERFLOW && !is_over[i]) {
             over.push_back(i);
             is_over[i] = 1;
         }
     ctx->n_over += (double)over.size();
     // first-level reruns read their key rows from the stash when every overflowing query got a stash row
     bool use_stash = false;
-    if (stash_cap > 0 && !over.empty()) {
+    if (stash_cap > 0 && !over.empty() && exotic.empty()) {
         int cnt = 0;
         CK(cudaMemcpy(&cnt, ctx->stash_count.p, 4, cudaMemcpyDeviceToHost));
         if (cnt == (int)over.size() && cnt <= stash_cap) {
@@ -657,80 +732,98 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             use_stash = true;
         }
     }
-    int cap2 = cap;
     const int cap_max = next_pow2(std::max(4, n_leaf_bound));
-    while (!over.empty()) {
-        cap2 = (int)std::min<int64_t>((int64_t)cap2 * 16, cap_max);
-        // queries per rerun launch: bounded by the sub-batch size and by 2 GiB of slots
-        const int GB = (int)std::max<int64_t>(1, std::min<int64_t>(QB, ((int64_t)2 << 30) / ((int64_t)cap2 * 16)));
-        std::vector<int> still;
-        for (size_t o0 = 0; o0 < over.size(); o0 += GB) {
-            const int ng = (int)std::min<size_t>(GB, over.size() - o0);
-            if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
-            if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
-            if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
-            if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
-            CK(cudaMemcpyAsync(ctx->qlist.p, over.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
-            // gather the rows of the overflowing queries: one kernel for device-resident queries, one host-side gather +
-            // one copy otherwise (a memcpy call per row would cost more than the rerun itself)
-            if (!matrix && !io.h_queries && !io.h_bytes) {
-                // qlist holds batch-relative ids; the resident rows of this macro-batch start at base0
-                CK(launch_gather_rows((const char*)io.d_queries + (size_t)base0 * qrow, (const int*)ctx->qlist.p, ctx->q_rm.p, ng,
-                                      qrow, s));
-                ctx->n_launch += 1;
-            } else {
-                const size_t rb = matrix ? qrow : (io.h_queries ? qrow : (size_t)io.byte_stride);
-                const char* src = matrix ? (const char*)io.h_rows : (io.h_queries ? (const char*)io.h_queries : (const char*)io.h_bytes);
-                ctx->h_gather.resize((size_t)ng * rb);
-                for (int j = 0; j < ng; ++j)
-                    memcpy(ctx->h_gather.data() + (size_t)j * rb, src + ((size_t)base0 + over[o0 + j]) * rb, rb);
-                void* dst = matrix ? ctx->keys.p : (io.h_queries ? ctx->q_rm.p : ctx->q_bytes.p);
-                CK(cudaMemcpyAsync(dst, ctx->h_gather.data(), (size_t)ng * rb, cudaMemcpyHostToDevice, s));
-                CK(cudaStreamSynchronize(s));  // h_gather is reused by the next group
-            }
-            if (io.h_bytes)
-                CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
-                               (int*)ctx->bad_flag.p, s));
-            SelectArgs sb = sa;
-            sb.out_map = (const int*)ctx->qlist.p;
-            sb.q_begin = 0;
-            sb.cap = cap2;
-            sb.obs_node = (int*)ctx->obs_node2.p;
-            sb.obs_dist = (double*)ctx->obs_dist2.p;
-            sb.obs_len = (int*)ctx->obs_len2.p;
-            sb.pair_counter = nullptr;
-            sb.stash_keys = nullptr;
-            if (use_stash) sb.keys_nuc = (const uint32_t*)ctx->stash_keys.p + (size_t)o0 * ldk;
-            if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_stash)) return -1;
-            if (fetch_counts()) return -1;
-            CK(cudaStreamSynchronize(s));
-            if (io.obs_count) {
-                std::vector<int> un((size_t)ng * cap2);
-                std::vector<double> ud((size_t)ng * cap2);
-                CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
-                for (int j = 0; j < ng; ++j) {
-                    const int i = over[o0 + j];
-                    if (hS[i] == ST_OVERFLOW) continue;
-                    const int k = std::min(hK[i], io.obs_cap);
-                    memcpy(io.obs_node + (size_t)(base0 + i) * io.obs_cap, &un[(size_t)j * cap2], (size_t)k * 4);
-                    memcpy(io.obs_dist + (size_t)(base0 + i) * io.obs_cap, &ud[(size_t)j * cap2], (size_t)k * 8);
-                }
-            }
-            if (!io.stop_after_select) {
-                const int* ov = over.data() + o0;
-                if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, true, cap2,
-                                  (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
+    // reruns `list` with slot capacity cap_first, then 16x larger for whoever still overflows
+    auto rerun = [&](std::vector<int> list, bool slow, int cap_first, bool stash_first) -> int {
+        int cap2 = cap_first;
+        bool use_st = stash_first;
+        if (slow && !slow_ctx && ensure_ref_bytes(ctx, s)) return -1;
+        while (!list.empty()) {
+            // queries per rerun launch: bounded by the sub-batch size and by 2 GiB of slots
+            const int GB = (int)std::max<int64_t>(1, std::min<int64_t>(QB, ((int64_t)2 << 30) / ((int64_t)cap2 * 16)));
+            std::vector<int> still;
+            for (size_t o0 = 0; o0 < list.size(); o0 += GB) {
+                const int ng = (int)std::min<size_t>(GB, list.size() - o0);
+                if (ensure(ctx, ctx->obs_node2, (size_t)ng * cap2 * 4)) return -1;
+                if (ensure(ctx, ctx->obs_dist2, (size_t)ng * cap2 * 8)) return -1;
+                if (ensure(ctx, ctx->obs_len2, (size_t)ng * cap2 * 4)) return -1;
+                if (!matrix && ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
+                if (slow && (ensure(ctx, ctx->q_bytes_p, (size_t)QB * ctx->Lp) ||
+                             (!slow_ctx && ensure(ctx, ctx->keys_w, (size_t)ng * ldk * 8))))
                     return -1;
+                CK(cudaMemcpyAsync(ctx->qlist.p, list.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
+                // gather the rows of the queries: one kernel for device-resident queries, one host-side gather + one copy
+                // otherwise (a memcpy call per row would cost more than the rerun itself)
+                if (!matrix && !io.h_queries && !io.h_bytes) {
+                    // qlist holds batch-relative ids; the resident rows of this macro-batch start at base0
+                    CK(launch_gather_rows((const char*)io.d_queries + (size_t)base0 * qrow, (const int*)ctx->qlist.p, ctx->q_rm.p,
+                                          ng, qrow, s));
+                    ctx->n_launch += 1;
+                } else {
+                    const size_t rb = matrix ? qrow : (io.h_queries ? qrow : (size_t)io.byte_stride);
+                    const char* src = matrix ? (const char*)io.h_rows : (io.h_queries ? (const char*)io.h_queries : (const char*)io.h_bytes);
+                    ctx->h_gather.resize((size_t)ng * rb);
+                    for (int j = 0; j < ng; ++j)
+                        memcpy(ctx->h_gather.data() + (size_t)j * rb, src + ((size_t)base0 + list[o0 + j]) * rb, rb);
+                    void* dst = matrix ? ctx->keys.p : (io.h_queries ? ctx->q_rm.p : ctx->q_bytes.p);
+                    CK(cudaMemcpyAsync(dst, ctx->h_gather.data(), (size_t)ng * rb, cudaMemcpyHostToDevice, s));
+                    CK(cudaStreamSynchronize(s));  // h_gather is reused by the next group
+                }
+                if (io.h_bytes && slow)
+                    CK(launch_repitch_bytes((const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->Lp,
+                                            (uint8_t*)ctx->q_bytes_p.p, s));
+                else if (io.h_bytes)
+                    CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
+                                   (int*)ctx->bad_flag.p, s));
+                else if (slow)
+                    CK(launch_unpack_nuc((const uint32_t*)ctx->q_rm.p, ng, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, s));
+                SelectArgs sb = sa;
+                sb.out_map = (const int*)ctx->qlist.p;
+                sb.q_begin = 0;
+                sb.cap = cap2;
+                sb.obs_node = (int*)ctx->obs_node2.p;
+                sb.obs_dist = (double*)ctx->obs_dist2.p;
+                sb.obs_len = (int*)ctx->obs_len2.p;
+                sb.pair_counter = nullptr;
+                sb.stash_keys = nullptr;
+                if (use_st) sb.keys_nuc = (const uint32_t*)ctx->stash_keys.p + (size_t)o0 * ldk;
+                if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_st, slow, (const uint8_t*)ctx->q_bytes_p.p,
+                                         slow_ctx ? ctx->keys.p : ctx->keys_w.p))
+                    return -1;
+                if (fetch_counts()) return -1;
                 CK(cudaStreamSynchronize(s));
+                if (io.obs_count) {
+                    std::vector<int> un((size_t)ng * cap2);
+                    std::vector<double> ud((size_t)ng * cap2);
+                    CK(cudaMemcpy(un.data(), ctx->obs_node2.p, un.size() * 4, cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(ud.data(), ctx->obs_dist2.p, ud.size() * 8, cudaMemcpyDeviceToHost));
+                    for (int j = 0; j < ng; ++j) {
+                        const int i = list[o0 + j];
+                        if (hS[i] == ST_OVERFLOW) continue;
+                        const int k = std::min(hK[i], io.obs_cap);
+                        memcpy(io.obs_node + (size_t)(base0 + i) * io.obs_cap, &un[(size_t)j * cap2], (size_t)k * 4);
+                        memcpy(io.obs_dist + (size_t)(base0 + i) * io.obs_cap, &ud[(size_t)j * cap2], (size_t)k * 8);
+                    }
+                }
+                if (!io.stop_after_select) {
+                    const int* ov = list.data() + o0;
+                    if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, true, cap2,
+                                      (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
+                        return -1;
+                    CK(cudaStreamSynchronize(s));
+                }
+                for (int j = 0; j < ng; ++j)
+                    if (hS[list[o0 + j]] == ST_OVERFLOW) still.push_back(list[o0 + j]);
             }
-            for (int j = 0; j < ng; ++j)
-                if (hS[over[o0 + j]] == ST_OVERFLOW) still.push_back(over[o0 + j]);
+            if (cap2 >= cap_max && !still.empty()) return fail(ctx, "internal error: observed set larger than the number of leaves");
+            list.swap(still);
+            cap2 = (int)std::min<int64_t>((int64_t)cap2 * 16, cap_max);
+            use_st = false;  // deeper levels recompute: their rows are no longer contiguous in the stash
         }
-        if (cap2 >= cap_max && !still.empty()) return fail(ctx, "internal error: observed set larger than the number of leaves");
-        over.swap(still);
-        use_stash = false;  // deeper levels recompute: their rows are no longer contiguous in the stash
-    }
+        return 0;
+    };
+    if (!exotic.empty() && rerun(exotic, true, cap, false)) return -1;
+    if (!over.empty() && rerun(over, slow_ctx, (int)std::min<int64_t>((int64_t)cap * 16, cap_max), use_stash)) return -1;
 
     // ---------------- parity export of the observed sets ----------------
     if (io.obs_count) {
@@ -851,6 +944,11 @@ int apples_ctx_create(int device, apples_ctx** out) {
         if (cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
             rc = -4;
+    for (int i = 0; i < 2 && !rc; ++i)
+        if (cudaStreamCreateWithFlags(&ctx->pl_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = -4;
+    if (!rc && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = -4;
     if (!rc && dense_nuc_configure() != cudaSuccess) rc = -5;
     if (rc) {
         apples_ctx_destroy(ctx);  // releases whatever was created
@@ -866,7 +964,8 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->aa_tab, &ctx->reps_aa_tm, &ctx->reps_aav,
-                     &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
+                     &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_bytes_p, &ctx->rep_bytes_p,
+                     &ctx->q_bytes_p, &ctx->q_rowflag, &ctx->keys_w, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
@@ -883,6 +982,11 @@ void apples_ctx_destroy(apples_ctx* ctx) {
         if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pl_stream[i]) cudaStreamDestroy(ctx->pl_stream[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -934,7 +1038,6 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
     if ((kind != APPLES_NUC && kind != APPLES_AA) || L <= 0 || n_ref <= 0 || n_rep <= 0 || !packed_refs || !ref_node ||
         !packed_reps || !group_offsets || !group_members)
         return fail(ctx, "apples_set_reference: bad arguments");
-    if (kind == APPLES_NUC && L > 65535) return fail(ctx, "nucleotide alignments longer than 65535 columns are not supported");
     for (int i = 0; i < n_rep; ++i)
         if (group_offsets[i + 1] < group_offsets[i]) return fail(ctx, "apples_set_reference: group_offsets not monotone");
     const int n_mem = group_offsets[n_rep];
@@ -963,6 +1066,15 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
     CK(cudaMemcpy(ctx->ref_node.p, ref_node, (size_t)n_ref * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->goff.p, group_offsets, (size_t)(n_rep + 1) * 4, cudaMemcpyHostToDevice));
     if (n_mem) CK(cudaMemcpy(ctx->gmem.p, group_members, (size_t)n_mem * 4, cudaMemcpyHostToDevice));
+    ctx->nuc_slow = false;
+    ctx->bytes_ready = false;
+    if (kind == APPLES_NUC && L > 65535) {
+        // 16-bit counts do not hold: the whole context runs the byte-compare fallback (32-bit counts, 64-bit keys)
+        ctx->nuc_slow = true;
+        if (ensure_ref_bytes(ctx, ctx->stream)) return -1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
     if (kind == APPLES_AA) {
         if (aa_prepare_reps(ctx, ctx->stream)) return -1;
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1028,7 +1140,6 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
     if ((kind != APPLES_NUC && kind != APPLES_AA) || L <= 0 || n_ref <= 0 || n_rep <= 0 || !ref_bytes || row_stride < L ||
         !ref_node || !group_offsets || !group_members)
         return fail(ctx, "apples_set_reference_bytes: bad arguments");
-    if (kind == APPLES_NUC && L > 65535) return fail(ctx, "nucleotide alignments longer than 65535 columns are not supported");
     for (int i = 0; i < n_rep; ++i)
         if (group_offsets[i + 1] < group_offsets[i]) return fail(ctx, "apples_set_reference_bytes: group_offsets not monotone");
     const int n_mem = group_offsets[n_rep];
@@ -1071,12 +1182,24 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
     int bad = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, ctx->bad_flag.p, 4, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    ctx->nuc_slow = false;
+    ctx->bytes_ready = false;
+    if (e == cudaSuccess && kind == APPLES_NUC && (bad || L > 65535)) {
+        // the reference holds bytes other than A,C,G,T,- (ordinary characters for jc69, distance.py:733-737) or is longer
+        // than the 16-bit counts allow: keep the byte rows, every query of this context takes the byte-compare fallback
+        ctx->nuc_slow = true;
+        if (ensure(ctx, ctx->ref_bytes_p, (size_t)n_ref * ctx->Lp) || ensure(ctx, ctx->rep_bytes_p, (size_t)n_rep * ctx->Lp)) {
+            cleanup();
+            return -1;
+        }
+        e = launch_repitch_bytes((const uint8_t*)d_bytes.p, row_stride, n_ref, L, ctx->Lp, (uint8_t*)ctx->ref_bytes_p.p, s);
+        if (e == cudaSuccess) e = launch_repitch_bytes((const uint8_t*)d_rep_bytes.p, L, n_rep, L, ctx->Lp, (uint8_t*)ctx->rep_bytes_p.p, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        ctx->bytes_ready = e == cudaSuccess;
+    }
     cleanup();
     if (e != cudaSuccess) return fail(ctx, "apples_set_reference_bytes: %s", cudaGetErrorString(e));
-    if (bad) {
-        ctx->kind = -1;
-        return fail(ctx, "reference alignment contains bytes the 2-bit nucleotide packing cannot express (only A,C,G,T,-)");
-    }
+    if (ctx->nuc_slow) return 0;
     if (kind == APPLES_AA) {
         if (aa_prepare_reps(ctx, s)) return -1;
         CK(cudaStreamSynchronize(s));
@@ -1186,6 +1309,24 @@ int apples_distance_counts(apples_ctx* ctx, int64_t nq, const void* packed_queri
         ensure(ctx, dd, n_out * 8)) { cleanup(); return -1; }
     cudaMemcpyAsync(dq.p, packed_queries, (size_t)nq * row, cudaMemcpyHostToDevice, s);
     cudaMemsetAsync(dm.p, 0, n_out * 4, s);
+    if (ctx->kind == APPLES_NUC && ctx->nuc_slow) {
+        DevBuf qb, kw;
+        auto cleanup2 = [&]() { release(qb); release(kw); cleanup(); };
+        if (ensure(ctx, qb, (size_t)nq * ctx->Lp) || ensure(ctx, kw, n_out * 8)) { cleanup2(); return -1; }
+        launch_unpack_nuc((const uint32_t*)dq.p, (int)nq, ctx->L, ctx->W, ctx->Lp, (uint8_t*)qb.p, s);
+        launch_dense_bytes((const uint8_t*)qb.p, ctx->Lp, (int)nq, (const uint8_t*)ctx->ref_bytes_p.p, ctx->Lp, ctx->n_ref, ctx->Lp,
+                           (unsigned long long*)kw.p, ctx->n_ref, s);
+        launch_bytes_keys_to_counts((const unsigned long long*)kw.p, (int64_t)n_out, overlap_vmin(ctx->L, overlap_frac), (uint32_t*)dm.p,
+                                    (uint32_t*)dv.p, (double*)dd.p, s);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(mism, dm.p, n_out * 4, cudaMemcpyDeviceToHost, s);
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(valid, dv.p, n_out * 4, cudaMemcpyDeviceToHost, s);
+        if (e2 == cudaSuccess) e2 = cudaMemcpyAsync(dist, dd.p, n_out * 8, cudaMemcpyDeviceToHost, s);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(s);
+        if (e2 != cudaSuccess) rc = fail(ctx, "apples_distance_counts: %s", cudaGetErrorString(e2));
+        cleanup2();
+        return rc;
+    }
     if (ctx->kind == APPLES_NUC) {
         if (!ctx->refs_wm_ready) {
             const size_t wm = (size_t)3 * ctx->Wp * ctx->ref_pad * 4;
@@ -1279,15 +1420,16 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
     if (!ctx || !out) return -1;
-    double v[20] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+    double v[21] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
                     ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid,
                     ctx->n_over, ctx->max_K, ctx->max_V, ctx->dense_mhz, ctx->n_place_class[0], ctx->n_place_class[1],
-                    ctx->n_place_class[2], ctx->n_place_class[3], ctx->n_place_class[4]};
-    for (int i = 0; i < n && i < 20; ++i) out[i] = v[i];
+                    ctx->n_place_class[2], ctx->n_place_class[3], ctx->n_place_class[4], ctx->n_slow};
+    for (int i = 0; i < n && i < 21; ++i) out[i] = v[i];
     if (reset) {
         for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
         ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = ctx->n_over = ctx->max_K = ctx->max_V = 0;
         for (int c = 0; c < PLACE_NCLASS; ++c) ctx->n_place_class[c] = 0;
+        ctx->n_slow = 0;
     }
     return 0;
 }

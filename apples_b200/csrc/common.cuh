@@ -90,7 +90,7 @@ __device__ __forceinline__ double scoredist_from_sum(double tot, uint32_t v, int
 // ---------------------------------------------------------------------------------------------------------------
 // selection (select.cu) and placement (placement.cu) launch arguments
 // ---------------------------------------------------------------------------------------------------------------
-enum { SEL_NUC = 0, SEL_AA = 1, SEL_MATRIX = 2 };
+enum { SEL_NUC = 0, SEL_AA = 1, SEL_MATRIX = 2, SEL_NUCW = 3 };
 
 struct SelectArgs {
     int n;                 // queries in this launch; their key / query rows are rows 0..n-1 of keys_* / q_*
@@ -100,13 +100,17 @@ struct SelectArgs {
     int n_units;           // representatives (alignment) or matrix columns
     int64_t ldk;           // row stride of the key matrix
     const uint32_t* keys_nuc;  // [nq][ldk] packed (mismatch | valid << 16)
-    const double* keys_f64;    // [nq][ldk] distances (protein representatives / matrix rows)
+    const double* keys_f64;    // [nq][ldk] distances (protein representatives / matrix rows); SEL_NUCW: 64-bit count keys
     const int* goff;       // cluster CSR
     const int* gmem;
     const int* ref_node;
     const uint32_t* refs_nuc;  // row-major [n_ref][3][W]
     const uint32_t* q_nuc;     // row-major [n][3][W]
     int W;
+    const uint8_t* refs_bytes; // SEL_NUCW: raw alignment bytes [n_ref][refs_bstride]
+    int64_t refs_bstride;
+    const uint8_t* q_bytes;    // SEL_NUCW: [n][q_bstride]
+    int64_t q_bstride;
     const uint8_t* refs_aa;    // [n_ref][Lp]
     const uint8_t* q_aa;       // [n][Lp]
     int Lp;
@@ -192,7 +196,14 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
 cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s);
 cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s);
 cudaError_t dense_nuc_configure();
-cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad, cudaStream_t s);
+cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad, cudaStream_t s,
+                        int* row_flag = nullptr);
+cudaError_t launch_repitch_bytes(const uint8_t* src, int64_t src_stride, int n, int L, int Lp, uint8_t* dst, cudaStream_t s);
+cudaError_t launch_unpack_nuc(const uint32_t* planes, int n, int L, int W, int Lp, uint8_t* dst, cudaStream_t s);
+void launch_dense_bytes(const uint8_t* q, int64_t q_stride, int nq, const uint8_t* r, int64_t r_stride, int n_r, int Lp,
+                        unsigned long long* keys, int64_t ldk, cudaStream_t s);
+void launch_bytes_keys_to_counts(const unsigned long long* keys, int64_t n, int vmin, uint32_t* mism, uint32_t* valid, double* dist,
+                                 cudaStream_t s);
 cudaError_t launch_gather_rows(const void* src, const int* idx, void* dst, int n, size_t row_bytes, cudaStream_t s);
 cudaError_t launch_consensus(int kind, const uint8_t* bytes, int64_t row_stride, int L, int n_rep, const int* goff,
                              const int* gmem, uint8_t* out, int64_t out_stride, cudaStream_t s);

@@ -609,3 +609,60 @@ void aa_build_tables(const double* blosum441, uint32_t* out) {
             out[21 * AA_TABW + a * AA_TABW + b] = (uint32_t)(v & ((1u << AA_LIMB) - 1));
         }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// byte-compare fallback of the nucleotide distance stage: the reference's definition applied to the raw bytes
+// (distance.py:733-737), for inputs the 2-bit planes cannot carry -- alignments longer than 65 535 columns (16-bit
+// counts) and bytes other than A,C,G,T,- that survive fasta2dic (non-letters such as '.', '*', '?', digits) and count as
+// ordinary characters.  One block per query, one warp per representative (grid-stride), 4 sites per lane and step; keys
+// are (mismatch | valid << 32).  ~30x slower than the bit-plane kernel: a correctness path for rare inputs.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
+
+__global__ void __launch_bounds__(256) dense_bytes_kernel(const uint8_t* __restrict__ q, int64_t q_stride, int nq,
+                                                          const uint8_t* __restrict__ r, int64_t r_stride, int n_r, int Lp,
+                                                          unsigned long long* __restrict__ keys, int64_t ldk) {
+    const int qi = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t* qrow = reinterpret_cast<const uint32_t*>(q + (size_t)qi * q_stride);
+    const int nw = Lp / 4;
+    for (int ri = warp; ri < n_r; ri += 8) {
+        const uint32_t* rrow = reinterpret_cast<const uint32_t*>(r + (size_t)ri * r_stride);
+        uint32_t m = 0, v = 0;
+        for (int w = lane; w < nw; w += 32) {
+            const uint32_t a = qrow[w], b = rrow[w];
+            const uint32_t both = nz_bytes(a ^ 0x2d2d2d2du) & nz_bytes(b ^ 0x2d2d2d2du);
+            v += __popc(both);
+            m += __popc(nz_bytes(a ^ b) & both);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m += __shfl_xor_sync(0xffffffffu, m, o);
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        }
+        if (lane == 0) keys[(size_t)qi * ldk + ri] = (unsigned long long)m | ((unsigned long long)v << 32);
+    }
+}
+
+void launch_dense_bytes(const uint8_t* q, int64_t q_stride, int nq, const uint8_t* r, int64_t r_stride, int n_r, int Lp,
+                        unsigned long long* keys, int64_t ldk, cudaStream_t s) {
+    if (nq <= 0) return;
+    dense_bytes_kernel<<<nq, 256, 0, s>>>(q, q_stride, nq, r, r_stride, n_r, Lp, keys, ldk);
+}
+
+// parity export in byte mode: mism / valid / jc69 of every (query, reference) pair
+__global__ void bytes_keys_to_counts_kernel(const unsigned long long* __restrict__ keys, int64_t n, int vmin, uint32_t* mism,
+                                            uint32_t* valid, double* dist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = (uint32_t)(keys[i] & 0xffffffffull), v = (uint32_t)(keys[i] >> 32);
+    mism[i] = m;
+    valid[i] = v;
+    dist[i] = jc69_from_counts(m, v, vmin);
+}
+
+void launch_bytes_keys_to_counts(const unsigned long long* keys, int64_t n, int vmin, uint32_t* mism, uint32_t* valid, double* dist,
+                                 cudaStream_t s) {
+    if (n <= 0) return;
+    bytes_keys_to_counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n, vmin, mism, valid, dist);
+}

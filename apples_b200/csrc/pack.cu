@@ -10,7 +10,7 @@
 #include "common.cuh"
 
 __global__ void pack_nuc_kernel(const uint8_t* __restrict__ bytes, int64_t row_stride, int n, int L, int W,
-                                uint32_t* __restrict__ out, int* __restrict__ bad) {
+                                uint32_t* __restrict__ out, int* __restrict__ bad, int* __restrict__ row_flag) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)n * W) return;
     const int row = (int)(t / W), w = (int)(t % W);
@@ -27,7 +27,9 @@ __global__ void pack_nuc_kernel(const uint8_t* __restrict__ bytes, int64_t row_s
             hi |= (code >> 1) << s;
             va |= 1u << s;
         } else if (c != '-') {
+            // a byte the 2-bit code cannot carry: the row goes through the byte-compare fallback (distance.cu)
             *bad = 1;
+            if (row_flag) row_flag[row] = 1;
         }
     }
     uint32_t* o = out + (size_t)row * 3 * W + w;
@@ -61,12 +63,12 @@ __global__ void pack_aa_kernel(const uint8_t* __restrict__ bytes, int64_t row_st
 }
 
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad,
-                        cudaStream_t s) {
+                        cudaStream_t s, int* row_flag) {
     if (n <= 0) return cudaSuccess;
     if (kind == APPLES_NUC) {
         const int W = apples_words_per_row(L);
         const int64_t total = (int64_t)n * W;
-        pack_nuc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, W, (uint32_t*)out, bad);
+        pack_nuc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bytes, row_stride, n, L, W, (uint32_t*)out, bad, row_flag);
     } else {
         const int Lp = apples_aa_row_bytes(L);
         const int64_t total = (int64_t)n * Lp;
@@ -123,5 +125,44 @@ cudaError_t launch_gather_rows(const void* src, const int* idx, void* dst, int n
     const int row_vec = (int)(row_bytes / 16);
     const int64_t total = (int64_t)n * row_vec;
     gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const uint4*)src, idx, (uint4*)dst, n, row_vec);
+    return cudaGetLastError();
+}
+
+
+// byte rows [n][src_stride] -> [n][Lp] with the tail padded by '-' (Lp a multiple of 16): the operand layout of the
+// byte-compare fallback (whole 32-bit words, gaps do not count)
+__global__ void repitch_bytes_kernel(const uint8_t* __restrict__ src, int64_t src_stride, int n, int L, int Lp,
+                                     uint8_t* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * Lp) return;
+    const int row = (int)(t / Lp), s = (int)(t % Lp);
+    dst[t] = s < L ? src[(size_t)row * src_stride + s] : (uint8_t)'-';
+}
+
+cudaError_t launch_repitch_bytes(const uint8_t* src, int64_t src_stride, int n, int L, int Lp, uint8_t* dst, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t total = (int64_t)n * Lp;
+    repitch_bytes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, src_stride, n, L, Lp, dst);
+    return cudaGetLastError();
+}
+
+// bit-planes [n][3][W] -> bytes [n][Lp] ('A','C','G','T','-'; padding '-')
+__global__ void unpack_nuc_kernel(const uint32_t* __restrict__ planes, int n, int L, int W, int Lp, uint8_t* __restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n * Lp) return;
+    const int row = (int)(t / Lp), s = (int)(t % Lp);
+    uint8_t c = '-';
+    if (s < L) {
+        const uint32_t* p = planes + (size_t)row * 3 * W + s / 32;
+        const uint32_t b = 1u << (s % 32);
+        if (p[2 * W] & b) c = "ACGT"[((p[0] & b) ? 1 : 0) | ((p[W] & b) ? 2 : 0)];
+    }
+    dst[t] = c;
+}
+
+cudaError_t launch_unpack_nuc(const uint32_t* planes, int n, int L, int W, int Lp, uint8_t* dst, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t total = (int64_t)n * Lp;
+    unpack_nuc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, n, L, W, Lp, dst);
     return cudaGetLastError();
 }

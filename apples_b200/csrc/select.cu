@@ -33,6 +33,14 @@ struct Key<SEL_NUC> {
     uint32_t m, v;
     int idx;
 };
+// SEL_NUCW: nucleotide counts of the byte-compare fallback (alignments longer than 65 535 columns, or symbols other than
+// A,C,G,T,- that survive fasta2dic and count as ordinary characters in jc69, distance.py:733-737): 32-bit counts in
+// 64-bit keys, 64-bit products
+template <>
+struct Key<SEL_NUCW> {
+    uint32_t m, v;
+    int idx;
+};
 template <>
 struct Key<SEL_AA> {
     double d;
@@ -48,6 +56,10 @@ __device__ __forceinline__ bool key_less(const Key<SEL_NUC>& a, const Key<SEL_NU
     const uint32_t x = a.m * b.v, y = b.m * a.v;  // counts <= 65535: products fit 32 bits
     return x < y || (x == y && a.idx < b.idx);
 }
+__device__ __forceinline__ bool key_less(const Key<SEL_NUCW>& a, const Key<SEL_NUCW>& b) {
+    const uint64_t x = (uint64_t)a.m * b.v, y = (uint64_t)b.m * a.v;
+    return x < y || (x == y && a.idx < b.idx);
+}
 __device__ __forceinline__ bool key_less(const Key<SEL_AA>& a, const Key<SEL_AA>& b) {
     return a.d < b.d || (a.d == b.d && a.idx < b.idx);
 }
@@ -60,7 +72,7 @@ constexpr int KEY_NONE_IDX = 0x7fffffff;
 template <int KIND>
 __device__ __forceinline__ Key<KIND> key_none() {
     Key<KIND> k;
-    if constexpr (KIND == SEL_NUC) {
+    if constexpr (KIND == SEL_NUC || KIND == SEL_NUCW) {
         k.m = 1u;
         k.v = 0u;
     } else {
@@ -81,6 +93,13 @@ __device__ __forceinline__ Key<SEL_NUC> key_shfl(const Key<SEL_NUC>& k, int src)
     o.idx = __shfl_sync(FULLMASK, k.idx, src);
     return o;
 }
+__device__ __forceinline__ Key<SEL_NUCW> key_shfl(const Key<SEL_NUCW>& k, int src) {
+    Key<SEL_NUCW> o;
+    o.m = __shfl_sync(FULLMASK, k.m, src);
+    o.v = __shfl_sync(FULLMASK, k.v, src);
+    o.idx = __shfl_sync(FULLMASK, k.idx, src);
+    return o;
+}
 template <int KIND>
 __device__ __forceinline__ Key<KIND> key_shfl(const Key<KIND>& k, int src) {
     Key<KIND> o;
@@ -90,6 +109,13 @@ __device__ __forceinline__ Key<KIND> key_shfl(const Key<KIND>& k, int src) {
 }
 __device__ __forceinline__ Key<SEL_NUC> key_shfl_xor(const Key<SEL_NUC>& k, int o) {
     Key<SEL_NUC> r;
+    r.m = __shfl_xor_sync(FULLMASK, k.m, o);
+    r.v = __shfl_xor_sync(FULLMASK, k.v, o);
+    r.idx = __shfl_xor_sync(FULLMASK, k.idx, o);
+    return r;
+}
+__device__ __forceinline__ Key<SEL_NUCW> key_shfl_xor(const Key<SEL_NUCW>& k, int o) {
+    Key<SEL_NUCW> r;
     r.m = __shfl_xor_sync(FULLMASK, k.m, o);
     r.v = __shfl_xor_sync(FULLMASK, k.v, o);
     r.idx = __shfl_xor_sync(FULLMASK, k.idx, o);
@@ -112,6 +138,10 @@ template <>
 struct RawT<SEL_NUC> {
     using T = uint32_t;
 };
+template <>
+struct RawT<SEL_NUCW> {
+    using T = unsigned long long;   // mismatch | valid << 32
+};
 __device__ __forceinline__ Key<SEL_NUC> make_key_nuc(uint32_t raw, int idx) {
     Key<SEL_NUC> k;
     k.m = raw & 0xffffu;
@@ -123,6 +153,12 @@ template <int KIND>
 __device__ __forceinline__ Key<KIND> make_key(typename RawT<KIND>::T raw, int idx) {
     if constexpr (KIND == SEL_NUC) {
         return make_key_nuc(raw, idx);
+    } else if constexpr (KIND == SEL_NUCW) {
+        Key<SEL_NUCW> k;
+        k.m = (uint32_t)(raw & 0xffffffffull);
+        k.v = (uint32_t)(raw >> 32);
+        k.idx = idx;
+        return k;
     } else {
         Key<KIND> k;
         k.d = raw;
@@ -134,6 +170,8 @@ template <int KIND>
 __device__ __forceinline__ typename RawT<KIND>::T load_raw(const SelectArgs& a, int row, int u) {
     if constexpr (KIND == SEL_NUC)
         return a.keys_nuc[(size_t)row * a.ldk + u];
+    else if constexpr (KIND == SEL_NUCW)
+        return reinterpret_cast<const unsigned long long*>(a.keys_f64)[(size_t)row * a.ldk + u];
     else
         return a.keys_f64[(size_t)row * a.ldk + u];
 }
@@ -166,6 +204,14 @@ __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_NUC>&
     if (a.gate.P_hi == 0u) return 2;  // negative threshold: nothing is near
     if (lhs <= a.gate.P_lo * k.v) return 1;
     if (lhs >= a.gate.P_hi * k.v) return 2;
+    return band_is_near(k.m, k.v, a.gate.vmin, a.thr) ? 1 : 2;
+}
+__device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_NUCW>& k) {
+    if (k.v == 0u || (long long)k.v < (long long)a.gate.vmin || 4ull * k.m >= 3ull * k.v) return 0;
+    const uint64_t lhs = (uint64_t)k.m << 16;
+    if (a.gate.P_hi == 0u) return 2;
+    if (lhs <= (uint64_t)a.gate.P_lo * k.v) return 1;
+    if (lhs >= (uint64_t)a.gate.P_hi * k.v) return 2;
     return band_is_near(k.m, k.v, a.gate.vmin, a.thr) ? 1 : 2;
 }
 __device__ __forceinline__ int classify(const SelectArgs& a, const Key<SEL_AA>& k) {
@@ -213,6 +259,45 @@ __device__ __forceinline__ void member_counts_nuc(const SelectArgs& a, const uin
         for (int k = 0; k < NR; ++k) acc[k] += __shfl_xor_sync(FULLMASK, acc[k], o);
 #pragma unroll
     for (int k = 0; k < NR; ++k) out[k] = acc[k];
+}
+
+// byte-compare twin for the fallback: the reference's own definition on raw bytes (distance.py:733-737): a site counts
+// when neither byte is '-', and mismatches when the bytes differ.  4 sites per 32-bit word, SWAR.
+__device__ __forceinline__ void bytes_counts_word(uint32_t a, uint32_t b, uint32_t& m, uint32_t& v) {
+    // per byte: high bit set iff the byte is non-zero (bytes are < 0x80 after fasta2dic's ASCII input; the general form
+    // below is exact for any byte value)
+    auto nz = [](uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; };
+    const uint32_t da = nz(a ^ 0x2d2d2d2du), db = nz(b ^ 0x2d2d2d2du);   // 0x2d = '-'
+    const uint32_t both = da & db;
+    v += __popc(both);
+    m += __popc(nz(a ^ b) & both);
+}
+
+template <int NR>
+__device__ __forceinline__ void member_counts_bytes(const SelectArgs& a, const uint8_t* __restrict__ qrow, const int* rows, int lane,
+                                                    uint32_t* om, uint32_t* ov) {
+    uint32_t m[NR], v[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) m[k] = v[k] = 0;
+    // rows are padded with '-' to a.Lp (a multiple of 16) bytes by the caller: whole words, no tail
+    const int nw = a.Lp / 4;
+    for (int w = lane; w < nw; w += 32) {
+        const uint32_t q = *reinterpret_cast<const uint32_t*>(qrow + 4 * w);
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const uint32_t r = *reinterpret_cast<const uint32_t*>(a.refs_bytes + (size_t)rows[k] * a.refs_bstride + 4 * w);
+            bytes_counts_word(q, r, m[k], v[k]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            m[k] += __shfl_xor_sync(FULLMASK, m[k], o);
+            v[k] += __shfl_xor_sync(FULLMASK, v[k], o);
+        }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { om[k] = m[k]; ov[k] = v[k]; }
 }
 
 __constant__ double c_blosum45_sel[441] = {
@@ -288,6 +373,13 @@ __device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<
     observe<SEL_NUC>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
 }
 
+__device__ __forceinline__ void observe_nucw_counts(const SelectArgs& a, WarpSel<SEL_NUCW>& st, int slot, int self, int row,
+                                                    uint32_t m, uint32_t v, const Key<SEL_NUCW>& ukey, int pos, int lane) {
+    if (v == 0u || (long long)v < (long long)a.gate.vmin || 4ull * m >= 3ull * v) return;   // distance < 0: not stored
+    const unsigned long long c = (unsigned long long)m | ((unsigned long long)v << 32);
+    observe<SEL_NUCW>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
+}
+
 template <int KIND, int NR = 2>
 __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& st, int slot, int q, int self,
                                             const Key<KIND>& ukey, int lane, const double* aa_tab) {
@@ -295,7 +387,19 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         observe<KIND>(a, st, slot, self, a.col_node[ukey.idx], ukey.d, ukey.d == 0.0, ukey, 0, lane);
     } else {
         const int b = a.goff[ukey.idx], e = a.goff[ukey.idx + 1];
-        if constexpr (KIND == SEL_NUC) {
+        if constexpr (KIND == SEL_NUCW) {
+            const uint8_t* qrow = a.q_bytes + (size_t)q * a.q_bstride;
+            for (int x = b; x < e && st.kcount <= a.cap; x += NR) {
+                int rows[NR];
+                uint32_t cm[NR], cv[NR];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
+                member_counts_bytes<NR>(a, qrow, rows, lane, cm, cv);
+#pragma unroll
+                for (int k = 0; k < NR; ++k)
+                    if (x + k < e) observe_nucw_counts(a, st, slot, self, rows[k], cm[k], cv[k], ukey, x + k - b, lane);
+            }
+        } else if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
                 int rows[NR];
@@ -408,6 +512,12 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
                 const bool ok = (int)v >= a.gate.vmin;
                 const bool pfar = (r << 16) >= a.gate.P_hi * v;
                 const bool less = m * l2.v < l2.m * v;  // by ratio; units arrive in ascending order, ties are not less
+                if (ok && (!pfar || less)) ev |= 1u << j;
+            } else if constexpr (KIND == SEL_NUCW) {
+                const uint32_t m = (uint32_t)(raw[j] & 0xffffffffull), v = (uint32_t)(raw[j] >> 32);
+                const bool ok = (long long)v >= (long long)a.gate.vmin;
+                const bool pfar = ((uint64_t)m << 16) >= (uint64_t)a.gate.P_hi * v;
+                const bool less = (uint64_t)m * l2.v < (uint64_t)l2.m * v;
                 if (ok && (!pfar || less)) ev |= 1u << j;
             } else {
                 const int u = u0 + j * 32 + lane;
@@ -570,6 +680,12 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
                 dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
             }
         }
+        if constexpr (KIND == SEL_NUCW) {
+            for (int i = lane; i < K; i += 32) {
+                const unsigned long long c = (unsigned long long)__double_as_longlong(dist[i]);
+                dist[i] = jc69_from_counts((uint32_t)(c & 0xffffffffull), (uint32_t)(c >> 32), a.gate.vmin);
+            }
+        }
         for (int i = K + lane; i < n2; i += 32) {
             node[i] = 0x7fffffff;
             dist[i] = 0.0;
@@ -615,6 +731,8 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
         select_kernel<SEL_NUC, true><<<grid, block, 0, s>>>(a);
     else if (kind == SEL_NUC)
         select_kernel<SEL_NUC, false><<<grid, block, 0, s>>>(a);
+    else if (kind == SEL_NUCW)
+        select_kernel<SEL_NUCW, false><<<grid, block, 0, s>>>(a);
     else if (kind == SEL_AA)
         select_kernel<SEL_AA, false><<<grid, block, 0, s>>>(a);
     else

@@ -182,12 +182,12 @@ class GpuPlacer:
         return K, V, ov
 
     def timings(self, reset=False):
-        v = np.zeros(20, np.float64)
-        self.lib.apples_get_timings(self.h, _lib.ptr(v), 20, 1 if reset else 0)
+        v = np.zeros(21, np.float64)
+        self.lib.apples_get_timings(self.h, _lib.ptr(v), 21, 1 if reset else 0)
         keys = ['h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms', 'launches',
                 'rep_distance_launches', 'pairs', 'observed', 'valid_nodes', 'overflow_queries', 'max_observed',
                 'max_valid_nodes', 'rep_distance_sm_mhz', 'placed_smem64', 'placed_smem128', 'placed_smem256',
-                'placed_smem512', 'placed_block']
+                'placed_smem512', 'placed_block', 'fallback_queries']
         return dict(zip(keys, v.tolist()))
 
     # ------------------------------------------------------------------------------------------------ parity exports

@@ -107,7 +107,9 @@ int apples_place_batch(apples_ctx* ctx, int64_t nq, const void* packed_queries, 
  * (fasta2dic.py:42-72: upper-case letters, '-' for gaps and for letters outside the alphabet), uint8[rows][row_stride]
  * with the first L bytes of every row used.  Packing into the device layout and the per-cluster consensus
  * representatives (PoolRepresentativeWorker.py:30-85: column-wise majority in alphabet order, first maximum wins) are
- * computed on the device.  Nucleotide bytes other than A,C,G,T,- are an error. */
+ * computed on the device.  Nucleotide bytes other than A,C,G,T,- (non-letters: fasta2dic maps every other letter to '-')
+ * are ordinary characters for jc69 (distance.py:733-737); rows that hold them, and alignments longer than 65 535
+ * columns, are computed by a byte-compare fallback with 32-bit counts (exact, about 30x slower than the bit-plane path). */
 int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, const uint8_t* ref_bytes,
                                int64_t row_stride, const int32_t* ref_node, int32_t n_rep, const int32_t* group_offsets,
                                const int32_t* group_members);
@@ -150,7 +152,7 @@ int apples_edge_solutions(apples_ctx* ctx, const void* packed_query, const doubl
 
 /* test seam: per-query counts of the LAST macro-batch placed through this context (at most 2^20 queries): K = observed
  * leaves, V = valid nodes of the restricted subtree (Subtree.num_nodes, Subtree.py:42), overflowed = 1 where the query
- * went through the overflow rerun (observed set larger than the slot capacity).  Any pointer may be NULL. */
+ * went through a rerun (observed set larger than the slot capacity, or the byte-compare fallback).  Any pointer may be NULL. */
 int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32_t* overflowed);
 
 /* accumulated device time per stage since the last call with reset != 0, in milliseconds (CUDA events):
@@ -159,7 +161,7 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
  * [11] overflow reruns (queries) [12] largest observed set [13] largest restricted subtree
  * [14] effective SM clock in MHz during the last representative-distance launch (clock64 / globaltimer, in-kernel)
  * [15..19] queries placed by the shared-memory placement launches of 64 / 128 / 256 / 512 node slots and by the
- * block-per-query launch (global scratch) */
+ * block-per-query launch (global scratch)  [20] queries that went through the byte-compare fallback */
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset);
 
 /* ---- host side of SURVEY.md section 8 (f1) / (f3) in native code (no CUDA kernel involved) ---- */

@@ -332,17 +332,6 @@ def test_error_behaviour_and_ragged_inputs(workdir):
         for x, y in zip(full, part):
             assert (x[:n] == y).all()
     pl.close()
-    # nucleotide alignments longer than 65535 columns are refused (16-bit counts)
-    t2 = BackboneTree.from_newick('((A:1,B:1):1,C:1,D:1);')
-    pl2 = GpuPlacer(t2, None, t2.name_to_node, device=0)
-    W = lib.apples_words_per_row(70000)
-    z = np.zeros((4, 3, W), np.uint32)
-    rn = np.array([0, 1, 3, 4], np.int32)
-    go = np.arange(5, dtype=np.int32)
-    gm = np.arange(4, dtype=np.int32)
-    rc = lib.apples_set_reference(pl2.h, 0, 70000, 4, _lib.ptr(z), _lib.ptr(rn), 4, _lib.ptr(z), _lib.ptr(go), _lib.ptr(gm))
-    assert rc != 0 and b'65535' in lib.apples_last_error(pl2.h)
-    pl2.close()
 
 
 def test_tiny_tree_and_all_singletons(workdir):
@@ -417,11 +406,6 @@ def test_device_packer_and_consensus(case, workdir):
     ob = b.observed_sets(params, packed=b.pack_queries(seqs), self_node=sn, cap=2048)
     for x, y in zip(oa, ob):
         assert (x == y).all()
-    if not ci.protein:
-        bad = fasta.as_byte_matrix(seqs[:2], b.L).copy()
-        bad[1, 7] = ord('.')
-        with pytest.raises(RuntimeError):
-            b.place_bytes(bad, None, params)
     a.close()
     b.close()
 
@@ -768,4 +752,121 @@ def test_config5_parity_including_overflow_reruns(workdir):
         if _check_p('c5', q[0], got, p, False, octx, q) == 'tie':
             ties += 1
     assert ties <= 2
+    pl.close()
+
+
+def _oracle_check(tag, tree, tfp, refs, reps, queries, res, opt, protein=False):
+    from oracle import apples_oracle as orc
+    otree, onames = orc.load_tree(tfp)
+    octx = orc.OracleContext(otree, onames, refs=refs, representatives=reps, protein=protein, method=opt.method_name,
+                             criterion=opt.criterion_name, negative_branch=opt.negative_branch,
+                             filt_threshold=opt.filt_threshold, baseobs=opt.base_observation_threshold,
+                             overlap=opt.minimum_alignment_overlap)
+    ties = 0
+    for q, r in zip(queries, res):
+        exp, _ = octx.runquery(q[0], q[1], None)
+        assert r['placements'][0]['n'] == exp['placements'][0]['n']
+        if _check_p(tag, q[0], r['placements'][0]['p'][0], exp['placements'][0]['p'][0], False, octx, q) == 'tie':
+            ties += 1
+    return ties
+
+
+def test_symbols_outside_acgt_count_as_characters(workdir):
+    """Bytes other than A,C,G,T,- survive fasta2dic only as non-letters ('.', '*', '?', digits) and are ordinary
+    characters for jc69 (distance.py:733-737: a site counts when neither byte is '-', and mismatches when the bytes
+    differ).  The 2-bit planes cannot carry them: such QUERIES are recomputed by the byte-compare fallback inside the same
+    batch; a REFERENCE that holds them puts the whole context into byte mode.  Both against the oracle."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200.placer import GpuPlacer, place_batch
+    from apples_b200.reference import ReducedReference
+    from apples_b200 import fasta
+    ci = util.CaseInputs('c1_align_FM_MLSE', workdir)
+    tree, _ = ci.product_state()
+    rng = np.random.default_rng(99)
+    names = list(ci.refs.keys())
+    # ---- exotic queries, clean reference
+    queries = []
+    for i, (qn, qs, _) in enumerate(ci.queries):
+        s = qs.copy()
+        if i % 2 == 0:
+            for pos in rng.integers(0, len(s), 1 + 3 * i):
+                s[pos] = rng.choice([b'.', b'*', b'?', b'7'])
+        queries.append((qn, s, None))
+    twin = ci.refs[names[5]].copy()            # identical to a reference except for one exotic site: no zero shortcut
+    twin[np.flatnonzero(twin != b'-')[10]] = b'?'
+    queries.append(('twin', twin, None))
+    ref = ReducedReference(None, False, ci.tree_fp, 0.2, 1, cluster_tsv=ci.tsv, tree=tree, refs=ci.refs)
+    ref.set_baseobs(25)
+    opt = types.SimpleNamespace(method_name='FM', criterion_name='MLSE', negative_branch=False, base_observation_threshold=25,
+                                filt_threshold=0.2, minimum_alignment_overlap=0.001, exclude_intplace=False)
+    pl = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+    res = place_batch(ref, opt, tree.name_to_node, queries, tree=tree, placer=pl)
+    assert pl.timings()['fallback_queries'] == sum(1 for q in queries if not np.isin(q[1], [b'A', b'C', b'G', b'T', b'-']).all())
+    reps = orc.representatives_from_tsv(ci.tsv, ci.refs, False)
+    assert _oracle_check('exoticq', tree, ci.tree_fp, ci.refs, reps, queries, res, opt) <= 1
+    # a small slot capacity sends exotic queries through the overflow escalation of the fallback as well
+    pl.set_limits(slot_cap=8)
+    res2 = place_batch(ref, opt, tree.name_to_node, queries, tree=tree, placer=pl)
+    assert [r['placements'][0]['p'] for r in res2] == [r['placements'][0]['p'] for r in res]
+    pl.close()
+    # ---- exotic reference rows (members of clusters and singletons alike): the whole context runs in byte mode
+    refs2 = {k: v.copy() for k, v in ci.refs.items()}
+    for k in rng.choice(names, 40, replace=False):
+        row = refs2[k]
+        for pos in rng.integers(0, len(row), 5):
+            row[pos] = rng.choice([b'?', b'.'])
+    ref2 = ReducedReference(None, False, ci.tree_fp, 0.2, 1, cluster_tsv=ci.tsv, tree=tree, refs=refs2)
+    ref2.set_baseobs(25)
+    res3 = place_batch(ref2, opt, tree.name_to_node, queries, tree=tree, device=0)
+    reps2 = orc.representatives_from_tsv(ci.tsv, refs2, False)
+    assert _oracle_check('exoticr', tree, ci.tree_fp, refs2, reps2, queries, res3, opt) <= 1
+    # counts export in byte mode: the reference's definition on the raw bytes
+    pl2 = GpuPlacer(tree, ref2, tree.name_to_node, device=0)
+    clean = [q[1] for q in ci.queries[:3]]
+    mism, valid, dist = pl2.distance_counts(pl2.pack_queries(clean), 0.001)
+    for qi, qs in enumerate(clean):
+        for ri in range(0, len(pl2.ref_names), 11):
+            m, v = orc.nuc_counts(qs, refs2[pl2.ref_names[ri]])
+            assert (mism[qi, ri], valid[qi, ri]) == (m, v)
+            assert util.close(dist[qi, ri], orc.jc69(qs, refs2[pl2.ref_names[ri]], 0.001), REL, 0.0)
+    pl2.close()
+
+
+def test_alignment_longer_than_65535_columns(workdir):
+    """16-bit packed counts end at 65 535 columns; longer nucleotide alignments take the byte-compare path with 32-bit
+    counts (the reference has no limit).  80 001 columns (not a multiple of 4 or 16), 40-leaf backbone, against the oracle,
+    through the byte API and through the packed API."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200 import synth, fasta, _lib
+    from apples_b200.placer import GpuPlacer, place_batch, results_to_jplace
+    from apples_b200.reference import ReducedReference
+    from apples_b200.tree import BackboneTree
+    L = 80001
+    nwk = synth.random_tree(40, seed=5, mean_edge=0.03)
+    tfp = os.path.join(workdir, 'long.nwk')
+    open(tfp, 'w').write(nwk)
+    tree = BackboneTree.from_newick(tfp)
+    refs, states = synth.evolve_alignment(tree, L, seed=6)
+    qd, _ = synth.make_queries(tree, states, 5, seed=7)
+    queries = [(k, v, None) for k, v in qd.items()]
+    ref = ReducedReference(None, False, None, 0.2, 1, tree=tree, refs=refs)
+    ref.set_baseobs(25)
+    opt = types.SimpleNamespace(method_name='OLS', criterion_name='MLSE', negative_branch=False, base_observation_threshold=25,
+                                filt_threshold=0.2, minimum_alignment_overlap=0.001, exclude_intplace=False)
+    res = place_batch(ref, opt, tree.name_to_node, queries, tree=tree, device=0)
+    assert _oracle_check('long', tree, tfp, refs, ref.representatives, queries, res, opt) <= 1
+    # packed API (host-packed planes in): same placements
+    pl = GpuPlacer(tree, None, tree.name_to_node, device=0)
+    pl.set_reference(ref, on_device=False)
+    params = pl.params_from_options(opt, ref)
+    names = [q[0] for q in queries]
+    out = pl.place_packed(pl.pack_queries([q[1] for q in queries]), pl.self_nodes(names), params)
+    res2 = results_to_jplace(names, [False] * len(names), out, log=False)
+    assert [r['placements'][0]['p'] for r in res2] == [r['placements'][0]['p'] for r in res]
+    mism, valid, dist = pl.distance_counts(pl.pack_queries([queries[0][1]]), 0.001)
+    m, v = orc.nuc_counts(queries[0][1], refs[pl.ref_names[3]])
+    assert (mism[0, 3], valid[0, 3]) == (m, v)
+    assert valid.max() > 65535   # counts beyond 16 bits really occur
     pl.close()
