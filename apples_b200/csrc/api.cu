@@ -32,8 +32,6 @@ struct apples_ctx {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;       // host->device staging of the next sub-batch overlaps compute
-    cudaStream_t pl_stream[2] = {nullptr, nullptr};   // the placement launch classes run side by side (partial last waves)
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     std::string err;
 
@@ -646,23 +644,15 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         pa.obs_node = on;
         pa.obs_dist = od;
         pa.obs_len = ol;
-        // The launch classes are independent: the two large-footprint classes (256 / 512 node slots: 6 / 3 warps per SM) go to
-        // side streams so that their long, thin tails run beside the two big launches instead of after them.
+        // (running the classes side by side on extra streams was measured: 4.51 vs 4.56 ms per step -- the first launch fills
+        // the shared memory of every SM, so the kernels serialise anyway; kept sequential)
         Span sp_all(ctx, T_PLACE);
-        CK(cudaEventRecord(ctx->ev_fork, s));
-        bool side_used[2] = {false, false};
-        for (int c = PLACE_CLASS_512; c >= 0; --c) {
+        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
             if (!sizes[c]) continue;
-            const int side = c == PLACE_CLASS_512 ? 0 : c == PLACE_CLASS_256 ? 1 : -1;
-            cudaStream_t st = side >= 0 ? ctx->pl_stream[side] : s;
-            if (side >= 0) {
-                CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));
-                side_used[side] = true;
-            }
             pa.n = sizes[c];
             pa.qlist = d_q + begin[c];
             pa.slot_list = d_slot ? d_slot + begin[c] : nullptr;
-            CK(launch_place(prm->method, c, pa, st));
+            CK(launch_place(prm->method, c, pa, s));
             ctx->n_launch += 1;
             ctx->n_place_class[c] += sizes[c];
         }
@@ -701,11 +691,6 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             i0 = i1;
             if (i0 < iend) CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused by the next chunk
         }
-        for (int k = 0; k < 2; ++k)
-            if (side_used[k]) {
-                CK(cudaEventRecord(ctx->ev_join[k], ctx->pl_stream[k]));
-                CK(cudaStreamWaitEvent(s, ctx->ev_join[k], 0));
-            }
         return 0;
     };
 
@@ -944,11 +929,6 @@ int apples_ctx_create(int device, apples_ctx** out) {
         if (cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
             rc = -4;
-    for (int i = 0; i < 2 && !rc; ++i)
-        if (cudaStreamCreateWithFlags(&ctx->pl_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess)
-            rc = -4;
-    if (!rc && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = -4;
     if (!rc && dense_nuc_configure() != cudaSuccess) rc = -5;
     if (rc) {
         apples_ctx_destroy(ctx);  // releases whatever was created
@@ -982,11 +962,6 @@ void apples_ctx_destroy(apples_ctx* ctx) {
         if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
-    for (int i = 0; i < 2; ++i) {
-        if (ctx->pl_stream[i]) cudaStreamDestroy(ctx->pl_stream[i]);
-        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
-    }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
