@@ -22,7 +22,7 @@ FLAG_DEGENERATE = 0x200
 # every symbol the header declares (tests/test_cabi.py checks the library exports exactly these)
 SYMBOLS = [
     'apples_words_per_row', 'apples_aa_row_bytes', 'apples_device_count', 'apples_ctx_create', 'apples_ctx_destroy', 'apples_last_error',
-    'apples_ctx_stream', 'apples_ctx_set_limits', 'apples_set_tree', 'apples_set_reference', 'apples_set_matrix_columns', 'apples_place_batch',
+    'apples_ctx_stream', 'apples_ctx_set_limits', 'apples_ctx_set_dense_mode', 'apples_set_tree', 'apples_set_reference', 'apples_set_matrix_columns', 'apples_place_batch',
     'apples_place_batch_matrix', 'apples_set_reference_bytes', 'apples_place_batch_bytes', 'apples_queries_upload', 'apples_place_resident', 'apples_results_download', 'apples_results_to_device',
     'apples_distance_counts', 'apples_observed_sets', 'apples_edge_solutions', 'apples_get_timings', 'apples_last_counts',
     'apples_fasta_open', 'apples_fasta_close', 'apples_fasta_count', 'apples_fasta_max_len', 'apples_fasta_stride',
@@ -63,6 +63,7 @@ def load():
     lib.apples_ctx_stream.argtypes = [vp]
     lib.apples_ctx_stream.restype = vp
     lib.apples_ctx_set_limits.argtypes = [vp, i64, i64, i32]
+    lib.apples_ctx_set_dense_mode.argtypes = [vp, i32]
     lib.apples_set_tree.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.apples_set_reference.argtypes = [vp, C.c_int, i32, i32, vp, vp, i32, vp, vp, vp]
     lib.apples_set_matrix_columns.argtypes = [vp, i32, vp]

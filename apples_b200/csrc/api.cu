@@ -49,6 +49,11 @@ struct apples_ctx {
     bool bytes_ready = false;     // ref_bytes_p / rep_bytes_p hold the reference
     DevBuf ref_bytes_p, rep_bytes_p, q_bytes_p, q_rowflag, keys_w;
     double n_slow = 0;            // queries that went through the fallback
+    // tensor-core experiment (dense_tc.cu): 0 = integer-pipe kernel (default), 1 = tcgen05 kind::i8 kernel
+    int dense_mode = 0;
+    bool tc_ready = false;        // reps_img holds the representatives' operand images
+    int tc_nw = 0, tc_rep_pad = 0;
+    DevBuf reps_img, q_img;
     bool refs_wm_ready = false;
     // matrix mode
     int n_cols = 0;
@@ -248,6 +253,19 @@ int ensure_ref_bytes(apples_ctx* ctx, cudaStream_t s) {
     return 0;
 }
 
+// operand images of the representatives for the tensor-core kernel (after reps_rm is on the device)
+int tc_prepare_reps(apples_ctx* ctx, cudaStream_t s) {
+    ctx->tc_ready = false;
+    if (ctx->dense_mode != 1 || ctx->kind != APPLES_NUC || ctx->nuc_slow || ctx->L > dense_tc_max_sites()) return 0;
+    ctx->tc_nw = (ctx->L + 31) / 32;
+    ctx->tc_rep_pad = round_up(ctx->n_rep, dense_tc_tile_rows());
+    if (ensure(ctx, ctx->reps_img, dense_tc_image_bytes(ctx->tc_rep_pad, ctx->tc_nw))) return -1;
+    launch_tc_image((const uint32_t*)ctx->reps_rm.p, ctx->n_rep, ctx->W, ctx->tc_nw, ctx->tc_rep_pad, 127, ctx->reps_img.p, s);
+    CK(cudaGetLastError());
+    ctx->tc_ready = true;
+    return 0;
+}
+
 TreeDev tree_dev(apples_ctx* ctx) {
     TreeDev t;
     t.M = ctx->M;
@@ -314,7 +332,9 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     const int cap = std::min(ctx->slot_cap, next_pow2(std::max(4, n_leaf_bound)));
 
     const size_t qrow = matrix ? (size_t)ctx->n_cols * 8 : query_row_bytes(ctx);
-    if (ensure(ctx, ctx->keys, (size_t)QB * ldk * key_bytes)) return -1;
+    const bool use_tc = sel_kind == SEL_NUC && ctx->tc_ready;
+    if (ensure(ctx, ctx->keys, (size_t)(use_tc ? round_up(QB, 256) : QB) * ldk * key_bytes)) return -1;
+    if (use_tc && ensure(ctx, ctx->q_img, dense_tc_image_bytes(round_up(QB, 256), ctx->tc_nw))) return -1;
     const bool two_bufs = n > QB;  // more than one sub-batch: stage the next one while this one computes
     if (io.h_bytes) {
         if (ensure(ctx, ctx->q_bytes, (size_t)QB * io.byte_stride) || ensure(ctx, ctx->bad_flag, 4)) return -1;
@@ -440,6 +460,21 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             ctx->n_dense_launch += 1;
             ctx->n_pairs += (double)nb * ctx->n_rep;
             ctx->n_slow += nb;
+        } else if (sel_kind == SEL_NUC && use_tc) {
+            const int q_pad = round_up(nb, 256);
+            {
+                Span sp(ctx, T_TRANSPOSE);
+                launch_tc_image((const uint32_t*)d_q, nb, ctx->W, ctx->tc_nw, q_pad, 125, ctx->q_img.p, s);
+                ctx->n_launch += 1;
+            }
+            {
+                Span sp(ctx, T_DENSE);
+                launch_dense_tc(ctx->q_img.p, q_pad, ctx->reps_img.p, ctx->tc_rep_pad, ctx->tc_nw, (uint32_t*)ctx->keys.p, ldk,
+                                ctx->num_sms, s);
+                ctx->n_launch += 1;
+                ctx->n_dense_launch += 1;
+            }
+            ctx->n_pairs += (double)nb * ctx->n_rep;
         } else if (sel_kind == SEL_NUC) {
             {
                 Span sp(ctx, T_TRANSPOSE);
@@ -930,6 +965,7 @@ int apples_ctx_create(int device, apples_ctx** out) {
             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
             rc = -4;
     if (!rc && dense_nuc_configure() != cudaSuccess) rc = -5;
+    if (!rc && dense_tc_configure() != cudaSuccess) rc = -5;
     if (rc) {
         apples_ctx_destroy(ctx);  // releases whatever was created
         return rc;
@@ -945,7 +981,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
     DevBuf* all[] = {&ctx->t_parent, &ctx->t_elen, &ctx->t_level, &ctx->t_first, &ctx->refs_rm, &ctx->reps_rm,
                      &ctx->reps_wm, &ctx->refs_wm, &ctx->reps_nv, &ctx->refs_nv, &ctx->q_nv, &ctx->aa_tab, &ctx->reps_aa_tm, &ctx->reps_aav,
                      &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_bytes_p, &ctx->rep_bytes_p,
-                     &ctx->q_bytes_p, &ctx->q_rowflag, &ctx->keys_w, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
+                     &ctx->q_bytes_p, &ctx->q_rowflag, &ctx->keys_w, &ctx->reps_img, &ctx->q_img, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
                      &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
@@ -975,6 +1011,14 @@ int apples_ctx_set_limits(apples_ctx* ctx, int64_t max_subbatch, int64_t scratch
     if (max_subbatch > 0) ctx->max_subbatch = max_subbatch;
     if (scratch_bytes > 0) ctx->scratch_limit = (size_t)scratch_bytes;
     if (slot_cap > 0) ctx->slot_cap = next_pow2(std::max(4, slot_cap));
+    return 0;
+}
+
+int apples_ctx_set_dense_mode(apples_ctx* ctx, int32_t mode) {
+    if (!ctx) return -1;
+    if (mode != 0 && mode != 1) return fail(ctx, "apples_ctx_set_dense_mode: mode must be 0 (integer pipes) or 1 (tensor cores)");
+    ctx->dense_mode = mode;
+    ctx->tc_ready = false;   // takes effect with the next apples_set_reference*
     return 0;
 }
 
@@ -1028,7 +1072,7 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
     ctx->W = apples_words_per_row(L);
     ctx->Wp = round_up(ctx->W, DT_WC);
     ctx->Lp = apples_aa_row_bytes(L);
-    ctx->rep_pad = round_up(n_rep, DT_TR);
+    ctx->rep_pad = round_up(n_rep, ctx->dense_mode == 1 ? 256 : DT_TR);
     ctx->ref_pad = round_up(n_ref, DT_TR);
     ctx->refs_wm_ready = false;
     const size_t row = query_row_bytes(ctx);
@@ -1063,6 +1107,7 @@ int apples_set_reference(apples_ctx* ctx, int kind, int32_t L, int32_t n_ref, co
         if (ensure(ctx, ctx->reps_nv, (size_t)ctx->rep_pad * 4)) return -1;
         launch_row_valid((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_nv.p, ctx->rep_pad, ctx->stream);
         CK(cudaGetLastError());
+        if (tc_prepare_reps(ctx, ctx->stream)) return -1;
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return 0;
@@ -1131,7 +1176,7 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
     ctx->W = apples_words_per_row(L);
     ctx->Wp = round_up(ctx->W, DT_WC);
     ctx->Lp = apples_aa_row_bytes(L);
-    ctx->rep_pad = round_up(n_rep, DT_TR);
+    ctx->rep_pad = round_up(n_rep, ctx->dense_mode == 1 ? 256 : DT_TR);
     ctx->ref_pad = round_up(n_ref, DT_TR);
     ctx->refs_wm_ready = false;
     const size_t row = query_row_bytes(ctx);
@@ -1188,6 +1233,7 @@ int apples_set_reference_bytes(apples_ctx* ctx, int kind, int32_t L, int32_t n_r
         if (ensure(ctx, ctx->reps_nv, (size_t)ctx->rep_pad * 4)) return -1;
         launch_row_valid((const uint32_t*)ctx->reps_rm.p, n_rep, ctx->W, (uint32_t*)ctx->reps_nv.p, ctx->rep_pad, s);
         CK(cudaGetLastError());
+        if (tc_prepare_reps(ctx, s)) return -1;
         CK(cudaStreamSynchronize(s));
     }
     return 0;

@@ -196,6 +196,14 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
 cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s);
 cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s);
 cudaError_t dense_nuc_configure();
+// tensor-core experiment (dense_tc.cu)
+cudaError_t dense_tc_configure();
+int dense_tc_max_sites();
+int dense_tc_tile_rows();
+size_t dense_tc_image_bytes(int rows_pad, int n_w);
+void launch_tc_image(const uint32_t* planes, int rows, int W, int n_w, int rows_pad, int vw, void* out, cudaStream_t s);
+void launch_dense_tc(const void* a_img, int q_pad, const void* b_img, int r_pad, int n_w, uint32_t* keys, int64_t ldk, int num_sms,
+                     cudaStream_t s);
 cudaError_t launch_pack(int kind, const uint8_t* bytes, int64_t row_stride, int n, int L, void* out, int* bad, cudaStream_t s,
                         int* row_flag = nullptr);
 cudaError_t launch_repitch_bytes(const uint8_t* src, int64_t src_stride, int n, int L, int Lp, uint8_t* dst, cudaStream_t s);

@@ -36,6 +36,10 @@ class GpuPlacer:
             raise RuntimeError('apples_ctx_create(device=%d) failed with code %d (no usable CUDA device?)' % (device, rc))
         self.h = h
         self.device = int(device)
+        # experiment switch (dense_tc.cu): APPLES_B200_DENSE=tensor selects the tcgen05 kernel for the representative counts
+        import os as _os
+        if _os.environ.get('APPLES_B200_DENSE', '') == 'tensor':
+            self._check(self.lib.apples_ctx_set_dense_mode(self.h, 1))
         self._check(self.lib.apples_set_tree(self.h, tree.num_nodes, _lib.ptr(tree.parent), _lib.ptr(tree.edge_length),
                                              _lib.ptr(tree.level), _lib.ptr(tree.first)))
         self.reference = None
@@ -63,6 +67,10 @@ class GpuPlacer:
             self.close()
         except Exception:
             pass
+
+    def set_dense_mode(self, mode):
+        """0 = integer-pipe kernel (default), 1 = tensor-core experiment; call before set_reference."""
+        self._check(self.lib.apples_ctx_set_dense_mode(self.h, int(mode)))
 
     def set_limits(self, max_subbatch=0, scratch_bytes=0, slot_cap=0):
         self._check(self.lib.apples_ctx_set_limits(self.h, int(max_subbatch), int(scratch_bytes), int(slot_cap)))

@@ -79,6 +79,12 @@ void* apples_ctx_stream(apples_ctx* ctx);
  * overflow rerun (power of two). */
 int apples_ctx_set_limits(apples_ctx* ctx, int64_t max_subbatch, int64_t scratch_bytes, int32_t slot_cap);
 
+/* EXPERIMENT: which kernel computes the query x representative counts of nucleotide alignments.  0 (default) = the
+ * integer-pipe LOP3/POPC kernel of the north star; 1 = the tcgen05 kind::i8 tensor-core kernel (dense_tc.cu), which gives
+ * bit-identical keys.  Call before apples_set_reference*; alignments the experiment does not cover (more than 33 816
+ * columns, byte-compare fallback) keep using the default kernel. */
+int apples_ctx_set_dense_mode(apples_ctx* ctx, int32_t mode);
+
 /* Backbone tree as flat arrays over the M nodes (replaces the treeswift node graph prepared by
  * prepareTree.py:24-34 + util.py:57-88).  parent[root] = -1; edge_length of a node is the length of the edge above
  * it; level = BFS depth (root 0); first[u] = smallest id in the subtree of u. */

@@ -870,3 +870,29 @@ def test_alignment_longer_than_65535_columns(workdir):
     assert (mism[0, 3], valid[0, 3]) == (m, v)
     assert valid.max() > 65535   # counts beyond 16 bits really occur
     pl.close()
+
+
+def test_tensor_core_experiment_is_bit_identical(workdir):
+    """dense_tc.cu (opt-in): the tcgen05 kind::i8 kernel computes the query x representative counts as one int8 dot product
+    per pair (simplex embedding of the alphabet, S = 63503 * match - mismatch) and must give the SAME 32-bit keys as the
+    integer-pipe kernel -- so every result array of a batch is byte-identical between the two modes."""
+    from apples_b200 import _lib, fasta
+    from apples_b200.placer import GpuPlacer
+    nwk, tree, refs, ref, queries, _ = _synthetic(6000, 2500, 5000, 900, workdir)
+    ref.set_baseobs(25)
+    names = list(queries.keys())
+    mat = fasta.as_byte_matrix([queries[k] for k in names], 2500)
+    params = _lib.make_params('FM', 'MLSE')
+    out = []
+    for mode in (0, 1):
+        pl = GpuPlacer(tree, None, tree.name_to_node, device=0)
+        pl.set_dense_mode(mode)
+        pl.set_reference(ref)
+        pl.set_limits(max_subbatch=2048)     # several tensor-core launches incl. a ragged last one
+        out.append(pl.place_bytes(mat, None, params))
+        t = pl.timings()
+        assert t['rep_distance_launches'] >= 3
+        pl.close()
+    for x, y in zip(*out):
+        assert x.tobytes() == y.tobytes()
+    assert ((out[0][4] & 0xff) == 0).mean() > 0.9

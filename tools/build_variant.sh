@@ -10,7 +10,8 @@ out=build/variants; tmp=build/variants/obj_$name
 mkdir -p $tmp
 NV="/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $flags"
 for f in distance select placement; do $NV -fmad=false -c $src/$f.cu -o $tmp/$f.o & done
-for f in pack api; do $NV -c $src/$f.cu -o $tmp/$f.o & done
+for f in pack api dense_tc; do $NV -c $src/$f.cu -o $tmp/$f.o & done
+$NV -c $src/hostio.cpp -o $tmp/hostio.o &
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out/libapples_b200_$name.so $tmp/*.o
 rm -rf $tmp
