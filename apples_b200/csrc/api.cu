@@ -49,8 +49,10 @@ struct apples_ctx {
     bool bytes_ready = false;     // ref_bytes_p / rep_bytes_p hold the reference
     DevBuf ref_bytes_p, rep_bytes_p, q_bytes_p, q_rowflag, keys_w;
     double n_slow = 0;            // queries that went through the fallback
-    // tensor-core experiment (dense_tc.cu): 0 = integer-pipe kernel (default), 1 = tcgen05 kind::i8 kernel
-    int dense_mode = 0;
+    // representative-count kernel: 1 = tcgen05 kind::i8 tensor-core kernel (dense_tc.cu, default), 0 = integer-pipe LOP3/POPC
+    // kernel (distance.cu; also taken automatically beyond 33 816 columns)
+    int dense_mode = 1;
+    double n_tc_launch = 0;
     bool tc_ready = false;        // reps_img holds the representatives' operand images
     int tc_nw = 0, tc_rep_pad = 0;
     DevBuf reps_img, q_img;
@@ -473,6 +475,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                                 ctx->num_sms, s);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
+                ctx->n_tc_launch += 1;
             }
             ctx->n_pairs += (double)nb * ctx->n_rep;
         } else if (sel_kind == SEL_NUC) {
@@ -1441,16 +1444,17 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
 
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset) {
     if (!ctx || !out) return -1;
-    double v[21] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
+    double v[22] = {ctx->t_ms[T_H2D], ctx->t_ms[T_TRANSPOSE], ctx->t_ms[T_DENSE], ctx->t_ms[T_SELECT], ctx->t_ms[T_PLACE],
                     ctx->t_ms[T_D2H], ctx->n_launch, ctx->n_dense_launch, ctx->n_pairs, ctx->n_obs, ctx->n_valid,
                     ctx->n_over, ctx->max_K, ctx->max_V, ctx->dense_mhz, ctx->n_place_class[0], ctx->n_place_class[1],
-                    ctx->n_place_class[2], ctx->n_place_class[3], ctx->n_place_class[4], ctx->n_slow};
-    for (int i = 0; i < n && i < 21; ++i) out[i] = v[i];
+                    ctx->n_place_class[2], ctx->n_place_class[3], ctx->n_place_class[4], ctx->n_slow, ctx->n_tc_launch};
+    for (int i = 0; i < n && i < 22; ++i) out[i] = v[i];
     if (reset) {
         for (int i = 0; i < T_NSTAGE; ++i) ctx->t_ms[i] = 0;
         ctx->n_launch = ctx->n_dense_launch = ctx->n_pairs = ctx->n_obs = ctx->n_valid = ctx->n_over = ctx->max_K = ctx->max_V = 0;
         for (int c = 0; c < PLACE_NCLASS; ++c) ctx->n_place_class[c] = 0;
         ctx->n_slow = 0;
+        ctx->n_tc_launch = 0;
     }
     return 0;
 }

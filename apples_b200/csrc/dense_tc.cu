@@ -1,5 +1,6 @@
-// EXPERIMENT (opt-in, apples_ctx_set_dense_mode(ctx, 1)): the query x representative count stage on the 5th-generation
-// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), bit-exact against the LOP3/POPC kernel of distance.cu.
+// Kernel (a), default for nucleotide alignments: the query x representative count stage (apples/distance.py:733-737 as
+// called from apples/Reference.py:138-142) on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM),
+// bit-identical to the LOP3/POPC kernel of distance.cu (which stays selectable: apples_ctx_set_dense_mode(ctx, 0)).
 //
 // BASELINE.json's north star says "no tensor cores are used, since nothing here is a dense contraction".  The mismatch
 // count IS a contraction once the alphabet is embedded in a regular simplex: with
@@ -7,14 +8,14 @@
 // scaled by 126 and a fourth component that is 125 on the query side and 127 on the reference side for a valid site (all
 // four components are 0 at a gap), one site contributes
 //     126^2 * (3 or -1) + 125 * 127 = 63503 (match)  or  -1 (mismatch)  or  0 (a gap on either side)
-// to an int8 dot product with K = 4 L.  One s32 accumulator S = 63503 * match - mismatch therefore carries BOTH counts of
-// distance.py:733-737 exactly (|S| < 2^31 for L <= 33 816):
+// to an int8 dot product with K = 4 L.  One s32 accumulator S = 63503 * match - mismatch therefore carries BOTH counts
+// exactly (|S| < 2^31 for L <= 33 816):
 //     match = (S + 63503) div 63504,   mismatch = 63503 * match - S,   valid = match + mismatch.
-// The shipped default stays the integer-pipe kernel; this path exists to measure what the reformulation buys on B200
-// (DESIGN.md section 9).
+// Measured at config 5 on B200: 29.8 ms per 125 000 x 21 924 x 5000 step against 137.1 ms for the integer-pipe kernel at
+// 0.78 of its pipe roofline: the stage is compute-bound, so it belongs on the tensor cores.
 //
-// Kernel: persistent, one CTA per SM, 192 threads: warp 0 = TMA producer (1-D bulk copies of pre-arranged operand images),
-// warp 1 = MMA issuer (one thread), warps 2-5 = epilogue (tcgen05.ld, decode, 32-bit keys identical to distance.cu's).
+// Kernel: persistent, one CTA per SM: warp 0 = TMA producer (1-D bulk copies of pre-arranged operand images), warp 1 = MMA
+// issuer (one thread), warps 2-9 = epilogue (tcgen05.ld, decode, 32-bit keys identical to distance.cu's).
 // CTA tile 256 queries x 256 representatives = two M=128, N=256 accumulators (all 512 TMEM columns) sharing the B operand in
 // shared memory, 3 stages of 32 sites (128 bytes of K per row: A 32 KB + B 32 KB).  Operands are K-major, no swizzle: an
 // operand image is [k16 = 8][row block = 32][8 rows][16 bytes], i.e. 128-byte core matrices with SBO = 128 B between row
@@ -26,7 +27,8 @@ constexpr int TC_TN = 256;                 // representative rows per CTA tile
 constexpr int TC_KS = 128;                 // K bytes per row and stage = 32 sites = one plane word
 constexpr int TC_STAGES = 3;
 constexpr int TC_IMG = TC_TM * TC_KS;      // bytes of one operand image (32 KB)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;           // two per TMEM lane quarter, each takes half of the 256 columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SMEM = TC_STAGES * 2 * TC_IMG + 1024 + 256;   // + alignment slack + barriers
 constexpr int TC_W = 63504;                // 4 * 126^2
 constexpr int TC_MAX_L = 33816;            // 63503 * L < 2^31
@@ -80,43 +82,61 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// operand images: bit-planes [rows][3][W] -> int8 [rows_pad / 256][n_w][8][32][8][16]  (one 32 KB image per tile and word)
-// one thread per 16 output bytes (= 4 sites x 4 components); `vw` = the value of the fourth component (125 / 127)
+// operand images: bit-planes [rows][3][W] -> int8 [rows_pad / 256][n_w][8][32][8][16]  (one 32 KB image per tile and word).
+// One block per (tile of 256 rows, chunk of 32 words): the plane words are read coalesced along the row (32 consecutive
+// words = 128 bytes per warp load) into shared memory, then every thread writes 16-byte pieces (4 sites x 4 components) so
+// that a warp writes 512 contiguous bytes.  `vw` = the value of the fourth component (125 queries / 127 references).
+// HBM-bound: 128 bytes written per 12 bytes read.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void tc_image_kernel(const uint32_t* __restrict__ planes, int rows, int W, int n_w, int rows_pad, int vw,
-                                uint4* __restrict__ out) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)(rows_pad / TC_TM) * n_w * (TC_IMG / 16);
-    if (t >= total) return;
-    const int r8 = (int)(t & 7), rb = (int)((t >> 3) & 31), k16 = (int)((t >> 8) & 7);
-    const int64_t img = t >> 11;
-    const int w = (int)(img % n_w);
-    const int row = (int)(img / n_w) * TC_TM + rb * 8 + r8;
-    uint32_t lo = 0, hi = 0, va = 0;
-    if (row < rows) {
-        const uint32_t* p = planes + (size_t)row * 3 * W + w;
-        lo = p[0];
-        hi = p[W];
-        va = p[2 * W];
+constexpr int TCI_WCH = 32;   // words per block
+__global__ void __launch_bounds__(256) tc_image_kernel(const uint32_t* __restrict__ planes, int rows, int W, int n_w, int vw,
+                                                       uint4* __restrict__ out) {
+    extern __shared__ uint32_t sp[];   // [3][256][TCI_WCH + 1]
+    const int tile = blockIdx.y, w0 = blockIdx.x * TCI_WCH;
+    const int row0 = tile * TC_TM;
+    for (int idx = threadIdx.x; idx < 3 * TC_TM * TCI_WCH; idx += 256) {
+        const int wl = idx % TCI_WCH, p = (idx / TCI_WCH) % 3, r = idx / (3 * TCI_WCH);
+        uint32_t x = 0;
+        if (row0 + r < rows && w0 + wl < n_w) x = planes[((size_t)(row0 + r) * 3 + p) * W + w0 + wl];
+        sp[(p * TC_TM + r) * (TCI_WCH + 1) + wl] = x;
     }
-    uint32_t o[4];
+    __syncthreads();
+    const int nwl = min(TCI_WCH, n_w - w0);
+    for (int wl = 0; wl < nwl; ++wl) {
+        uint4* img = out + ((size_t)tile * n_w + w0 + wl) * (TC_IMG / 16);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int s = k16 * 4 + j;
-        const uint32_t l = (lo >> s) & 1u, h = (hi >> s) & 1u, v = (va >> s) & 1u;
-        // A(0)=(+,+,+) C(1)=(+,-,-) G(2)=(-,+,-) T(3)=(-,-,+), code = lo | hi << 1
-        const uint32_t x = h ? 0x82u : 0x7eu;           // -126 : +126
-        const uint32_t y = l ? 0x82u : 0x7eu;
-        const uint32_t z = (l ^ h) ? 0x82u : 0x7eu;
-        o[j] = v ? (x | (y << 8) | (z << 16) | ((uint32_t)vw << 24)) : 0u;
+        for (int i = 0; i < TC_IMG / 16 / 256; ++i) {
+            const int t = threadIdx.x + 256 * i;          // uint4 index inside the image: ((k16 * 32 + rb) * 8 + r8)
+            const int r = ((t >> 3) & 31) * 8 + (t & 7), k16 = t >> 8;
+            const uint32_t lo = sp[(0 * TC_TM + r) * (TCI_WCH + 1) + wl], hi = sp[(1 * TC_TM + r) * (TCI_WCH + 1) + wl],
+                           va = sp[(2 * TC_TM + r) * (TCI_WCH + 1) + wl];
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = k16 * 4 + j;
+                const uint32_t l = (lo >> s) & 1u, h = (hi >> s) & 1u, v = (va >> s) & 1u;
+                // A(0)=(+,+,+) C(1)=(+,-,-) G(2)=(-,+,-) T(3)=(-,-,+), code = lo | hi << 1; 0x7e = +126, 0x82 = -126
+                const uint32_t x = h ? 0x82u : 0x7eu;
+                const uint32_t y = l ? 0x82u : 0x7eu;
+                const uint32_t z = (l ^ h) ? 0x82u : 0x7eu;
+                o[j] = v ? (x | (y << 8) | (z << 16) | ((uint32_t)vw << 24)) : 0u;
+            }
+            img[t] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
     }
-    out[t] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+static const int TCI_SMEM = 3 * TC_TM * (TCI_WCH + 1) * 4;
+
 void launch_tc_image(const uint32_t* planes, int rows, int W, int n_w, int rows_pad, int vw, void* out, cudaStream_t s) {
-    const int64_t total = (int64_t)(rows_pad / TC_TM) * n_w * (TC_IMG / 16);
-    if (total <= 0) return;
-    tc_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(planes, rows, W, n_w, rows_pad, vw, (uint4*)out);
+    if (rows_pad <= 0 || n_w <= 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tc_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCI_SMEM);
+        configured = true;
+    }
+    dim3 grid((n_w + TCI_WCH - 1) / TCI_WCH, rows_pad / TC_TM);
+    tc_image_kernel<<<grid, 256, TCI_SMEM, s>>>(planes, rows, W, n_w, vw, (uint4*)out);
 }
 
 struct TcArgs {
@@ -164,7 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const TcArgs a)
             tc_mbar_init(&empty[s], 1);
         }
         tc_mbar_init(tfull, 1);
-        tc_mbar_init(tempty, 4);   // one arrival per epilogue warp
+        tc_mbar_init(tempty, TC_EPI_WARPS);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: all 512 columns (two 128 x 256 s32 accumulators)
@@ -220,8 +240,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const TcArgs a)
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
+        // ===== epilogue: a warp can read the TMEM lanes 32 * (warp % 4) .. + 31; two warps share a quarter, 128 columns each =====
         const int quarter = warp & 3;
+        const int c0 = ((warp - 2) >> 2) * (TC_TN / 2);
         uint32_t tl = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
             int qt, rt;
@@ -233,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const TcArgs a)
                 const int row = qt * TC_TM + h * 128 + quarter * 32 + lane;
                 uint32_t* out = a.keys + (size_t)row * a.ldk + (size_t)rt * TC_TN;
 #pragma unroll 1
-                for (int c = 0; c < TC_TN; c += 32) {
+                for (int c = c0; c < c0 + TC_TN / 2; c += 32) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(h * TC_TN + c);
                     asm volatile(

@@ -36,10 +36,11 @@ class GpuPlacer:
             raise RuntimeError('apples_ctx_create(device=%d) failed with code %d (no usable CUDA device?)' % (device, rc))
         self.h = h
         self.device = int(device)
-        # experiment switch (dense_tc.cu): APPLES_B200_DENSE=tensor selects the tcgen05 kernel for the representative counts
+        # A/B switch for measurements: APPLES_B200_DENSE=intpipe selects the integer-pipe LOP3/POPC kernel for the
+        # representative counts instead of the default tensor-core kernel (identical results)
         import os as _os
-        if _os.environ.get('APPLES_B200_DENSE', '') == 'tensor':
-            self._check(self.lib.apples_ctx_set_dense_mode(self.h, 1))
+        if _os.environ.get('APPLES_B200_DENSE', '') == 'intpipe':
+            self._check(self.lib.apples_ctx_set_dense_mode(self.h, 0))
         self._check(self.lib.apples_set_tree(self.h, tree.num_nodes, _lib.ptr(tree.parent), _lib.ptr(tree.edge_length),
                                              _lib.ptr(tree.level), _lib.ptr(tree.first)))
         self.reference = None
@@ -69,7 +70,7 @@ class GpuPlacer:
             pass
 
     def set_dense_mode(self, mode):
-        """0 = integer-pipe kernel (default), 1 = tensor-core experiment; call before set_reference."""
+        """1 = tensor-core kernel (default), 0 = integer-pipe kernel; identical results; call before set_reference."""
         self._check(self.lib.apples_ctx_set_dense_mode(self.h, int(mode)))
 
     def set_limits(self, max_subbatch=0, scratch_bytes=0, slot_cap=0):
@@ -190,12 +191,12 @@ class GpuPlacer:
         return K, V, ov
 
     def timings(self, reset=False):
-        v = np.zeros(21, np.float64)
-        self.lib.apples_get_timings(self.h, _lib.ptr(v), 21, 1 if reset else 0)
+        v = np.zeros(22, np.float64)
+        self.lib.apples_get_timings(self.h, _lib.ptr(v), 22, 1 if reset else 0)
         keys = ['h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms', 'launches',
                 'rep_distance_launches', 'pairs', 'observed', 'valid_nodes', 'overflow_queries', 'max_observed',
                 'max_valid_nodes', 'rep_distance_sm_mhz', 'placed_smem64', 'placed_smem128', 'placed_smem256',
-                'placed_smem512', 'placed_block', 'fallback_queries']
+                'placed_smem512', 'placed_block', 'fallback_queries', 'tensor_core_launches']
         return dict(zip(keys, v.tolist()))
 
     # ------------------------------------------------------------------------------------------------ parity exports

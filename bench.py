@@ -47,6 +47,9 @@ def parse(argv=None):
     ap.add_argument('--cpu-sample', type=int, default=0, help='queries in the CPU-baseline sample (0 = auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--dense', default='tensor', choices=['tensor', 'intpipe'],
+                    help='kernel of the representative counts: tcgen05 tensor-core kernel (default) or the integer-pipe '
+                         'LOP3/POPC kernel (identical results)')
     ap.add_argument('--no-cli', action='store_true', help='skip the run_apples.py command-line measurement (cli_e2e)')
     ap.add_argument('--slot-cap', type=int, default=0, help='observed-list slots per query before a rerun (0 = library default)')
     ap.add_argument('--sub-batch', type=int, default=0, help='queries per dense/selection launch (0 = library default)')
@@ -312,6 +315,7 @@ def main():
     tree, arrays, packed_q, q_bytes, info, host = build_workload(args, device, rank, want_host)
     nq = args.queries_per_gpu
     pl = GpuPlacer(tree, None, tree.name_to_node, device=local_rank)
+    pl.set_dense_mode(0 if args.dense == 'intpipe' else 1)
     pl.set_reference_arrays(**arrays)
     if args.slot_cap or args.sub_batch:
         pl.set_limits(max_subbatch=args.sub_batch, slot_cap=args.slot_cap)
@@ -486,6 +490,28 @@ def main():
                 'plain_popcount_peak': plain_peak / 1e12, 'frac_of_plain_popcount_peak': cs_rate / plain_peak,
                 'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
                         'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg_bytes}}
+    used_tc = tm.get('tensor_core_launches', 0) > 0
+    if used_tc and not prot:
+        # tensor-core kernel: one int8 dot product of K = 4 components x 32-site words per (query, representative)
+        n_w = (args.sites + 31) // 32
+        ops = 2.0 * q_per_launch * n_rep * n_w * 128
+        tops = ops / (dense_ms * 1e-3) / 1e12
+        bf16_burst = float(peaks.get('bf16_tflops', 1590.0))
+        bf16_sust = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        nominal = 4500.0
+        img_bytes = (q_per_launch + n_rep) * n_w * 128.0 + 4.0 * q_per_launch * n_rep
+        roofline = {'kernel': 'dense_tc_kernel (tcgen05.mma kind::i8, query x representative mismatch/valid counts as one int8 dot '
+                              'product per pair)', 'bound': 'tensor', 'achieved': tops, 'peak': nominal, 'unit': 'TOP/s (int8)',
+                    'frac': tops / nominal, 'traffic': None, 'avg_launch_ms': dense_ms, 'launches': n_dense,
+                    'peak_source': 'nominal dense int8 (4.5 POP/s = 2 x nominal bf16): MEASURED_PEAKS.json holds no int8 figure; '
+                                   'against 2 x the measured bf16 GEMM (%s) the fraction is %.2f burst (2 x %.0f) / %.2f '
+                                   'sustained (2 x %.0f)' % (peak_src, tops / (2 * bf16_burst), bf16_burst,
+                                                             tops / (2 * bf16_sust), bf16_sust),
+                    'algorithmic_ops_per_launch': ops,
+                    'cell_sites_per_s': cs_rate, 'vs_int_pipe_balanced_peak': cs_rate / bal_peak,
+                    'hbm': {'achieved': img_bytes / (dense_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                            'frac': img_bytes / (dense_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': peak_src,
+                            'algorithmic_bytes_per_launch': img_bytes}}
     if prot:
         # amino-acid dense kernel: one BLOSUM45 lookup (two conflict-free 32-bit shared-memory loads) per (query,
         # representative, site).  Bound by the shared-memory pipe: 32 banks x 4 B per clock per SM = one 32-lane LDS.32
@@ -527,8 +553,9 @@ def main():
     stages = {k: tm[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms', 'placement_ms', 'd2h_ms')}
     line = {'metric': 'queries placed/sec', 'value': value, 'unit': 'queries/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u8 codes, 44-bit fixed-point table sums + f64' if prot else 'u32 popcount + f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'n_representatives': n_rep, 'queries_per_step': nq * world,
+            'dtype': ('u8 codes, 44-bit fixed-point table sums + f64' if prot else
+                      ('int8 (s32 accumulate) + f64' if used_tc else 'u32 popcount + f64')), 'data': 'synthetic',
+            'config': {'workload': workload, 'dense_kernel': 'tensor' if used_tc else ('lookup' if prot else 'intpipe'), 'n_representatives': n_rep, 'queries_per_step': nq * world,
                        'l2': 'inputs larger than L2 (packed queries %.0f MB + packed reference %.0f MB per GPU)'
                              % (nq * row_bytes / 1e6, (args.leaves + n_rep) * row_bytes / 1e6),
                        'parallelism': 'queries sharded over %d GPU(s), reference + tree replicated, final NCCL all-gather' % world},

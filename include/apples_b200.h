@@ -79,10 +79,11 @@ void* apples_ctx_stream(apples_ctx* ctx);
  * overflow rerun (power of two). */
 int apples_ctx_set_limits(apples_ctx* ctx, int64_t max_subbatch, int64_t scratch_bytes, int32_t slot_cap);
 
-/* EXPERIMENT: which kernel computes the query x representative counts of nucleotide alignments.  0 (default) = the
- * integer-pipe LOP3/POPC kernel of the north star; 1 = the tcgen05 kind::i8 tensor-core kernel (dense_tc.cu), which gives
- * bit-identical keys.  Call before apples_set_reference*; alignments the experiment does not cover (more than 33 816
- * columns, byte-compare fallback) keep using the default kernel. */
+/* Which kernel computes the query x representative mismatch / overlap counts of nucleotide alignments.
+ * 1 (default) = the tcgen05 kind::i8 tensor-core kernel (dense_tc.cu): the two counts of distance.py:733-737 as ONE int8 dot
+ * product per pair (simplex embedding of A,C,G,T; exact s32 accumulation in TMEM); 0 = the integer-pipe LOP3/POPC kernel of
+ * the north star (distance.cu).  Both give bit-identical 32-bit keys.  Call before apples_set_reference*.  Alignments the
+ * tensor-core kernel does not cover (more than 33 816 columns) use the integer-pipe kernel automatically. */
 int apples_ctx_set_dense_mode(apples_ctx* ctx, int32_t mode);
 
 /* Backbone tree as flat arrays over the M nodes (replaces the treeswift node graph prepared by
@@ -167,7 +168,8 @@ int apples_last_counts(apples_ctx* ctx, int64_t n, int32_t* K, int32_t* V, int32
  * [11] overflow reruns (queries) [12] largest observed set [13] largest restricted subtree
  * [14] effective SM clock in MHz during the last representative-distance launch (clock64 / globaltimer, in-kernel)
  * [15..19] queries placed by the shared-memory placement launches of 64 / 128 / 256 / 512 node slots and by the
- * block-per-query launch (global scratch)  [20] queries that went through the byte-compare fallback */
+ * block-per-query launch (global scratch)  [20] queries that went through the byte-compare fallback
+ * [21] representative-distance launches that ran on the tensor cores */
 int apples_get_timings(apples_ctx* ctx, double* out, int n, int reset);
 
 /* ---- host side of SURVEY.md section 8 (f1) / (f3) in native code (no CUDA kernel involved) ---- */
