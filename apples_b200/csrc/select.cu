@@ -25,6 +25,11 @@
 
 #define FULLMASK 0xffffffffu
 
+// software prefetch into L2: the key rows come straight from DRAM (the dense kernel wrote 11 GB since), the member rows
+// are random rows of a 384 MB array; the scan and the member loop wait on exactly these loads (ncu: 46 % of the stall
+// samples of round 1's kernel)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int KIND>
 struct Key;
 
@@ -401,6 +406,11 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
             }
         } else if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
+            {   // all member rows of the cluster, 128-byte lines spread over the lanes
+                const int lines = (3 * a.W * 4 + 127) / 128;
+                for (int i = lane; i < (e - b) * lines; i += 32)
+                    prefetch_l2(reinterpret_cast<const char*>(a.refs_nuc + (size_t)a.gmem[b + i / lines] * 3 * a.W) + (i % lines) * 128);
+            }
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
                 int rows[NR];
                 uint32_t c[NR];
@@ -492,6 +502,14 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
     constexpr int U = 8;  // independent loads in flight per lane
     Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
     for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * U) {
+        {   // the 128-byte lines of the chunk after next (32 * U keys = 8 or 16 lines per chunk)
+            constexpr int PER_LINE = 128 / (int)sizeof(Raw);
+            const int u = u0 + 2 * 32 * U + lane * PER_LINE;
+            if (lane < 32 * U / PER_LINE && u < a.n_units) {
+                if constexpr (KIND == SEL_NUC) prefetch_l2(a.keys_nuc + (size_t)slot * a.ldk + u);
+                else prefetch_l2(a.keys_f64 + (size_t)slot * a.ldk + u);
+            }
+        }
         Raw raw[U];
 #pragma unroll
         for (int j = 0; j < U; ++j) {

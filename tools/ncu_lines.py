@@ -20,7 +20,7 @@ import tempfile
 
 def main():
     rep, so, cubin, func = sys.argv[1:5]
-    top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+    top = int(sys.argv[5]) if len(sys.argv) > 5 else 40   # argv[6]: optional substring of the demangled name (template args)
     tmp = tempfile.mkdtemp()
     subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(so)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
     dis = subprocess.run(['nvdisasm', '-g', os.path.join(tmp, cubin)], capture_output=True, text=True, check=True).stdout
@@ -38,6 +38,18 @@ def main():
             seq.append((m.group(2), cur))
     out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # a report with several captured launches lists them one after the other, each introduced by a "Kernel Name" row: take
+    # the LAST launch whose demangled name starts like the function asked for (APPLES_NCU_PICK=n selects the n-th instead)
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    m0 = re.match(r'_Z(\d+)', func)
+    want = func[m0.end():m0.end() + int(m0.group(1))] if m0 else func
+    cand = [i for i in starts if want in rows[i][1]]
+    if len(sys.argv) > 6:
+        cand = [i for i in cand if sys.argv[6] in rows[i][1]]
+    pick = int(os.environ.get('APPLES_NCU_PICK', '-1'))
+    st = cand[pick]
+    en = next((i for i in starts if i > st), len(rows))
+    rows = rows[st:en]
     h = rows[1]
     si, ii, so_, ti = h.index('# Samples'), h.index('Instructions Executed'), h.index('Source'), h.index('Thread Instructions Executed')
     prof = [(r[so_].strip(), int(r[si]), int(r[ii]), int(r[ti])) for r in rows[2:] if len(r) > ii]
