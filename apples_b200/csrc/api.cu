@@ -2,6 +2,7 @@
 //   H2D -> transpose -> dense representative distances -> selection (+ member distances) -> placement -> D2H
 // that replaces pool.starmap(queryworker.runquery, queries) (run_apples.py:94-102).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -33,6 +34,10 @@ struct apples_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;       // host->device staging of the next sub-batch overlaps compute
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // the placement of the ordinary queries runs here while the reruns of the few large / exotic ones (thin, long kernels)
+    // occupy the main stream
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
 
     // tree
@@ -64,7 +69,7 @@ struct apples_ctx {
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
     DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
-    DevBuf obs_node2, obs_dist2, qlist, pl_lists, rec_off, stack_off, recs, stacks;
+    DevBuf obs_node2, obs_dist2, qlist, pl_lists, pl_lists2, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
     // resident queries
@@ -85,7 +90,7 @@ struct apples_ctx {
     std::vector<int> h_first;      // host copy of first[]: node u is a leaf iff first[u] == u
     std::vector<int> h_ref_node, h_col_node;  // re-validated when the tree changes
     std::vector<long long> h_rec_off, h_stack_off;
-    std::vector<int> h_pl_lists;
+    std::vector<int> h_pl_lists, h_pl_lists2;
     double n_place_class[PLACE_NCLASS] = {0, 0, 0, 0, 0};
     std::vector<char> h_gather;
     int slot_cap = 256;
@@ -316,6 +321,14 @@ int check_params(apples_ctx* ctx, const apples_params* p) {
 //   phase 4  results D2H / D2D
 int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const apples_params* prm) {
     cudaStream_t s = ctx->stream;
+    // APPLES_B200_TRACE=1: host wall-clock of the pipeline phases of every macro-batch on stderr (debugging aid)
+    static const bool trace = getenv("APPLES_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        fprintf(stderr, "[apples_b200] %-28s +%8.3f ms\n", what, ms);
+    };
     const bool matrix = io.h_rows != nullptr;
     const bool nuc = !matrix && ctx->kind == APPLES_NUC;
     const bool slow_ctx = nuc && ctx->nuc_slow;   // byte-compare fallback for every query of this context
@@ -598,6 +611,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (used[buf]) CK(cudaEventRecord(ctx->ev_free[buf], s));
     }
 
+    mark("phase 1 launched");
     // ---------------- phase 2 ----------------
     auto fetch_counts = [&]() -> int {
         Span sp(ctx, T_D2H);
@@ -608,6 +622,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     };
     if (fetch_counts()) return -1;
     CK(cudaStreamSynchronize(s));
+    mark("phase 1 done on the device");
     // queries holding bytes other than A,C,G,T,- (they survive fasta2dic only as non-letters and count as ordinary
     // characters in jc69, distance.py:733-737): the 2-bit planes cannot carry them, so those queries are recomputed by the
     // byte-compare fallback below; their first-pass results are discarded
@@ -646,8 +661,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     // four shared-memory launches (V + 1 <= 64 / 128 / 256 / 512) and one block-per-query launch with global scratch, chunked
     // if the scratch pool would be exceeded.
     auto place_entries = [&](int cnt, auto id, auto active, bool entry_slots, int capx, const int* on, const double* od,
-                             const int* ol) -> int {
-        std::vector<int>& L = ctx->h_pl_lists;
+                             const int* ol, cudaStream_t st, DevBuf& dl, std::vector<int>& L) -> int {
         L.clear();
         int begin[PLACE_NCLASS + 1];
         // pass 1: class sizes; pass 2: fill (query ids first, then the slot rows in the second half of the buffer)
@@ -674,9 +688,9 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             L[pos] = qi;
             L[(size_t)total + pos] = i;
         }
-        if (ensure(ctx, ctx->pl_lists, (size_t)2 * total * 4)) return -1;
-        CK(cudaMemcpyAsync(ctx->pl_lists.p, L.data(), (size_t)(entry_slots ? 2 : 1) * total * 4, cudaMemcpyHostToDevice, s));
-        const int* d_q = (const int*)ctx->pl_lists.p;
+        if (ensure(ctx, dl, (size_t)2 * total * 4)) return -1;
+        CK(cudaMemcpyAsync(dl.p, L.data(), (size_t)(entry_slots ? 2 : 1) * total * 4, cudaMemcpyHostToDevice, st));
+        const int* d_q = (const int*)dl.p;
         const int* d_slot = entry_slots ? d_q + total : nullptr;
         pa.cap = capx;
         pa.obs_node = on;
@@ -684,13 +698,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         pa.obs_len = ol;
         // (running the classes side by side on extra streams was measured: 4.51 vs 4.56 ms per step -- the first launch fills
         // the shared memory of every SM, so the kernels serialise anyway; kept sequential)
-        Span sp_all(ctx, T_PLACE);
+        Span sp_all(ctx, T_PLACE, st);
         for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
             if (!sizes[c]) continue;
             pa.n = sizes[c];
             pa.qlist = d_q + begin[c];
             pa.slot_list = d_slot ? d_slot + begin[c] : nullptr;
-            CK(launch_place(prm->method, c, pa, s));
+            CK(launch_place(prm->method, c, pa, st));
             ctx->n_launch += 1;
             ctx->n_place_class[c] += sizes[c];
         }
@@ -715,8 +729,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             h_stack_off[i1 - i0] = stk;
             if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * PLACE_NODE_SLOT_BYTES)) return -1;
             if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * PLACE_CHAIN_SLOT_BYTES)) return -1;
-            CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
-            CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, st));
             pa.n = i1 - i0;
             pa.qlist = d_q + i0;
             pa.slot_list = d_slot ? d_slot + i0 : nullptr;
@@ -724,10 +738,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             pa.stack_off = (const long long*)ctx->stack_off.p;
             pa.recs = ctx->recs.p;
             pa.stacks = ctx->stacks.p;
-            CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, s));
+            CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, st));
             ctx->n_launch += 1;
             i0 = i1;
-            if (i0 < iend) CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused by the next chunk
+            if (i0 < iend) CK(cudaStreamSynchronize(st));  // the scratch pool and the offset arrays are reused by the next chunk
         }
         return 0;
     };
@@ -831,7 +845,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 if (!io.stop_after_select) {
                     const int* ov = list.data() + o0;
                     if (place_entries(ng, [&](int i) { return ov[i]; }, [&](int) { return true; }, true, cap2,
-                                      (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p))
+                                      (const int*)ctx->obs_node2.p, (const double*)ctx->obs_dist2.p, (const int*)ctx->obs_len2.p, s,
+                                      ctx->pl_lists, ctx->h_pl_lists))
                         return -1;
                     CK(cudaStreamSynchronize(s));
                 }
@@ -845,9 +860,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
         return 0;
     };
+    // (Starting the placement of the ordinary queries on a side stream beside the rerun kernels was measured: the step did
+    // not change -- the rerun kernels then run with fewer resident blocks and take as much longer as the overlap saves.)
+    const bool main_placed = false;
     if (!exotic.empty() && rerun(exotic, true, cap, false)) return -1;
     if (!over.empty() && rerun(over, slow_ctx, (int)std::min<int64_t>((int64_t)cap * 16, cap_max), use_stash)) return -1;
 
+    mark("reruns done");
     // ---------------- parity export of the observed sets ----------------
     if (io.obs_count) {
         const int ocap = io.obs_cap;
@@ -872,9 +891,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
     if (!io.stop_after_select) {
         // ---------------- phase 3 ----------------
-        if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, false, cap,
-                          (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p, (const int*)ctx->obs_len.p))
+        if (main_placed) {
+            CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        } else if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, false, cap,
+                                 (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p, (const int*)ctx->obs_len.p, s,
+                                 ctx->pl_lists, ctx->h_pl_lists)) {
             return -1;
+        }
         {   // zero-distance shortcut / too-few-distances records of the whole batch
             Span sp(ctx, T_PLACE);
             pa.n = n;
@@ -893,6 +916,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
     }
     CK(cudaStreamSynchronize(s));
+    mark("batch done");
     if (dbg) {
         CK(cudaMemcpy(io.dbg_x1, ctx->dbg_x1.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(io.dbg_x2, ctx->dbg_x2.p, (size_t)ctx->M * 8, cudaMemcpyDeviceToHost));
@@ -967,6 +991,10 @@ int apples_ctx_create(int device, apples_ctx** out) {
         if (cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
             rc = -4;
+    if (!rc && (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess))
+        rc = -4;
     if (!rc && dense_nuc_configure() != cudaSuccess) rc = -5;
     if (!rc && dense_tc_configure() != cudaSuccess) rc = -5;
     if (rc) {
@@ -986,7 +1014,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
                      &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_bytes_p, &ctx->rep_bytes_p,
                      &ctx->q_bytes_p, &ctx->q_rowflag, &ctx->keys_w, &ctx->reps_img, &ctx->q_img, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists, &ctx->pl_lists2,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,
@@ -1001,6 +1029,12 @@ void apples_ctx_destroy(apples_ctx* ctx) {
         if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
+    if (ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
