@@ -69,7 +69,7 @@ struct apples_ctx {
     DevBuf q_rm, q_wm, keys, self_node, obs_node, obs_dist, obs_len, obs_len2, Kd, Vd, statusd, zero_edge, pair_counter;
     DevBuf q_bytes, q_bytes2, q_rm2, bad_flag, clk_probe, stash_keys, stash_ids, stash_count;
     double dense_mhz = 0.0;  // effective SM clock of the last dense launch (clock64 / globaltimer of CTA 0)
-    DevBuf obs_node2, obs_dist2, qlist, pl_lists, pl_lists2, rec_off, stack_off, recs, stacks;
+    DevBuf obs_node2, obs_dist2, qlist, pl_lists, pl_lists2, bin_counts, bin_lists, rec_off, stack_off, recs, stacks;
     DevBuf o_edge, o_err, o_distal, o_pendant, o_status;
     DevBuf dbg_x1, dbg_x2, dbg_err, dbg_valid;
     // resident queries
@@ -160,9 +160,16 @@ struct Span {
 };
 
 void collect_spans(apples_ctx* ctx) {
+    static const bool trace = getenv("APPLES_B200_TRACE") != nullptr;
+    static const char* names[] = {"h2d", "transpose", "dense", "select", "place", "d2h"};
     for (auto& s : ctx->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ctx->t_ms[s.stage] += ms;
+        if (trace && !ctx->spans.empty()) {   // device timeline: start of every span relative to the first one
+            float off = 0.f;
+            cudaEventElapsedTime(&off, ctx->spans.front().a, s.a);
+            fprintf(stderr, "[apples_b200]   dev %-9s @%8.3f ms  %7.3f ms\n", names[s.stage], off, ms);
+        }
         ctx->ev_pool.push_back(s.a);
         ctx->ev_pool.push_back(s.b);
     }
@@ -390,6 +397,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         ensure(ctx, ctx->qlist, (size_t)std::max(n, 1) * 4) || ensure(ctx, ctx->pl_lists, (size_t)std::max(n, 1) * 8))
         return -1;
     CK(cudaMemsetAsync(ctx->pair_counter.p, 0, 8, s));
+    if (ensure(ctx, ctx->bin_counts, 64) || ensure(ctx, ctx->bin_lists, (size_t)PLACE_NCLASS * std::max(n, 1) * 4)) return -1;
+    CK(cudaMemsetAsync(ctx->bin_counts.p, 0, 64, s));
     const bool dbg = io.dbg_x1 != nullptr;
     if (dbg) {
         if (ensure(ctx, ctx->dbg_x1, (size_t)ctx->M * 8) || ensure(ctx, ctx->dbg_x2, (size_t)ctx->M * 8) ||
@@ -611,6 +620,15 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (used[buf]) CK(cudaEventRecord(ctx->ev_free[buf], s));
     }
 
+    // launch classes of the placeable queries, sorted on the device (counts: 5 ints at offset 0, stats: 4 u64 at offset 32)
+    CK(launch_bin_classes(n, (const int*)ctx->statusd.p, (const int*)ctx->Kd.p, (const int*)ctx->Vd.p,
+                          (io.h_bytes && nuc && !slow_ctx) ? (const int*)ctx->q_rowflag.p : nullptr, (int*)ctx->bin_counts.p,
+                          (int*)ctx->bin_lists.p, (unsigned long long*)((char*)ctx->bin_counts.p + 32), s));
+    ctx->n_launch += 1;
+    int h_bin[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long h_bin_stats[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h_bin, ctx->bin_counts.p, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_bin_stats, (char*)ctx->bin_counts.p + 32, 32, cudaMemcpyDeviceToHost, s));
     mark("phase 1 launched");
     // ---------------- phase 2 ----------------
     auto fetch_counts = [&]() -> int {
@@ -827,8 +845,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_st, slow, (const uint8_t*)ctx->q_bytes_p.p,
                                          slow_ctx ? ctx->keys.p : ctx->keys_w.p))
                     return -1;
+                mark("  rerun select launched");
                 if (fetch_counts()) return -1;
                 CK(cudaStreamSynchronize(s));
+                mark("  rerun select done");
                 if (io.obs_count) {
                     std::vector<int> un((size_t)ng * cap2);
                     std::vector<double> ud((size_t)ng * cap2);
@@ -860,9 +880,69 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
         return 0;
     };
-    // (Starting the placement of the ordinary queries on a side stream beside the rerun kernels was measured: the step did
-    // not change -- the rerun kernels then run with fewer resident blocks and take as much longer as the overlap saves.)
-    const bool main_placed = false;
+    // The ordinary queries are placed first, straight from the class lists the device built: no host pass over the batch
+    // stands between the last selection kernel and the placement launches, and the host prepares the reruns meanwhile.
+    // (Running this pass on a side stream BESIDE the rerun kernels was measured: the step did not change -- the rerun
+    // kernels then run with fewer resident blocks and take as much longer as the overlap saves.)
+    bool main_placed = false;
+    if (trace) fprintf(stderr, "[apples_b200] classes %d %d %d %d %d\n", h_bin[0], h_bin[1], h_bin[2], h_bin[3], h_bin[4]);
+    if (!io.stop_after_select) {
+        pa.cap = cap;
+        pa.obs_node = (const int*)ctx->obs_node.p;
+        pa.obs_dist = (const double*)ctx->obs_dist.p;
+        pa.obs_len = (const int*)ctx->obs_len.p;
+        pa.slot_list = nullptr;
+        Span sp(ctx, T_PLACE);
+        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
+            if (!h_bin[c]) continue;
+            pa.n = h_bin[c];
+            pa.qlist = (const int*)ctx->bin_lists.p + (size_t)c * n;
+            CK(launch_place(prm->method, c, pa, s));
+            ctx->n_launch += 1;
+            ctx->n_place_class[c] += h_bin[c];
+        }
+        // the few ordinary queries with more than 511 valid nodes (long unary paths): block-per-query kernel, scratch sized
+        // on the host from their counts
+        const int nbk = h_bin[PLACE_CLASS_BLOCK];
+        if (nbk) {
+            const int* d_list = (const int*)ctx->bin_lists.p + (size_t)PLACE_CLASS_BLOCK * n;
+            std::vector<int> ids(nbk);
+            CK(cudaMemcpy(ids.data(), d_list, (size_t)nbk * 4, cudaMemcpyDeviceToHost));
+            ctx->n_place_class[PLACE_CLASS_BLOCK] += nbk;
+            int i0 = 0;
+            while (i0 < nbk) {
+                long long recs = 0, stk = 0;
+                int i1 = i0;
+                while (i1 < nbk) {
+                    const long long v = hV[ids[i1]] + 1, k = hK[ids[i1]];
+                    if (i1 > i0 && (size_t)(recs + v) * PLACE_NODE_SLOT_BYTES > ctx->scratch_limit) break;
+                    h_rec_off[i1 - i0] = recs;
+                    h_stack_off[i1 - i0] = stk;
+                    recs += v;
+                    stk += k;
+                    ++i1;
+                }
+                h_rec_off[i1 - i0] = recs;
+                h_stack_off[i1 - i0] = stk;
+                if (ensure(ctx, ctx->recs, (size_t)std::max<long long>(recs, 1) * PLACE_NODE_SLOT_BYTES)) return -1;
+                if (ensure(ctx, ctx->stacks, (size_t)std::max<long long>(stk, 1) * PLACE_CHAIN_SLOT_BYTES)) return -1;
+                CK(cudaMemcpyAsync(ctx->rec_off.p, h_rec_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(ctx->stack_off.p, h_stack_off.data(), (size_t)(i1 - i0 + 1) * 8, cudaMemcpyHostToDevice, s));
+                pa.n = i1 - i0;
+                pa.qlist = d_list + i0;
+                pa.rec_off = (const long long*)ctx->rec_off.p;
+                pa.stack_off = (const long long*)ctx->stack_off.p;
+                pa.recs = ctx->recs.p;
+                pa.stacks = ctx->stacks.p;
+                CK(launch_place(prm->method, PLACE_CLASS_BLOCK, pa, s));
+                ctx->n_launch += 1;
+                i0 = i1;
+                CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused (next chunk, reruns)
+            }
+        }
+        main_placed = true;
+    }
+    mark("main placement launched");
     if (!exotic.empty() && rerun(exotic, true, cap, false)) return -1;
     if (!over.empty() && rerun(over, slow_ctx, (int)std::min<int64_t>((int64_t)cap * 16, cap_max), use_stash)) return -1;
 
@@ -882,22 +962,29 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             memcpy(io.obs_dist + (size_t)(base0 + i) * ocap, &td[(size_t)i * cap], (size_t)k * 8);
         }
     }
-    for (int i = 0; i < n; ++i)
-        if (hS[i] == ST_PLACE) {
-            ctx->n_obs += hK[i];
-            ctx->n_valid += hV[i];
-            ctx->max_K = std::max(ctx->max_K, (double)hK[i]);
-            ctx->max_V = std::max(ctx->max_V, (double)hV[i]);
-        }
+    // statistics: the device summed the ordinary queries while sorting them, the rerun ones are few
+    ctx->n_obs += (double)h_bin_stats[0];
+    ctx->n_valid += (double)h_bin_stats[1];
+    ctx->max_K = std::max(ctx->max_K, (double)h_bin_stats[2]);
+    ctx->max_V = std::max(ctx->max_V, (double)h_bin_stats[3]);
+    for (const std::vector<int>* lst : {&exotic, &over})
+        for (int i : *lst)
+            if (hS[i] == ST_PLACE) {
+                ctx->n_obs += hK[i];
+                ctx->n_valid += hV[i];
+                ctx->max_K = std::max(ctx->max_K, (double)hK[i]);
+                ctx->max_V = std::max(ctx->max_V, (double)hV[i]);
+            }
     if (!io.stop_after_select) {
         // ---------------- phase 3 ----------------
         if (main_placed) {
-            CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+            // launched before the reruns
         } else if (place_entries(n, [](int i) { return i; }, [&](int qi) { return !is_over[qi]; }, false, cap,
                                  (const int*)ctx->obs_node.p, (const double*)ctx->obs_dist.p, (const int*)ctx->obs_len.p, s,
                                  ctx->pl_lists, ctx->h_pl_lists)) {
             return -1;
         }
+        mark("stats done");
         {   // zero-distance shortcut / too-few-distances records of the whole batch
             Span sp(ctx, T_PLACE);
             pa.n = n;
@@ -915,6 +1002,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             CK(cudaMemcpyAsync(io.status + base0, ctx->o_status.p, (size_t)n * 4, kd, s));
         }
     }
+    mark("tail launched");
     CK(cudaStreamSynchronize(s));
     mark("batch done");
     if (dbg) {
@@ -1014,7 +1102,7 @@ void apples_ctx_destroy(apples_ctx* ctx) {
                      &ctx->refs_aa_tm, &ctx->refs_aav, &ctx->q_aa_tm, &ctx->q_aav, &ctx->aa_valid, &ctx->ref_bytes_p, &ctx->rep_bytes_p,
                      &ctx->q_bytes_p, &ctx->q_rowflag, &ctx->keys_w, &ctx->reps_img, &ctx->q_img, &ctx->ref_node, &ctx->goff, &ctx->gmem, &ctx->col_node, &ctx->q_rm,
                      &ctx->q_wm, &ctx->keys, &ctx->self_node, &ctx->obs_node, &ctx->obs_dist, &ctx->obs_len, &ctx->obs_len2, &ctx->Kd, &ctx->Vd,
-                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists, &ctx->pl_lists2,
+                     &ctx->statusd, &ctx->zero_edge, &ctx->pair_counter, &ctx->q_bytes, &ctx->q_bytes2, &ctx->q_rm2, &ctx->bad_flag, &ctx->clk_probe, &ctx->stash_keys, &ctx->stash_ids, &ctx->stash_count, &ctx->obs_node2, &ctx->obs_dist2, &ctx->qlist, &ctx->pl_lists, &ctx->pl_lists2, &ctx->bin_counts, &ctx->bin_lists,
                      &ctx->rec_off, &ctx->stack_off, &ctx->recs, &ctx->stacks, &ctx->o_edge, &ctx->o_err,
                      &ctx->o_distal, &ctx->o_pendant, &ctx->o_status, &ctx->dbg_x1, &ctx->dbg_x2, &ctx->dbg_err,
                      &ctx->dbg_valid, &ctx->res_q, &ctx->res_self, &ctx->res_edge, &ctx->res_err, &ctx->res_distal,

@@ -195,6 +195,8 @@ void aa_build_tables(const double* blosum441, uint32_t* out);
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s);
 cudaError_t launch_place(int method, int vclass, const PlaceArgs& a, cudaStream_t s);
 cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s);
+cudaError_t launch_bin_classes(int n, const int* status, const int* K, const int* V, const int* row_flag, int* counts, int* lists,
+                               unsigned long long* stats, cudaStream_t s);
 cudaError_t dense_nuc_configure();
 // tensor-core experiment (dense_tc.cu)
 cudaError_t dense_tc_configure();

@@ -562,6 +562,31 @@ __global__ void finalize_kernel(const PlaceArgs a) {
     a.out_status[q] = (st == ST_ZERO) ? APPLES_ZERO_DIST_LEAF : APPLES_TOO_FEW_DISTANCES;
 }
 
+// Sorts the batch's placeable queries into the launch classes on the device (the host would need two passes over the
+// batch between two kernel launches, with the GPU idle): lists[c * n ..] = query ids of class c in arbitrary order (the
+// results do not depend on it), counts[c] = how many.  Queries whose observed set overflowed (status) or that wait for the
+// byte-compare fallback (row_flag) are left to the reruns.  stats = {sum K, sum V, max K, max V} over the binned queries.
+__global__ void bin_classes_kernel(int n, const int* __restrict__ status, const int* __restrict__ K, const int* __restrict__ V,
+                                   const int* __restrict__ row_flag, int* __restrict__ counts, int* __restrict__ lists,
+                                   unsigned long long* __restrict__ stats) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || status[q] != ST_PLACE || (row_flag && row_flag[q])) return;
+    const int v = V[q] + 1, k = K[q];
+    const int c = v <= 64 ? PLACE_CLASS_64 : v <= 128 ? PLACE_CLASS_128 : v <= 256 ? PLACE_CLASS_256 : v <= 512 ? PLACE_CLASS_512 : PLACE_CLASS_BLOCK;
+    lists[(size_t)c * n + atomicAdd(&counts[c], 1)] = q;
+    atomicAdd(&stats[0], (unsigned long long)k);
+    atomicAdd(&stats[1], (unsigned long long)(v - 1));
+    atomicMax(&stats[2], (unsigned long long)k);
+    atomicMax(&stats[3], (unsigned long long)(v - 1));
+}
+
+cudaError_t launch_bin_classes(int n, const int* status, const int* K, const int* V, const int* row_flag, int* counts, int* lists,
+                               unsigned long long* stats, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    bin_classes_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, status, K, V, row_flag, counts, lists, stats);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_place_finalize(const PlaceArgs& a, cudaStream_t s) {
     if (a.n <= 0) return cudaSuccess;
     finalize_kernel<<<(a.n + 255) / 256, 256, 0, s>>>(a);
