@@ -130,11 +130,6 @@ static const int TCI_SMEM = 3 * TC_TM * (TCI_WCH + 1) * 4;
 
 void launch_tc_image(const uint32_t* planes, int rows, int W, int n_w, int rows_pad, int vw, void* out, cudaStream_t s) {
     if (rows_pad <= 0 || n_w <= 0) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(tc_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCI_SMEM);
-        configured = true;
-    }
     dim3 grid((n_w + TCI_WCH - 1) / TCI_WCH, rows_pad / TC_TM);
     tc_image_kernel<<<grid, 256, TCI_SMEM, s>>>(planes, rows, W, n_w, vw, (uint4*)out);
 }
@@ -291,7 +286,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) dense_tc_kernel(const TcArgs a)
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
+// function attributes are per device: called by apples_ctx_create on the context's device
 cudaError_t dense_tc_configure() {
+    cudaError_t e = cudaFuncSetAttribute(tc_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCI_SMEM);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
 }
 
