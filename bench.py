@@ -416,7 +416,9 @@ def main():
                'd2h_bytes_per_step': (32 * nq + (32 * nq * world if world > 1 else 0)) * world,
                'input': 'alignment bytes (uint8 per site) in pinned host memory, packed on the device',
                'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps}
-        pl.timings(reset=True)
+        tme = pl.timings(reset=True)
+        e2e['stage_ms_per_step'] = {k: tme[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms',
+                                                                      'placement_ms', 'd2h_ms')}
 
     # sha1 of every rank's block of result records (block r = the queries generated from seed 1000 + r): block 0 of an
     # N-GPU run must carry the hash the 1-GPU run prints, block 1 the hash the 2-GPU run prints for it, and so on
