@@ -569,15 +569,31 @@ __global__ void finalize_kernel(const PlaceArgs a) {
 __global__ void bin_classes_kernel(int n, const int* __restrict__ status, const int* __restrict__ K, const int* __restrict__ V,
                                    const int* __restrict__ row_flag, int* __restrict__ counts, int* __restrict__ lists,
                                    unsigned long long* __restrict__ stats) {
+    // ranks inside the block through shared-memory counters, one global atomic per class and block (a global atomic per
+    // query serialised on nine addresses: 0.37 ms per 125k queries)
+    __shared__ int s_cnt[PLACE_NCLASS], s_base[PLACE_NCLASS];
+    __shared__ unsigned long long s_stat[4];
+    if (threadIdx.x < PLACE_NCLASS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 4) s_stat[threadIdx.x] = 0ull;
+    __syncthreads();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n || status[q] != ST_PLACE || (row_flag && row_flag[q])) return;
-    const int v = V[q] + 1, k = K[q];
-    const int c = v <= 64 ? PLACE_CLASS_64 : v <= 128 ? PLACE_CLASS_128 : v <= 256 ? PLACE_CLASS_256 : v <= 512 ? PLACE_CLASS_512 : PLACE_CLASS_BLOCK;
-    lists[(size_t)c * n + atomicAdd(&counts[c], 1)] = q;
-    atomicAdd(&stats[0], (unsigned long long)k);
-    atomicAdd(&stats[1], (unsigned long long)(v - 1));
-    atomicMax(&stats[2], (unsigned long long)k);
-    atomicMax(&stats[3], (unsigned long long)(v - 1));
+    const bool on = q < n && status[q] == ST_PLACE && !(row_flag && row_flag[q]);
+    int c = 0, rank = 0;
+    if (on) {
+        const int v = V[q] + 1, k = K[q];
+        c = v <= 64 ? PLACE_CLASS_64 : v <= 128 ? PLACE_CLASS_128 : v <= 256 ? PLACE_CLASS_256 : v <= 512 ? PLACE_CLASS_512 : PLACE_CLASS_BLOCK;
+        rank = atomicAdd(&s_cnt[c], 1);
+        atomicAdd(&s_stat[0], (unsigned long long)k);
+        atomicAdd(&s_stat[1], (unsigned long long)(v - 1));
+        atomicMax(&s_stat[2], (unsigned long long)k);
+        atomicMax(&s_stat[3], (unsigned long long)(v - 1));
+    }
+    __syncthreads();
+    if (threadIdx.x < PLACE_NCLASS && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < 2 && s_stat[threadIdx.x]) atomicAdd(&stats[threadIdx.x], s_stat[threadIdx.x]);
+    if (threadIdx.x >= 2 && threadIdx.x < 4 && s_stat[threadIdx.x]) atomicMax(&stats[threadIdx.x], s_stat[threadIdx.x]);
+    __syncthreads();
+    if (on) lists[(size_t)c * n + s_base[c] + rank] = q;
 }
 
 cudaError_t launch_bin_classes(int n, const int* status, const int* K, const int* V, const int* row_flag, int* counts, int* lists,

@@ -364,25 +364,28 @@ __device__ __forceinline__ void observe(const SelectArgs& a, WarpSel<KIND>& st, 
     }
     if (st.kcount < a.cap && lane == 0) {
         a.obs_node[(size_t)slot * a.cap + st.kcount] = node;
-        a.obs_dist[(size_t)slot * a.cap + st.kcount] = d;
+        // nucleotide members arrive as their packed integer counts: parked in the (still unused) chain-length row until
+        // the tail of the kernel sorts the leaves and writes the corrected fp64 distances
+        if constexpr (KIND == SEL_NUC) a.obs_len[(size_t)slot * a.cap + st.kcount] = (int)__double_as_longlong(d);
+        else a.obs_dist[(size_t)slot * a.cap + st.kcount] = d;
     }
     st.kcount++;
 }
 
 // nucleotide members are stored as their integer counts first (bit pattern in the double slot); the fp64 jc69
 // correction is applied afterwards for all observed leaves in parallel (finish_distances)
-__device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<SEL_NUC>& st, int slot, int self, int row,
+__device__ __forceinline__ void observe_nuc_counts(const SelectArgs& a, WarpSel<SEL_NUC>& st, int slot, int self, int node,
                                                    uint32_t c, const Key<SEL_NUC>& ukey, int pos, int lane) {
     const uint32_t m = c & 0xffffu, v = c >> 16;
     if (v == 0u || (int)v < a.gate.vmin || 4u * m >= 3u * v) return;  // distance < 0: not stored (Reference.py:150)
-    observe<SEL_NUC>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
+    observe<SEL_NUC>(a, st, slot, self, node, __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
 }
 
-__device__ __forceinline__ void observe_nucw_counts(const SelectArgs& a, WarpSel<SEL_NUCW>& st, int slot, int self, int row,
+__device__ __forceinline__ void observe_nucw_counts(const SelectArgs& a, WarpSel<SEL_NUCW>& st, int slot, int self, int node,
                                                     uint32_t m, uint32_t v, const Key<SEL_NUCW>& ukey, int pos, int lane) {
     if (v == 0u || (long long)v < (long long)a.gate.vmin || 4ull * m >= 3ull * v) return;   // distance < 0: not stored
     const unsigned long long c = (unsigned long long)m | ((unsigned long long)v << 32);
-    observe<SEL_NUCW>(a, st, slot, self, a.ref_node[row], __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
+    observe<SEL_NUCW>(a, st, slot, self, node, __longlong_as_double((long long)c), m == 0u, ukey, pos, lane);
 }
 
 template <int KIND, int NR = 2>
@@ -395,14 +398,16 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
         if constexpr (KIND == SEL_NUCW) {
             const uint8_t* qrow = a.q_bytes + (size_t)q * a.q_bstride;
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {
-                int rows[NR];
+                int rows[NR], nodes[NR];
                 uint32_t cm[NR], cv[NR];
 #pragma unroll
                 for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) nodes[k] = a.ref_node[rows[k]];
                 member_counts_bytes<NR>(a, qrow, rows, lane, cm, cv);
 #pragma unroll
                 for (int k = 0; k < NR; ++k)
-                    if (x + k < e) observe_nucw_counts(a, st, slot, self, rows[k], cm[k], cv[k], ukey, x + k - b, lane);
+                    if (x + k < e) observe_nucw_counts(a, st, slot, self, nodes[k], cm[k], cv[k], ukey, x + k - b, lane);
             }
         } else if constexpr (KIND == SEL_NUC) {
             const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
@@ -412,14 +417,18 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
                     prefetch_l2(reinterpret_cast<const char*>(a.refs_nuc + (size_t)a.gmem[b + i / lines] * 3 * a.W) + (i % lines) * 128);
             }
             for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
-                int rows[NR];
+                int rows[NR], nodes[NR];
                 uint32_t c[NR];
 #pragma unroll
                 for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
+                // node ids with the rows, not inside observe(): there each load would wait behind the previous entry's
+                // store (possible alias) -- a serial L2 round trip per observed leaf
+#pragma unroll
+                for (int k = 0; k < NR; ++k) nodes[k] = a.ref_node[rows[k]];
                 member_counts_nuc<NR>(a, qrow, rows, lane, c);
 #pragma unroll
                 for (int k = 0; k < NR; ++k)
-                    if (x + k < e) observe_nuc_counts(a, st, slot, self, rows[k], c[k], ukey, x + k - b, lane);
+                    if (x + k < e) observe_nuc_counts(a, st, slot, self, nodes[k], c[k], ukey, x + k - b, lane);
             }
         } else {
             for (int x = b; x < e && st.kcount <= a.cap; ++x) {
@@ -455,6 +464,26 @@ __device__ void sort_slot(int* node, double* dist, int n2, int lane) {
     }
 }
 
+// the same order through shared memory: keys (node id << log2(n2) | position), one compare-exchange per lane and step.
+// The in-place version above walks global memory with a possible alias between every store and the next load, i.e. one
+// L2 round trip per compare-exchange: 1.5 ms for the 4096-entry slot of the largest rerun query.
+__device__ void sort_keys_smem(uint32_t* key, int n2, int lane) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (n2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t with a zero inserted at bit log2(j)
+                const int l = i | j;
+                const uint32_t x = key[i], y = key[l];
+                if ((x > y) == ((i & k) == 0)) {
+                    key[i] = y;
+                    key[l] = x;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // nucleotide mode: 8 blocks of 4 warps per SM (64 registers, some spills) measured faster than 4 (128 registers): 12.1
 // vs 12.9 ms per 125k queries -- the kernel is latency-bound and wants warps, not registers
 #ifndef SEL_MINBLOCKS
@@ -470,6 +499,8 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
     constexpr int NR = HEAVY ? 8 : SEL_NR;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
+    constexpr int SORT_CAP = HEAVY ? 4096 : 256;       // entries of the shared-memory sort buffer of one warp
+    extern __shared__ uint32_t s_sortbuf[];            // [4 warps][SORT_CAP]
     __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
     const double* aa_tab = s_aa_tab;
     if constexpr (KIND == SEL_AA) {
@@ -501,6 +532,7 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
     constexpr int VEC = 1;
     constexpr int U = 8;  // independent loads in flight per lane
     Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
+    uint32_t bm = 1u, bv = 0u;  // count keys: event bound as a ratio; starts at l2 = none (1 / 0: every key with v > 0)
     for (int u0 = 0; u0 < a.n_units && st.kcount <= a.cap; u0 += 32 * U) {
         {   // the 128-byte lines of the chunk after next (32 * U keys = 8 or 16 lines per chunk)
             constexpr int PER_LINE = 128 / (int)sizeof(Raw);
@@ -517,26 +549,21 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
             raw[j] = 0;
             if (u < a.n_units) raw[j] = load_raw<KIND>(a, slot, u);
         }
-        // Per key, branch-free: is it an EVENT for this lane -- a far key smaller than the lane's second-smallest
-        // (bit j of `ev`), or a key that needs the exact classification (near, or inside the guard band)?  Almost
-        // every key is neither: certainly far (above the band) and not smaller than l2, decided by three multiplies
-        // and four compares (the scan used to be 70 % of this kernel's instructions).  Keys past the end of the row
-        // were loaded as 0: v = 0 fails the overlap gate (vmin >= 1).
+        // Per key, branch-free: is it an EVENT for this lane -- a far key smaller than the lane's second-smallest, or a
+        // key that needs the exact classification (near, or inside the guard band)?  Both are "ratio m / v below a bound":
+        // the bound (bm / bv) is the larger of the band's upper edge P_hi / 65536 and the ratio of l2, so one key costs two
+        // multiplies and one compare (the scan used to be 70 %, then 35 % of this kernel's instructions).  Almost every
+        // key is above the bound.  Keys past the end of the row were loaded as 0 (0 < 0 fails); a key under the overlap
+        // gate that passes is rejected by the exact classification.
         unsigned ev = 0u;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             if constexpr (KIND == SEL_NUC) {
                 const uint32_t r = raw[j], m = r & 0xffffu, v = r >> 16;
-                const bool ok = (int)v >= a.gate.vmin;
-                const bool pfar = (r << 16) >= a.gate.P_hi * v;
-                const bool less = m * l2.v < l2.m * v;  // by ratio; units arrive in ascending order, ties are not less
-                if (ok && (!pfar || less)) ev |= 1u << j;
+                if (m * bv < bm * v) ev |= 1u << j;
             } else if constexpr (KIND == SEL_NUCW) {
                 const uint32_t m = (uint32_t)(raw[j] & 0xffffffffull), v = (uint32_t)(raw[j] >> 32);
-                const bool ok = (long long)v >= (long long)a.gate.vmin;
-                const bool pfar = ((uint64_t)m << 16) >= (uint64_t)a.gate.P_hi * v;
-                const bool less = (uint64_t)m * l2.v < (uint64_t)l2.m * v;
-                if (ok && (!pfar || less)) ev |= 1u << j;
+                if ((uint64_t)m * bv < (uint64_t)bm * v) ev |= 1u << j;
             } else {
                 const int u = u0 + j * 32 + lane;
                 if (u < a.n_units && !(raw[j] > l2.d)) ev |= 1u << j;  // NaN and near keys included
@@ -563,6 +590,15 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
                         l2 = kj;
                     }
                 }
+            }
+            if constexpr (KIND == SEL_NUC) {   // l2.m << 16 and P_hi * v fit 32 bits (counts <= 65535, P_hi < 49154)
+                const bool far_rules = (l2.m << 16) > a.gate.P_hi * l2.v;
+                bm = far_rules ? l2.m : a.gate.P_hi;
+                bv = far_rules ? l2.v : 65536u;
+            } else if constexpr (KIND == SEL_NUCW) {
+                const bool far_rules = ((uint64_t)l2.m << 16) > (uint64_t)a.gate.P_hi * l2.v;
+                bm = far_rules ? l2.m : a.gate.P_hi;
+                bv = far_rules ? l2.v : 65536u;
             }
         }
         if (__any_sync(FULLMASK, nearb != 0u)) {
@@ -692,10 +728,28 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
         int n2 = 1;
         while (n2 < K) n2 <<= 1;
         __syncwarp();
-        if constexpr (KIND == SEL_NUC) {  // jc69 correction of the observed leaves, one per lane
-            for (int i = lane; i < K; i += 32) {
-                const uint32_t c = (uint32_t)__double_as_longlong(dist[i]);
-                dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+        int sh = 0;
+        while ((1 << sh) < n2) ++sh;
+        bool sorted = false;
+        if constexpr (KIND == SEL_NUC) {
+            int* cnt = a.obs_len + (size_t)oslot * a.cap;   // packed counts parked by observe()
+            if (n2 <= SORT_CAP && ((unsigned long long)a.tree.M << sh) <= (1ull << 32)) {
+                uint32_t* skey = s_sortbuf + (threadIdx.x >> 5) * SORT_CAP;
+                for (int i = lane; i < n2; i += 32) skey[i] = i < K ? (((uint32_t)node[i] << sh) | (uint32_t)i) : 0xffffffffu;
+                __syncwarp();
+                sort_keys_smem(skey, n2, lane);
+                for (int i = lane; i < K; i += 32) {   // gather: jc69 correction of the observed leaves in sorted order
+                    const uint32_t key = skey[i];
+                    const uint32_t c = (uint32_t)cnt[key & (uint32_t)(n2 - 1)];
+                    dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+                    node[i] = (int)(key >> sh);
+                }
+                sorted = true;
+            } else {   // slots beyond the buffer (second-level reruns) or node ids too wide for the packed key
+                for (int i = lane; i < K; i += 32) {
+                    const uint32_t c = (uint32_t)cnt[i];
+                    dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+                }
             }
         }
         if constexpr (KIND == SEL_NUCW) {
@@ -704,12 +758,15 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
                 dist[i] = jc69_from_counts((uint32_t)(c & 0xffffffffull), (uint32_t)(c >> 32), a.gate.vmin);
             }
         }
-        for (int i = K + lane; i < n2; i += 32) {
-            node[i] = 0x7fffffff;
-            dist[i] = 0.0;
+        if (!sorted) {
+            for (int i = K + lane; i < n2; i += 32) {
+                node[i] = 0x7fffffff;
+                dist[i] = 0.0;
+            }
+            __syncwarp();
+            sort_slot(node, dist, n2, lane);
         }
-        __syncwarp();
-        sort_slot(node, dist, n2, lane);
+        __syncwarp();   // the chain lengths below overwrite the parked counts
         // valid nodes = union of leaf -> MRCA paths, MRCA excluded (Subtree.py:23-43).  With leaves sorted by id the
         // chain owned by leaf i runs up to (excluding) the first ancestor that also contains leaf i+1; the last
         // leaf's chain stops below the first ancestor that contains leaf 0 (the MRCA).
@@ -745,14 +802,16 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
     const int warps = 4;
     dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
     if (a.n <= 0) return;
-    if (kind == SEL_NUC && a.out_map)  // overflow rerun
-        select_kernel<SEL_NUC, true><<<grid, block, 0, s>>>(a);
-    else if (kind == SEL_NUC)
-        select_kernel<SEL_NUC, false><<<grid, block, 0, s>>>(a);
+    const size_t sm = (size_t)warps * 256 * 4, sm_heavy = (size_t)warps * 4096 * 4;   // sort buffers (SORT_CAP)
+    if (kind == SEL_NUC && a.out_map) {  // overflow rerun
+        cudaFuncSetAttribute(select_kernel<SEL_NUC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_heavy);
+        select_kernel<SEL_NUC, true><<<grid, block, sm_heavy, s>>>(a);
+    } else if (kind == SEL_NUC)
+        select_kernel<SEL_NUC, false><<<grid, block, sm, s>>>(a);
     else if (kind == SEL_NUCW)
-        select_kernel<SEL_NUCW, false><<<grid, block, 0, s>>>(a);
+        select_kernel<SEL_NUCW, false><<<grid, block, sm, s>>>(a);
     else if (kind == SEL_AA)
-        select_kernel<SEL_AA, false><<<grid, block, 0, s>>>(a);
+        select_kernel<SEL_AA, false><<<grid, block, sm, s>>>(a);
     else
-        select_kernel<SEL_MATRIX, false><<<grid, block, 0, s>>>(a);
+        select_kernel<SEL_MATRIX, false><<<grid, block, sm, s>>>(a);
 }
