@@ -470,6 +470,7 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
 
     // distances + selection of the `nb` queries whose packed rows / matrix rows are at d_q / ctx->keys
     // `slow`: byte-compare fallback; d_qb = the queries' padded byte rows [nb][Lp], keys go to `kw` (64-bit, row stride ldk)
+    cudaStream_t cur = s;   // stream of distances_and_select (the first-level reruns run on the side stream)
     auto distances_and_select = [&](const void* d_q, int nb, SelectArgs& a, bool keys_ready = false, bool slow = false,
                                     const uint8_t* d_qb = nullptr, void* kw = nullptr) -> int {
         const int nb_pad = round_up(nb, DT_TQ);
@@ -477,9 +478,9 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         if (keys_ready) {
             // the key rows are already in a.keys_nuc (stash of the first pass)
         } else if (slow) {
-            Span sp(ctx, T_DENSE);
+            Span sp(ctx, T_DENSE, cur);
             launch_dense_bytes(d_qb, ctx->Lp, nb, (const uint8_t*)ctx->rep_bytes_p.p, ctx->Lp, ctx->n_rep, ctx->Lp,
-                               (unsigned long long*)kw, ldk, s);
+                               (unsigned long long*)kw, ldk, cur);
             ctx->n_launch += 1;
             ctx->n_dense_launch += 1;
             ctx->n_pairs += (double)nb * ctx->n_rep;
@@ -487,14 +488,14 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         } else if (sel_kind == SEL_NUC && use_tc) {
             const int q_pad = round_up(nb, 256);
             {
-                Span sp(ctx, T_TRANSPOSE);
-                launch_tc_image((const uint32_t*)d_q, nb, ctx->W, ctx->tc_nw, q_pad, 125, ctx->q_img.p, s);
+                Span sp(ctx, T_TRANSPOSE, cur);
+                launch_tc_image((const uint32_t*)d_q, nb, ctx->W, ctx->tc_nw, q_pad, 125, ctx->q_img.p, cur);
                 ctx->n_launch += 1;
             }
             {
-                Span sp(ctx, T_DENSE);
+                Span sp(ctx, T_DENSE, cur);
                 launch_dense_tc(ctx->q_img.p, q_pad, ctx->reps_img.p, ctx->tc_rep_pad, ctx->tc_nw, (uint32_t*)ctx->keys.p, ldk,
-                                ctx->num_sms, s);
+                                ctx->num_sms, cur);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
                 ctx->n_tc_launch += 1;
@@ -502,17 +503,17 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             ctx->n_pairs += (double)nb * ctx->n_rep;
         } else if (sel_kind == SEL_NUC) {
             {
-                Span sp(ctx, T_TRANSPOSE);
-                launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, DT_TQ, s);
-                launch_row_valid((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_nv.p, nb_pad, s);
+                Span sp(ctx, T_TRANSPOSE, cur);
+                launch_transpose_nuc((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_wm.p, ctx->Wp, nb_pad, DT_TQ, cur);
+                launch_row_valid((const uint32_t*)d_q, nb, ctx->W, (uint32_t*)ctx->q_nv.p, nb_pad, cur);
                 ctx->n_launch += 2;
             }
             {
-                Span sp(ctx, T_DENSE);
+                Span sp(ctx, T_DENSE, cur);
                 launch_dense_nuc_keys((const uint32_t*)ctx->q_wm.p, (const uint32_t*)ctx->q_nv.p, nb_pad,
                                       (const uint32_t*)ctx->reps_wm.p, (const uint32_t*)ctx->reps_nv.p, ctx->rep_pad,
                                       ctx->W, ctx->Wp, (uint32_t*)ctx->keys.p, ldk, (unsigned long long*)ctx->clk_probe.p,
-                                      ctx->num_sms, s);
+                                      ctx->num_sms, cur);
                 ctx->n_launch += 1;
                 ctx->n_dense_launch += 1;
             }
@@ -521,16 +522,16 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             const int q_pad = round_up(nb, AA_TQ);
             const int nc = aa_chunks(ctx->Lp);
             {
-                Span sp(ctx, T_TRANSPOSE);
-                launch_aa_layout((const uint8_t*)d_q, nb, ctx->Lp, AA_TQ, q_pad, (uint8_t*)ctx->q_aa_tm.p, (uint32_t*)ctx->q_aav.p, s);
+                Span sp(ctx, T_TRANSPOSE, cur);
+                launch_aa_layout((const uint8_t*)d_q, nb, ctx->Lp, AA_TQ, q_pad, (uint8_t*)ctx->q_aa_tm.p, (uint32_t*)ctx->q_aav.p, cur);
                 ctx->n_launch += 1;
             }
             (void)nc;
-            Span sp(ctx, T_DENSE);
+            Span sp(ctx, T_DENSE, cur);
             launch_dense_aa((const uint8_t*)ctx->q_aa_tm.p, (const uint32_t*)ctx->q_aav.p, q_pad, nb,
                             (const uint8_t*)ctx->reps_aa_tm.p, (const uint32_t*)ctx->reps_aav.p, ctx->aa_rep_pad, ctx->n_rep,
                             ctx->Lp, ctx->L, prm->overlap_frac, (const uint32_t*)ctx->aa_tab.p, (uint32_t*)ctx->aa_valid.p, ldk,
-                            (double*)ctx->keys.p, ldk, s);
+                            (double*)ctx->keys.p, ldk, cur);
             ctx->n_launch += 2;
             ctx->n_dense_launch += 1;
             ctx->n_pairs += (double)nb * ctx->n_rep;
@@ -546,8 +547,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
             a.stash_keys = nullptr;
         }
         {
-            Span sp(ctx, T_SELECT);
-            launch_select(kind_now, a, s);
+            Span sp(ctx, T_SELECT, cur);
+            launch_select(kind_now, a, cur);
             ctx->n_launch += 1;
         }
         CK(cudaGetLastError());
@@ -631,14 +632,14 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     CK(cudaMemcpyAsync(h_bin_stats, (char*)ctx->bin_counts.p + 32, 32, cudaMemcpyDeviceToHost, s));
     mark("phase 1 launched");
     // ---------------- phase 2 ----------------
-    auto fetch_counts = [&]() -> int {
-        Span sp(ctx, T_D2H);
-        CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    auto fetch_counts = [&](cudaStream_t fs) -> int {
+        Span sp(ctx, T_D2H, fs);
+        CK(cudaMemcpyAsync(hK.data(), ctx->Kd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, fs));
+        CK(cudaMemcpyAsync(hV.data(), ctx->Vd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, fs));
+        CK(cudaMemcpyAsync(hS.data(), ctx->statusd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, fs));
         return 0;
     };
-    if (fetch_counts()) return -1;
+    if (fetch_counts(s)) return -1;
     CK(cudaStreamSynchronize(s));
     mark("phase 1 done on the device");
     // queries holding bytes other than A,C,G,T,- (they survive fasta2dic only as non-letters and count as ordinary
@@ -789,10 +790,11 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     }
     const int cap_max = next_pow2(std::max(4, n_leaf_bound));
     // reruns `list` with slot capacity cap_first, then 16x larger for whoever still overflows
-    auto rerun = [&](std::vector<int> list, bool slow, int cap_first, bool stash_first) -> int {
+    // `ss`: stream of the selection stage (gather, distances, selection, counts); the placement of the rerun queries stays on `s`
+    auto rerun = [&](std::vector<int> list, bool slow, int cap_first, bool stash_first, cudaStream_t ss) -> int {
         int cap2 = cap_first;
         bool use_st = stash_first;
-        if (slow && !slow_ctx && ensure_ref_bytes(ctx, s)) return -1;
+        if (slow && !slow_ctx && ensure_ref_bytes(ctx, ss)) return -1;
         while (!list.empty()) {
             // queries per rerun launch: bounded by the sub-batch size and by 2 GiB of slots
             const int GB = (int)std::max<int64_t>(1, std::min<int64_t>(QB, ((int64_t)2 << 30) / ((int64_t)cap2 * 16)));
@@ -806,13 +808,13 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 if (slow && (ensure(ctx, ctx->q_bytes_p, (size_t)QB * ctx->Lp) ||
                              (!slow_ctx && ensure(ctx, ctx->keys_w, (size_t)ng * ldk * 8))))
                     return -1;
-                CK(cudaMemcpyAsync(ctx->qlist.p, list.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(ctx->qlist.p, list.data() + o0, (size_t)ng * 4, cudaMemcpyHostToDevice, ss));
                 // gather the rows of the queries: one kernel for device-resident queries, one host-side gather + one copy
                 // otherwise (a memcpy call per row would cost more than the rerun itself)
                 if (!matrix && !io.h_queries && !io.h_bytes) {
                     // qlist holds batch-relative ids; the resident rows of this macro-batch start at base0
                     CK(launch_gather_rows((const char*)io.d_queries + (size_t)base0 * qrow, (const int*)ctx->qlist.p, ctx->q_rm.p,
-                                          ng, qrow, s));
+                                          ng, qrow, ss));
                     ctx->n_launch += 1;
                 } else {
                     const size_t rb = matrix ? qrow : (io.h_queries ? qrow : (size_t)io.byte_stride);
@@ -821,17 +823,17 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                     for (int j = 0; j < ng; ++j)
                         memcpy(ctx->h_gather.data() + (size_t)j * rb, src + ((size_t)base0 + list[o0 + j]) * rb, rb);
                     void* dst = matrix ? ctx->keys.p : (io.h_queries ? ctx->q_rm.p : ctx->q_bytes.p);
-                    CK(cudaMemcpyAsync(dst, ctx->h_gather.data(), (size_t)ng * rb, cudaMemcpyHostToDevice, s));
-                    CK(cudaStreamSynchronize(s));  // h_gather is reused by the next group
+                    CK(cudaMemcpyAsync(dst, ctx->h_gather.data(), (size_t)ng * rb, cudaMemcpyHostToDevice, ss));
+                    CK(cudaStreamSynchronize(ss));  // h_gather is reused by the next group
                 }
                 if (io.h_bytes && slow)
                     CK(launch_repitch_bytes((const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->Lp,
-                                            (uint8_t*)ctx->q_bytes_p.p, s));
+                                            (uint8_t*)ctx->q_bytes_p.p, ss));
                 else if (io.h_bytes)
                     CK(launch_pack(ctx->kind, (const uint8_t*)ctx->q_bytes.p, io.byte_stride, ng, ctx->L, ctx->q_rm.p,
-                                   (int*)ctx->bad_flag.p, s));
+                                   (int*)ctx->bad_flag.p, ss));
                 else if (slow)
-                    CK(launch_unpack_nuc((const uint32_t*)ctx->q_rm.p, ng, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, s));
+                    CK(launch_unpack_nuc((const uint32_t*)ctx->q_rm.p, ng, ctx->L, ctx->W, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, ss));
                 SelectArgs sb = sa;
                 sb.out_map = (const int*)ctx->qlist.p;
                 sb.q_begin = 0;
@@ -842,12 +844,14 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 sb.pair_counter = nullptr;
                 sb.stash_keys = nullptr;
                 if (use_st) sb.keys_nuc = (const uint32_t*)ctx->stash_keys.p + (size_t)o0 * ldk;
-                if (distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_st, slow, (const uint8_t*)ctx->q_bytes_p.p,
-                                         slow_ctx ? ctx->keys.p : ctx->keys_w.p))
-                    return -1;
+                cur = ss;
+                const int drc = distances_and_select(matrix ? nullptr : ctx->q_rm.p, ng, sb, use_st, slow, (const uint8_t*)ctx->q_bytes_p.p,
+                                                     slow_ctx ? ctx->keys.p : ctx->keys_w.p);
+                cur = s;
+                if (drc) return -1;
                 mark("  rerun select launched");
-                if (fetch_counts()) return -1;
-                CK(cudaStreamSynchronize(s));
+                if (fetch_counts(ss)) return -1;
+                CK(cudaStreamSynchronize(ss));
                 mark("  rerun select done");
                 if (io.obs_count) {
                     std::vector<int> un((size_t)ng * cap2);
@@ -880,31 +884,17 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
         return 0;
     };
-    // The ordinary queries are placed first, straight from the class lists the device built: no host pass over the batch
-    // stands between the last selection kernel and the placement launches, and the host prepares the reruns meanwhile.
-    // (Running this pass on a side stream BESIDE the rerun kernels was measured: the step did not change -- the rerun
-    // kernels then run with fewer resident blocks and take as much longer as the overlap saves.)
-    bool main_placed = false;
-    if (trace) fprintf(stderr, "[apples_b200] classes %d %d %d %d %d\n", h_bin[0], h_bin[1], h_bin[2], h_bin[3], h_bin[4]);
-    if (!io.stop_after_select) {
-        pa.cap = cap;
-        pa.obs_node = (const int*)ctx->obs_node.p;
-        pa.obs_dist = (const double*)ctx->obs_dist.p;
-        pa.obs_len = (const int*)ctx->obs_len.p;
-        pa.slot_list = nullptr;
+    // the few ordinary queries with more than 511 valid nodes (long unary paths): block-per-query kernel, scratch sized on the
+    // host from their counts.  Runs after the reruns, which share the scratch pool and whose selection stage should start at once.
+    auto main_block_class = [&]() -> int {
         Span sp(ctx, T_PLACE);
-        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
-            if (!h_bin[c]) continue;
-            pa.n = h_bin[c];
-            pa.qlist = (const int*)ctx->bin_lists.p + (size_t)c * n;
-            CK(launch_place(prm->method, c, pa, s));
-            ctx->n_launch += 1;
-            ctx->n_place_class[c] += h_bin[c];
-        }
-        // the few ordinary queries with more than 511 valid nodes (long unary paths): block-per-query kernel, scratch sized
-        // on the host from their counts
         const int nbk = h_bin[PLACE_CLASS_BLOCK];
         if (nbk) {
+            pa.cap = cap;   // the reruns pointed the arguments at their own slots
+            pa.obs_node = (const int*)ctx->obs_node.p;
+            pa.obs_dist = (const double*)ctx->obs_dist.p;
+            pa.obs_len = (const int*)ctx->obs_len.p;
+            pa.slot_list = nullptr;
             const int* d_list = (const int*)ctx->bin_lists.p + (size_t)PLACE_CLASS_BLOCK * n;
             std::vector<int> ids(nbk);
             CK(cudaMemcpy(ids.data(), d_list, (size_t)nbk * 4, cudaMemcpyDeviceToHost));
@@ -940,11 +930,37 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                 CK(cudaStreamSynchronize(s));  // the scratch pool and the offset arrays are reused (next chunk, reruns)
             }
         }
+        return 0;
+    };
+    // The ordinary queries are placed first, straight from the class lists the device built: no host pass over the batch
+    // stands between the last selection kernel and the placement launches, and the host prepares the reruns meanwhile.
+    // (Running this pass on a side stream BESIDE the rerun kernels was measured: the step did not change -- the rerun
+    // kernels then run with fewer resident blocks and take as much longer as the overlap saves.)
+    bool main_placed = false;
+    if (trace) fprintf(stderr, "[apples_b200] classes %d %d %d %d %d\n", h_bin[0], h_bin[1], h_bin[2], h_bin[3], h_bin[4]);
+    if (!io.stop_after_select) {
+        pa.cap = cap;
+        pa.obs_node = (const int*)ctx->obs_node.p;
+        pa.obs_dist = (const double*)ctx->obs_dist.p;
+        pa.obs_len = (const int*)ctx->obs_len.p;
+        pa.slot_list = nullptr;
+        Span sp(ctx, T_PLACE);
+        for (int c = 0; c < PLACE_CLASS_BLOCK; ++c) {
+            if (!h_bin[c]) continue;
+            pa.n = h_bin[c];
+            pa.qlist = (const int*)ctx->bin_lists.p + (size_t)c * n;
+            CK(launch_place(prm->method, c, pa, s));
+            ctx->n_launch += 1;
+            ctx->n_place_class[c] += h_bin[c];
+        }
         main_placed = true;
     }
     mark("main placement launched");
-    if (!exotic.empty() && rerun(exotic, true, cap, false)) return -1;
-    if (!over.empty() && rerun(over, slow_ctx, (int)std::min<int64_t>((int64_t)cap * 16, cap_max), use_stash)) return -1;
+    // selection stage of the reruns on the high-priority side stream, beside the shared-memory placement launches above
+    cudaStream_t rs = ctx->side_stream;
+    if (!exotic.empty() && rerun(exotic, true, cap, false, rs)) return -1;
+    if (!over.empty() && rerun(over, slow_ctx, (int)std::min<int64_t>((int64_t)cap * 16, cap_max), use_stash, rs)) return -1;
+    if (main_placed && main_block_class()) return -1;
 
     mark("reruns done");
     // ---------------- parity export of the observed sets ----------------
@@ -1079,7 +1095,9 @@ int apples_ctx_create(int device, apples_ctx** out) {
         if (cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) != cudaSuccess)
             rc = -4;
-    if (!rc && (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;   // side stream: the rerun selection beside the main placement pass must not queue behind it
+    if (!rc) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (!rc && (cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess))
         rc = -4;

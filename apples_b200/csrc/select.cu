@@ -4,12 +4,14 @@
 // representatives in ascending (distance, index) order and expands a cluster while
 // `dist <= threshold or obs_num < baseobs`.  Because pops are ascending and obs_num only grows, that is
 //   taken = { clusters with dist <= threshold }  U  { the next clusters in (dist, index) order while obs_num < baseobs }
-// (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters as it meets them and keeps,
-// per lane, the two smallest far keys of its residue class; afterwards the far clusters are extracted in ascending
-// order (warp-wide minimum of the lane minima; a lane that has used both keys re-scans its residue class for the next
-// two) until obs_num reaches baseobs.  The scan is branch-free per key (three multiplies, four compares); the exact
-// classification runs only for the few keys that can matter.  A query whose observed set outgrows its slot stashes its
-// key row and is rerun with a larger slot by the HEAVY instantiation of the kernel.
+// (SURVEY.md section 8 a3).  The warp scans the query's key row once, expands near clusters (at once in select_kernel,
+// batched through a queue in select_nuc_kernel) and keeps, per lane, the two smallest far keys of its residue class;
+// afterwards the far clusters are extracted in ascending order (warp-wide minimum of the lane minima; a lane that has
+// used both keys re-scans its residue class for the next two) until obs_num reaches baseobs.  The scan is branch-free
+// per key (two multiplies, one compare); the exact classification runs only for the few keys that can matter.  A query
+// whose observed set outgrows its slot stashes its key row and is rerun with a larger slot (HEAVY instantiation).
+// Two kernels: select_nuc_kernel for the packed nucleotide counts of the dense kernels (the hot path), select_kernel for
+// the byte-compare fallback (SEL_NUCW), protein (SEL_AA) and distance-matrix (SEL_MATRIX) inputs.
 // Nucleotide keys are the exact integer pairs (mismatch, valid) from the dense kernel: ordering by the rational
 // mismatch/valid is ordering by jc69 distance (equal rationals give the identical double), so no fp64 is needed
 // for the ~R representatives per query; the corrected fp64 distance is evaluated only for the selected members.
@@ -402,33 +404,14 @@ __device__ __forceinline__ void expand_unit(const SelectArgs& a, WarpSel<KIND>& 
                 uint32_t cm[NR], cv[NR];
 #pragma unroll
                 for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
+                // node ids with the rows, not inside observe(): there each load would wait behind the previous entry's
+                // store (possible alias) -- a serial L2 round trip per observed leaf
 #pragma unroll
                 for (int k = 0; k < NR; ++k) nodes[k] = a.ref_node[rows[k]];
                 member_counts_bytes<NR>(a, qrow, rows, lane, cm, cv);
 #pragma unroll
                 for (int k = 0; k < NR; ++k)
                     if (x + k < e) observe_nucw_counts(a, st, slot, self, nodes[k], cm[k], cv[k], ukey, x + k - b, lane);
-            }
-        } else if constexpr (KIND == SEL_NUC) {
-            const uint32_t* qrow = a.q_nuc + (size_t)q * 3 * a.W;
-            {   // all member rows of the cluster, 128-byte lines spread over the lanes
-                const int lines = (3 * a.W * 4 + 127) / 128;
-                for (int i = lane; i < (e - b) * lines; i += 32)
-                    prefetch_l2(reinterpret_cast<const char*>(a.refs_nuc + (size_t)a.gmem[b + i / lines] * 3 * a.W) + (i % lines) * 128);
-            }
-            for (int x = b; x < e && st.kcount <= a.cap; x += NR) {  // past the slot capacity the query is rerun anyway
-                int rows[NR], nodes[NR];
-                uint32_t c[NR];
-#pragma unroll
-                for (int k = 0; k < NR; ++k) rows[k] = a.gmem[min(x + k, e - 1)];
-                // node ids with the rows, not inside observe(): there each load would wait behind the previous entry's
-                // store (possible alias) -- a serial L2 round trip per observed leaf
-#pragma unroll
-                for (int k = 0; k < NR; ++k) nodes[k] = a.ref_node[rows[k]];
-                member_counts_nuc<NR>(a, qrow, rows, lane, c);
-#pragma unroll
-                for (int k = 0; k < NR; ++k)
-                    if (x + k < e) observe_nuc_counts(a, st, slot, self, nodes[k], c[k], ukey, x + k - b, lane);
             }
         } else {
             for (int x = b; x < e && st.kcount <= a.cap; ++x) {
@@ -484,6 +467,31 @@ __device__ void sort_keys_smem(uint32_t* key, int n2, int lane) {
     }
 }
 
+// valid nodes = union of leaf -> MRCA paths, MRCA excluded (Subtree.py:23-43).  With leaves sorted by id the chain owned
+// by leaf i runs up to (excluding) the first ancestor that also contains leaf i+1; the last leaf's chain stops below the
+// first ancestor that contains leaf 0 (the MRCA).  Writes the chain lengths, returns their sum (every lane).
+__device__ __forceinline__ int chain_lengths(const SelectArgs& a, const int* node, int* len_out, int K, int lane) {
+    const int leaf0 = node[0];
+    int c = 0;
+    for (int i = lane; i < K; i += 32) {
+        int u = node[i];
+        const int nxt = (i + 1 < K) ? node[i + 1] : -1;
+        int len = 1;
+        while (true) {
+            const int p = a.tree.parent[u];
+            const bool top = (i + 1 < K) ? (p >= nxt) : (a.tree.first[p] <= leaf0);
+            if (top) break;
+            len++;
+            u = p;
+        }
+        len_out[i] = len;
+        c += len;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
+    return c;
+}
+
 // nucleotide mode: 8 blocks of 4 warps per SM (64 registers, some spills) measured faster than 4 (128 registers): 12.1
 // vs 12.9 ms per 125k queries -- the kernel is latency-bound and wants warps, not registers
 #ifndef SEL_MINBLOCKS
@@ -492,15 +500,12 @@ __device__ void sort_keys_smem(uint32_t* key, int n2, int lane) {
 #ifndef SEL_NR
 #define SEL_NR 2
 #endif
-// HEAVY: the rerun launches of the few queries with hundreds to thousands of observed leaves -- one partial wave of
-// warps whose time is the member loop of the largest query: eight reference rows in flight and the full register file
-template <int KIND, bool HEAVY>
-__global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOCKS : 4) select_kernel(const SelectArgs a) {
-    constexpr int NR = HEAVY ? 8 : SEL_NR;
+template <int KIND>
+__global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
+    static_assert(KIND != SEL_NUC, "packed nucleotide counts go through select_nuc_kernel");
+    constexpr int NR = SEL_NR;
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row of this launch's key / query matrices
-    constexpr int SORT_CAP = HEAVY ? 4096 : 256;       // entries of the shared-memory sort buffer of one warp
-    extern __shared__ uint32_t s_sortbuf[];            // [4 warps][SORT_CAP]
     __shared__ double s_aa_tab[KIND == SEL_AA ? 441 : 1];
     const double* aa_tab = s_aa_tab;
     if constexpr (KIND == SEL_AA) {
@@ -538,8 +543,7 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
             constexpr int PER_LINE = 128 / (int)sizeof(Raw);
             const int u = u0 + 2 * 32 * U + lane * PER_LINE;
             if (lane < 32 * U / PER_LINE && u < a.n_units) {
-                if constexpr (KIND == SEL_NUC) prefetch_l2(a.keys_nuc + (size_t)slot * a.ldk + u);
-                else prefetch_l2(a.keys_f64 + (size_t)slot * a.ldk + u);
+                prefetch_l2(a.keys_f64 + (size_t)slot * a.ldk + u);
             }
         }
         Raw raw[U];
@@ -558,10 +562,7 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
         unsigned ev = 0u;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            if constexpr (KIND == SEL_NUC) {
-                const uint32_t r = raw[j], m = r & 0xffffu, v = r >> 16;
-                if (m * bv < bm * v) ev |= 1u << j;
-            } else if constexpr (KIND == SEL_NUCW) {
+            if constexpr (KIND == SEL_NUCW) {
                 const uint32_t m = (uint32_t)(raw[j] & 0xffffffffull), v = (uint32_t)(raw[j] >> 32);
                 if ((uint64_t)m * bv < (uint64_t)bm * v) ev |= 1u << j;
             } else {
@@ -591,11 +592,7 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
                     }
                 }
             }
-            if constexpr (KIND == SEL_NUC) {   // l2.m << 16 and P_hi * v fit 32 bits (counts <= 65535, P_hi < 49154)
-                const bool far_rules = (l2.m << 16) > a.gate.P_hi * l2.v;
-                bm = far_rules ? l2.m : a.gate.P_hi;
-                bv = far_rules ? l2.v : 65536u;
-            } else if constexpr (KIND == SEL_NUCW) {
+            if constexpr (KIND == SEL_NUCW) {
                 const bool far_rules = ((uint64_t)l2.m << 16) > (uint64_t)a.gate.P_hi * l2.v;
                 bm = far_rules ? l2.m : a.gate.P_hi;
                 bv = far_rules ? l2.v : 65536u;
@@ -704,19 +701,6 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
     int V = 0;
     if (st.kcount > a.cap) {
         status = ST_OVERFLOW;  // the scan was cut short: rerun with a larger slot (the host escalates the capacity)
-        if constexpr (KIND == SEL_NUC) {
-            if (a.stash_keys != nullptr) {
-                int pos = 0;
-                if (lane == 0) pos = atomicAdd(a.stash_count, 1);
-                pos = __shfl_sync(FULLMASK, pos, 0);
-                if (pos < a.stash_cap) {
-                    const uint4* src = reinterpret_cast<const uint4*>(a.keys_nuc + (size_t)slot * a.ldk);
-                    uint4* dst = reinterpret_cast<uint4*>(a.stash_keys + (size_t)pos * a.ldk);
-                    for (int64_t x = lane; x < a.ldk / 4; x += 32) dst[x] = src[x];
-                    if (lane == 0) a.stash_ids[pos] = gid;
-                }
-            }
-        }
     } else if (st.has_zero) {
         status = ST_ZERO;
     } else if (st.kcount <= 2) {
@@ -728,37 +712,325 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
         int n2 = 1;
         while (n2 < K) n2 <<= 1;
         __syncwarp();
-        int sh = 0;
-        while ((1 << sh) < n2) ++sh;
-        bool sorted = false;
-        if constexpr (KIND == SEL_NUC) {
-            int* cnt = a.obs_len + (size_t)oslot * a.cap;   // packed counts parked by observe()
-            if (n2 <= SORT_CAP && ((unsigned long long)a.tree.M << sh) <= (1ull << 32)) {
-                uint32_t* skey = s_sortbuf + (threadIdx.x >> 5) * SORT_CAP;
-                for (int i = lane; i < n2; i += 32) skey[i] = i < K ? (((uint32_t)node[i] << sh) | (uint32_t)i) : 0xffffffffu;
-                __syncwarp();
-                sort_keys_smem(skey, n2, lane);
-                for (int i = lane; i < K; i += 32) {   // gather: jc69 correction of the observed leaves in sorted order
-                    const uint32_t key = skey[i];
-                    const uint32_t c = (uint32_t)cnt[key & (uint32_t)(n2 - 1)];
-                    dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
-                    node[i] = (int)(key >> sh);
-                }
-                sorted = true;
-            } else {   // slots beyond the buffer (second-level reruns) or node ids too wide for the packed key
-                for (int i = lane; i < K; i += 32) {
-                    const uint32_t c = (uint32_t)cnt[i];
-                    dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
-                }
-            }
-        }
         if constexpr (KIND == SEL_NUCW) {
             for (int i = lane; i < K; i += 32) {
                 const unsigned long long c = (unsigned long long)__double_as_longlong(dist[i]);
                 dist[i] = jc69_from_counts((uint32_t)(c & 0xffffffffull), (uint32_t)(c >> 32), a.gate.vmin);
             }
         }
-        if (!sorted) {
+        for (int i = K + lane; i < n2; i += 32) {
+            node[i] = 0x7fffffff;
+            dist[i] = 0.0;
+        }
+        __syncwarp();
+        sort_slot(node, dist, n2, lane);
+        __syncwarp();
+        V = chain_lengths(a, node, a.obs_len + (size_t)oslot * a.cap, K, lane);
+    }
+    if (lane == 0) {
+        a.K[gid] = st.kcount;
+        a.V[gid] = V;
+        a.status[gid] = status;
+        a.zero_edge[gid] = st.znode;
+    }
+}
+
+// ---- nucleotide alignment mode: the same selection with the member distances batched ------------------------------
+// The generic kernel above expands a cluster the moment it meets it: cluster offsets -> member rows -> reference rows is
+// a chain of three dependent round trips to L2 / DRAM per cluster, 12k clocks for a 9-member cluster on B200 -- 80 % of
+// the time of the rerun launch and the main stall of the first pass.  Here near units are only QUEUED during the scan
+// (shared memory, per warp); once 32 are pending, lane t takes unit t: one parallel load of the 32 cluster extents, a warp
+// prefix sum, and the members of all 32 clusters land in one flat list (row, owner lane, position in the cluster).  The
+// list is then walked NR rows at a time with the rows PF entries ahead prefetched into L2 -- their addresses are known
+// from the list, so nothing waits on a dependent chain any more.  The far units (needed while obs_num < baseobs,
+// Reference.py:146) go through the same queue one at a time, in ascending order.  The observed SET, the counts and the
+// zero tie-break (by unit key and position) do not depend on the order of expansion, so the results are those of the
+// generic kernel bit for bit.
+template <bool HEAVY>
+__global__ void __launch_bounds__(128, HEAVY ? 4 : SEL_MINBLOCKS) select_nuc_kernel(const SelectArgs a) {
+    constexpr int KIND = SEL_NUC;
+    constexpr int NR = HEAVY ? 8 : SEL_NR;
+    constexpr int WORDS = HEAVY ? 4096 : 1024;  // shared 32-bit words per warp (also the sort buffer of the tail)
+    constexpr int QCAP = 320;                   // pending units: fewer than 32 left over + one chunk of 256 keys
+    constexpr int LCAP = (WORDS - QCAP) / 2;    // member list entries
+    constexpr int PF = HEAVY ? 16 : 8;          // rows prefetched ahead of the one being counted
+    constexpr int POS_BITS = 27;
+    extern __shared__ uint32_t s_sortbuf[];
+    uint32_t* wbuf = s_sortbuf + (threadIdx.x >> 5) * WORDS;
+    int* queue = reinterpret_cast<int*>(wbuf);
+    int* lrow = reinterpret_cast<int*>(wbuf + QCAP);
+    uint32_t* lmeta = wbuf + QCAP + LCAP;
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= a.n) return;
+    const int gid = a.out_map ? a.out_map[slot] : a.q_begin + slot;
+    const int oslot = a.out_map ? slot : gid;
+    const int self = a.self_node ? a.self_node[gid] : -1;
+    const uint32_t* __restrict__ krow = a.keys_nuc + (size_t)slot * a.ldk;
+    const uint32_t* __restrict__ qrow = a.q_nuc + (size_t)slot * 3 * a.W;
+    const int lines = (3 * a.W * 4 + 127) / 128;   // 128-byte lines of a packed reference row
+
+    WarpSel<KIND> st;
+    st.obs_num = 0;
+    st.kcount = 0;
+    st.has_zero = false;
+    st.zpos = 0;
+    st.znode = -1;
+    st.zkey.idx = 0;
+
+    constexpr int U = 8;
+    Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
+    uint32_t bm = 1u, bv = 0u;
+    int u0 = 0, np = 0, qhead = 0;
+    bool scan_done = a.n_units <= 0, far_init = false, more = false;
+    unsigned long long pairs = 0ull;
+
+    for (;;) {
+        if (np < 32 && !scan_done) {
+            // leftovers to the front of the queue
+            int keep = 0;
+            if (lane < np) keep = queue[qhead + lane];
+            __syncwarp();
+            if (lane < np) queue[lane] = keep;
+            qhead = 0;
+            do {
+                // ---- one chunk of the scan.  Event test per key, branch-free: ratio m / v below the lane's bound, the
+                // larger of the band's upper edge P_hi / 65536 and the ratio of l2 (l2.m << 16 and P_hi * v fit 32 bits:
+                // counts <= 65535, P_hi < 49154) ----
+                {
+                    const int u = u0 + 2 * 32 * U + lane * 32;
+                    if (lane < U && u < a.n_units) prefetch_l2(krow + u);
+                }
+                uint32_t raw[U];
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int u = u0 + j * 32 + lane;
+                    raw[j] = 0;
+                    if (u < a.n_units) raw[j] = krow[u];
+                }
+                unsigned ev = 0u;
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const uint32_t r = raw[j], m = r & 0xffffu, v = r >> 16;
+                    if (m * bv < bm * v) ev |= 1u << j;
+                }
+                unsigned nearb = 0u;
+                if (__any_sync(FULLMASK, ev != 0u)) {
+                    while (ev) {
+                        const int j = __ffs(ev) - 1;
+                        ev &= ev - 1;
+                        uint32_t rj = raw[0];
+#pragma unroll
+                        for (int t = 1; t < U; ++t)
+                            if (j == t) rj = raw[t];
+                        const Key<KIND> kj = make_key<KIND>(rj, u0 + j * 32 + lane);
+                        const int c = classify(a, kj);
+                        if (c == 1) nearb |= 1u << j;
+                        if (c == 2 && key_less(kj, l2)) {
+                            if (key_less(kj, l1)) {
+                                l2 = l1;
+                                l1 = kj;
+                            } else {
+                                l2 = kj;
+                            }
+                        }
+                    }
+                    const bool far_rules = (l2.m << 16) > a.gate.P_hi * l2.v;
+                    bm = far_rules ? l2.m : a.gate.P_hi;
+                    bv = far_rules ? l2.v : 65536u;
+                }
+                if (__any_sync(FULLMASK, nearb != 0u)) {
+#pragma unroll
+                    for (int j = 0; j < U; ++j) {
+                        const unsigned bal = __ballot_sync(FULLMASK, (nearb >> j) & 1u);
+                        if ((nearb >> j) & 1u) queue[np + __popc(bal & ((1u << lane) - 1u))] = u0 + j * 32 + lane;
+                        np += __popc(bal);
+                    }
+                }
+                u0 += 32 * U;
+                scan_done = u0 >= a.n_units;
+            } while (np < 32 && !scan_done);
+            __syncwarp();
+        }
+        if (np == 0) {
+            // ---- the scan is over and every near unit is expanded: far units, ascending, while obs_num < baseobs ----
+            if (!(st.obs_num < a.baseobs && st.kcount <= a.cap)) break;
+            if (!far_init) {
+                more = !key_is_none(l2);  // the class may hold far keys beyond the two kept
+                far_init = true;
+            }
+            Key<KIND> g = l1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const Key<KIND> og = key_shfl_xor(g, o);
+                if (key_less(og, g)) g = og;
+            }
+            if (key_is_none(g)) break;  // no far unit left
+            const bool mine = l1.idx == g.idx;
+            if (mine) {
+                l1 = l2;
+                l2 = key_none<KIND>();
+            }
+            const unsigned refill = __ballot_sync(FULLMASK, mine && more && key_is_none(l1));
+            if (refill) {
+                const int owner = __ffs(refill) - 1;
+                Key<KIND> n1 = key_none<KIND>(), n2 = key_none<KIND>();
+                constexpr int RU = 4;
+                for (int k0 = lane; k0 * 32 < a.n_units; k0 += 32 * RU) {
+                    uint32_t rr[RU];
+#pragma unroll
+                    for (int j = 0; j < RU; ++j) {
+                        const int u = (k0 + 32 * j) * 32 + owner;
+                        rr[j] = 0;
+                        if (u < a.n_units) rr[j] = krow[u];
+                    }
+#pragma unroll
+                    for (int j = 0; j < RU; ++j) {
+                        const int u = (k0 + 32 * j) * 32 + owner;
+                        const Key<KIND> kj = make_key<KIND>(rr[j], u);
+                        if (u < a.n_units && classify(a, kj) == 2 && key_less(g, kj) && key_less(kj, n2)) {
+                            if (key_less(kj, n1)) {
+                                n2 = n1;
+                                n1 = kj;
+                            } else {
+                                n2 = kj;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {  // merge the sorted pairs
+                    const Key<KIND> b1 = key_shfl_xor(n1, o), b2 = key_shfl_xor(n2, o);
+                    if (key_less(b1, n1)) {
+                        n2 = key_less(n1, b2) ? n1 : b2;
+                        n1 = b1;
+                    } else if (key_less(b1, n2)) {
+                        n2 = b1;
+                    }
+                }
+                if (lane == owner) {
+                    l1 = n1;
+                    l2 = n2;
+                    more = !key_is_none(n2);
+                }
+            }
+            if (lane == 0) queue[0] = g.idx;
+            qhead = 0;
+            np = 1;
+            __syncwarp();
+        }
+        // ---- expand up to 32 pending units: lane t owns unit t ----
+        const int take = min(np, 32);
+        Key<KIND> ukey = key_none<KIND>();
+        int b = 0, e = 0;
+        if (lane < take) {
+            const int idx = queue[qhead + lane];
+            ukey = make_key<KIND>(krow[idx], idx);
+            b = a.goff[idx];
+            e = a.goff[idx + 1];
+        }
+        qhead += take;
+        np -= take;
+        int cur = b;
+        for (;;) {
+            const int rem = e - cur;
+            int incl = rem;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULLMASK, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(FULLMASK, incl, 31);
+            if (total == 0) break;
+            const int excl = incl - rem;
+            const int tk = max(0, min(rem, LCAP - excl));
+            for (int x = 0; x < tk; ++x) {
+                lrow[excl + x] = a.gmem[cur + x];
+                lmeta[excl + x] = ((uint32_t)lane << POS_BITS) | (uint32_t)(cur + x - b);
+            }
+            cur += tk;
+            const int nl = min(total, LCAP);
+            __syncwarp();
+            for (int i = lane; i < min(PF, nl) * lines; i += 32)
+                prefetch_l2(reinterpret_cast<const char*>(a.refs_nuc + (size_t)lrow[i / lines] * 3 * a.W) + (i % lines) * 128);
+            for (int x0 = 0; x0 < nl && st.kcount <= a.cap; x0 += NR) {
+                int rows[NR], nodes[NR];
+                uint32_t meta[NR], c[NR];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    const int x = min(x0 + k, nl - 1);
+                    rows[k] = lrow[x];
+                    meta[k] = lmeta[x];
+                }
+#pragma unroll
+                for (int k = 0; k < NR; ++k) nodes[k] = a.ref_node[rows[k]];
+                for (int i = lane; i < NR * lines; i += 32) {
+                    const int x = x0 + PF + i / lines;
+                    if (x < nl) prefetch_l2(reinterpret_cast<const char*>(a.refs_nuc + (size_t)lrow[x] * 3 * a.W) + (i % lines) * 128);
+                }
+                member_counts_nuc<NR>(a, qrow, rows, lane, c);
+#pragma unroll
+                for (int k = 0; k < NR; ++k)
+                    if (x0 + k < nl) {
+                        const Key<KIND> uk = key_shfl(ukey, (int)(meta[k] >> POS_BITS));
+                        observe_nuc_counts(a, st, oslot, self, nodes[k], c[k], uk, (int)(meta[k] & ((1u << POS_BITS) - 1u)), lane);
+                    }
+                pairs += (unsigned long long)min(NR, nl - x0);
+            }
+            __syncwarp();
+            if (st.kcount > a.cap) break;
+        }
+        if (st.kcount > a.cap) break;
+    }
+    if (lane == 0 && a.pair_counter && pairs) atomicAdd(a.pair_counter, pairs);
+
+    // ---- PoolQueryWorker.runquery:72-98 (as in select_kernel) ----
+    int status = ST_PLACE;
+    int V = 0;
+    if (st.kcount > a.cap) {
+        status = ST_OVERFLOW;
+        if (a.stash_keys != nullptr) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(a.stash_count, 1);
+            pos = __shfl_sync(FULLMASK, pos, 0);
+            if (pos < a.stash_cap) {
+                const uint4* src = reinterpret_cast<const uint4*>(krow);
+                uint4* dst = reinterpret_cast<uint4*>(a.stash_keys + (size_t)pos * a.ldk);
+                for (int64_t x = lane; x < a.ldk / 4; x += 32) dst[x] = src[x];
+                if (lane == 0) a.stash_ids[pos] = gid;
+            }
+        }
+    } else if (st.has_zero) {
+        status = ST_ZERO;
+    } else if (st.kcount <= 2) {
+        status = ST_TOO_FEW;
+    } else {
+        int* node = a.obs_node + (size_t)oslot * a.cap;
+        double* dist = a.obs_dist + (size_t)oslot * a.cap;
+        int* cnt = a.obs_len + (size_t)oslot * a.cap;   // packed counts parked by observe()
+        const int K = st.kcount;
+        int n2 = 1, sh = 0;
+        while (n2 < K) {
+            n2 <<= 1;
+            ++sh;
+        }
+        __syncwarp();
+        if (n2 <= WORDS && ((unsigned long long)a.tree.M << sh) <= (1ull << 32)) {
+            uint32_t* skey = wbuf;   // the queue and the member list are dead by now
+            for (int i = lane; i < n2; i += 32) skey[i] = i < K ? (((uint32_t)node[i] << sh) | (uint32_t)i) : 0xffffffffu;
+            __syncwarp();
+            sort_keys_smem(skey, n2, lane);
+            for (int i = lane; i < K; i += 32) {   // gather: jc69 correction of the observed leaves in sorted order
+                const uint32_t key = skey[i];
+                const uint32_t c = (uint32_t)cnt[key & (uint32_t)(n2 - 1)];
+                dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+                node[i] = (int)(key >> sh);
+            }
+        } else {   // slots beyond the buffer (second-level reruns) or node ids too wide for the packed key
+            for (int i = lane; i < K; i += 32) {
+                const uint32_t c = (uint32_t)cnt[i];
+                dist[i] = jc69_from_counts(c & 0xffffu, c >> 16, a.gate.vmin);
+            }
             for (int i = K + lane; i < n2; i += 32) {
                 node[i] = 0x7fffffff;
                 dist[i] = 0.0;
@@ -767,28 +1039,7 @@ __global__ void __launch_bounds__(128, (KIND == SEL_NUC && !HEAVY) ? SEL_MINBLOC
             sort_slot(node, dist, n2, lane);
         }
         __syncwarp();   // the chain lengths below overwrite the parked counts
-        // valid nodes = union of leaf -> MRCA paths, MRCA excluded (Subtree.py:23-43).  With leaves sorted by id the
-        // chain owned by leaf i runs up to (excluding) the first ancestor that also contains leaf i+1; the last
-        // leaf's chain stops below the first ancestor that contains leaf 0 (the MRCA).
-        const int leaf0 = node[0];
-        int c = 0;
-        for (int i = lane; i < K; i += 32) {
-            int u = node[i];
-            const int nxt = (i + 1 < K) ? node[i + 1] : -1;
-            int len = 1;
-            while (true) {
-                const int p = a.tree.parent[u];
-                const bool top = (i + 1 < K) ? (p >= nxt) : (a.tree.first[p] <= leaf0);
-                if (top) break;
-                len++;
-                u = p;
-            }
-            a.obs_len[(size_t)oslot * a.cap + i] = len;
-            c += len;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLMASK, c, o);
-        V = c;
+        V = chain_lengths(a, node, a.obs_len + (size_t)oslot * a.cap, K, lane);
     }
     if (lane == 0) {
         a.K[gid] = st.kcount;
@@ -802,16 +1053,16 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
     const int warps = 4;
     dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
     if (a.n <= 0) return;
-    const size_t sm = (size_t)warps * 256 * 4, sm_heavy = (size_t)warps * 4096 * 4;   // sort buffers (SORT_CAP)
+    const size_t sm_nuc = (size_t)warps * 1024 * 4, sm_heavy = (size_t)warps * 4096 * 4;   // select_nuc_kernel: WORDS
     if (kind == SEL_NUC && a.out_map) {  // overflow rerun
-        cudaFuncSetAttribute(select_kernel<SEL_NUC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_heavy);
-        select_kernel<SEL_NUC, true><<<grid, block, sm_heavy, s>>>(a);
+        cudaFuncSetAttribute(select_nuc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_heavy);
+        select_nuc_kernel<true><<<grid, block, sm_heavy, s>>>(a);
     } else if (kind == SEL_NUC)
-        select_kernel<SEL_NUC, false><<<grid, block, sm, s>>>(a);
+        select_nuc_kernel<false><<<grid, block, sm_nuc, s>>>(a);
     else if (kind == SEL_NUCW)
-        select_kernel<SEL_NUCW, false><<<grid, block, sm, s>>>(a);
+        select_kernel<SEL_NUCW><<<grid, block, 0, s>>>(a);
     else if (kind == SEL_AA)
-        select_kernel<SEL_AA, false><<<grid, block, sm, s>>>(a);
+        select_kernel<SEL_AA><<<grid, block, 0, s>>>(a);
     else
-        select_kernel<SEL_MATRIX, false><<<grid, block, sm, s>>>(a);
+        select_kernel<SEL_MATRIX><<<grid, block, 0, s>>>(a);
 }
