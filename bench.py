@@ -503,9 +503,17 @@ def main():
         bf16_sust = float(peaks.get('bf16_tflops_sustained', 1400.0))
         nominal = 4500.0
         img_bytes = (q_per_launch + n_rep) * n_w * 128.0 + 4.0 * q_per_launch * n_rep
+        tc_traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'dense_tc_traffic_r02.json')
+        if os.path.isfile(tpath):
+            # dram bytes of one ncu --set full capture of this kernel, scaled from the captured launch's pair count to this
+            # run's.  4.6x the algorithmic bytes: the operand images are re-read from DRAM when the 148 tiles in flight
+            # drift apart in K (L2 hit rate 68 %); at 2.2 TB/s it is a third of the HBM peak and not what binds the kernel
+            tj = json.load(open(tpath))
+            tc_traffic = tj['dram_bytes'] * (q_per_launch * n_rep) / tj['pairs']
         roofline = {'kernel': 'dense_tc_kernel (tcgen05.mma kind::i8, query x representative mismatch/valid counts as one int8 dot '
                               'product per pair)', 'bound': 'tensor', 'achieved': tops, 'peak': nominal, 'unit': 'TOP/s (int8)',
-                    'frac': tops / nominal, 'traffic': None, 'avg_launch_ms': dense_ms, 'launches': n_dense,
+                    'frac': tops / nominal, 'traffic': tc_traffic, 'avg_launch_ms': dense_ms, 'launches': n_dense,
                     'peak_source': 'nominal dense int8 (4.5 POP/s = 2 x nominal bf16): MEASURED_PEAKS.json holds no int8 figure; '
                                    'against 2 x the measured bf16 GEMM (%s) the fraction is %.2f burst (2 x %.0f) / %.2f '
                                    'sustained (2 x %.0f)' % (peak_src, tops / (2 * bf16_burst), bf16_burst,
@@ -540,7 +548,7 @@ def main():
     sel_bytes = nq * ((8.0 if prot else 4.0) * n_rep + K_avg * (args.sites if prot else 3 * W * 4) + 16.0 * K_avg)   # key row + member rows + observed list
     pla_bytes = nq * (12.0 * K_avg + 20.0 * V_avg + 36.0)
     pla_flops = nq * 110.0 * V_avg
-    roofline_select = {'kernel': 'select_kernel<SEL_NUC> (all launches of a step incl. overflow reruns)', 'bound': 'hbm',
+    roofline_select = {'kernel': 'select_nuc_kernel (all launches of a step incl. overflow reruns)', 'bound': 'hbm',
                        'achieved': sel_bytes / (sel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                        'frac': sel_bytes / (sel_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'ms_per_step': sel_ms,
                        'algorithmic_bytes_per_step': sel_bytes, 'peak_source': peak_src}
