@@ -62,19 +62,46 @@ def gather_records(rec, n_total=None, out=None):
     return full[:n_total]
 
 
+_GATHER_BUFFERS = {}   # (n_total, per, device) -> (device SoA buffer, pinned host twin)
+
+
+def _soa_views(buf, n):
+    """The five result arrays as views of one byte buffer laid out [edge i32 n | status i32 n | error | distal | pendant f64 n]."""
+    import torch
+    e = buf[0:4 * n].view(torch.int32)
+    s = buf[4 * n:8 * n].view(torch.int32)
+    f = buf[8 * n:32 * n].view(torch.float64)
+    return e, f[0:n], f[n:2 * n], f[2 * n:3 * n], s
+
+
 def gather_placements(local, n_total, device=None):
     """local: tuple (edge i32, error f64, distal f64, pendant f64, status i32) of this rank's shard as numpy arrays or
     torch tensors.  Returns the same tuple for all `n_total` queries in input order, as numpy arrays, after ONE
-    all-gather of 32-byte records."""
+    all-gather of 32-byte records.  With NCCL the gathered records are split into the five arrays on the device and come
+    back in ONE copy into a pinned host buffer that is reused from call to call: the returned arrays are views of it,
+    valid until the next call with the same shape (copy them to keep them)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return tuple(np.asarray(a.cpu() if hasattr(a, 'cpu') else a) for a in local)
     if device is None:
         device = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
-    ts = [(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device) for a in local]
+    ts = [(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device, non_blocking=True)
+          for a in local]
     full = gather_records(pack_records(*ts), n_total)
-    return tuple(t.cpu().numpy() for t in unpack_records(full))
+    parts = unpack_records(full)
+    if torch.device(device).type != 'cuda':
+        return tuple(t.numpy() for t in parts)
+    key = (int(n_total), str(device))
+    if key not in _GATHER_BUFFERS:
+        _GATHER_BUFFERS[key] = (torch.empty(32 * n_total, dtype=torch.uint8, device=device),
+                                torch.empty(32 * n_total, dtype=torch.uint8).pin_memory())
+    dbuf, hbuf = _GATHER_BUFFERS[key]
+    for dst, src in zip(_soa_views(dbuf, n_total), parts):
+        dst.copy_(src)
+    hbuf.copy_(dbuf, non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    return tuple(v.numpy() for v in _soa_views(hbuf, n_total))
 
 
 def place_sharded(place_fn, n_total):

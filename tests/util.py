@@ -17,8 +17,12 @@ def gunzip_to(name, workdir):
     """tests/golden/data/<name>.gz -> <workdir>/<name> (cached)."""
     dst = os.path.join(workdir, name)
     if not os.path.exists(dst):
-        with gzip.open(os.path.join(DATA, name + '.gz'), 'rb') as fi, open(dst, 'wb') as fo:
+        # written aside and renamed: the ranks of a multi-process test extract the same file at the same time, and a rank
+        # must never see a half-written one
+        tmp = '%s.%d.tmp' % (dst, os.getpid())
+        with gzip.open(os.path.join(DATA, name + '.gz'), 'rb') as fi, open(tmp, 'wb') as fo:
             fo.write(fi.read())
+        os.replace(tmp, dst)
     return dst
 
 
