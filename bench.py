@@ -400,11 +400,16 @@ def main():
         barrier()
         e0.record(stream)
         t0 = time.time()
+        t_place = t_gather = 0.0
         for _ in range(args.steps):
+            ta = time.time()
             out = pl.place_bytes(bytes_np, self_node, params)
+            tb = time.time()
             if world > 1:
                 # the product's multi-process path ends here: every rank holds all placements (placer.place_arrays)
                 out_all = parallel.gather_placements(out, nq * world, device=device)
+            t_place += tb - ta
+            t_gather += time.time() - tb
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
@@ -416,7 +421,9 @@ def main():
                'h2d_bytes_per_step': (int(bytes_host.numel()) + (32 * nq if world > 1 else 0)) * world,
                'd2h_bytes_per_step': (32 * nq + (32 * nq * world if world > 1 else 0)) * world,
                'input': 'alignment bytes (uint8 per site) in pinned host memory, packed on the device',
-               'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps}
+               'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps,
+               'rank0_place_call_ms_per_step': 1e3 * t_place / args.steps,
+               'rank0_gather_ms_per_step': 1e3 * t_gather / args.steps}
         tme = pl.timings(reset=True)
         e2e['stage_ms_per_step'] = {k: tme[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms',
                                                                       'placement_ms', 'd2h_ms')}
