@@ -755,6 +755,69 @@ def test_config5_parity_including_overflow_reruns(workdir):
     pl.close()
 
 
+@pytest.mark.parametrize('thr,baseobs', [(0.6, 25), (0.0005, 2500)])
+def test_clusters_larger_than_the_member_list(thr, baseobs, workdir):
+    """Four clusters of ~700 leaves each plus singletons: the members of one batch of pending clusters do not fit the
+    selection kernel's shared-memory member list (352 entries in the first pass, 1888 in the rerun), so the list is
+    filled and walked in rounds -- through the near phase (large threshold: everything is near) and through the far
+    phase (tiny threshold, -b 2500: the clusters are taken in ascending order until 2500 leaves are observed).  Observed
+    sets identical to the oracle's, placements within tolerance."""
+    import types
+    from oracle import apples_oracle as orc
+    from apples_b200 import synth
+    from apples_b200.placer import GpuPlacer, results_to_jplace
+    from apples_b200.reference import ReducedReference
+    from apples_b200.tree import BackboneTree
+    rng = np.random.default_rng(77)
+    n, L = 3000, 400
+    nwk = synth.random_tree(n, seed=5150, mean_edge=0.004)
+    tfp = os.path.join(workdir, 'bigclusters.nwk')
+    open(tfp, 'w').write(nwk)
+    tree = BackboneTree.from_newick(tfp)
+    refs, states = synth.evolve_alignment(tree, L, seed=5151, gap_frac=0.05)
+    qd, _ = synth.make_queries(tree, states, 6, seed=5152, mean_extra=0.01)
+    queries = [(k, v, None) for k, v in qd.items()]
+    names = list(refs.keys())
+    tsv = os.path.join(workdir, 'bigclusters_%s.tsv' % baseobs)
+    with open(tsv, 'w') as f:
+        f.write('SequenceName\tClusterNumber\n')
+        for nm in names:
+            f.write('%s\t%d\n' % (nm, -1 if rng.random() < 0.05 else int(rng.integers(1, 5))))
+    ref = ReducedReference(None, False, tfp, thr, 1, cluster_tsv=tsv, tree=tree, refs=refs)
+    opt = types.SimpleNamespace(method_name='FM', criterion_name='MLSE', negative_branch=False,
+                                base_observation_threshold=baseobs, filt_threshold=thr, minimum_alignment_overlap=0.001,
+                                exclude_intplace=False)
+    ref.set_baseobs(baseobs)
+    pl = GpuPlacer(tree, ref, tree.name_to_node, device=0)
+    params = pl.params_from_options(opt)
+    qn = [q[0] for q in queries]
+    sn = pl.self_nodes(qn)
+    packed = pl.pack_queries([q[1] for q in queries])
+    out = pl.place_packed(packed, sn, params)
+    count, node, dist = pl.observed_sets(params, packed=packed, self_node=sn, cap=4096)
+    res = results_to_jplace(qn, [False] * len(qn), out, log=False, degenerate='keep')
+    pl.close()
+    otree, onames = orc.load_tree(tfp)
+    octx = orc.OracleContext(otree, onames, refs=refs, representatives=orc.representatives_from_tsv(tsv, refs, False),
+                             method='FM', criterion='MLSE', filt_threshold=thr, baseobs=baseobs, overlap=0.001)
+    big = 0
+    for qi, (q, r) in enumerate(zip(queries, res)):
+        det = {}
+        exp, st = octx.runquery(q[0], q[1], None, detail=det)
+        eobs = {tree.name_to_node[k]: v for k, v in det['observed']}
+        k = int(count[qi])
+        assert k == len(eobs), (q[0], k, len(eobs))
+        big += k > 1888
+        if st in (0, 3):   # placed: sorted by node id, distances corrected (a zero-distance query keeps the raw list)
+            assert node[qi, :k].tolist() == sorted(eobs), q[0]
+            for u, d in zip(node[qi, :k].tolist(), dist[qi, :k].tolist()):
+                assert util.close(d, eobs[u], 1e-9, 0.0), (q[0], u)
+        else:
+            assert sorted(node[qi, :k].tolist()) == sorted(eobs), q[0]
+        _check_p('bigclusters', q[0], r['placements'][0]['p'][0], exp['placements'][0]['p'][0], False, octx, q)
+    assert big >= 3, 'the case no longer overflows the rerun member list'
+
+
 def _oracle_check(tag, tree, tfp, refs, reps, queries, res, opt, protein=False):
     from oracle import apples_oracle as orc
     otree, onames = orc.load_tree(tfp)
