@@ -368,7 +368,8 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
         }
     }
     if (slow_ctx && ensure(ctx, ctx->q_bytes_p, (size_t)QB * ctx->Lp)) return -1;
-    if (io.h_queries && two_bufs && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
+    // second packed-query buffer: staged packed queries, or the device packer's output for the sub-batch after this one
+    if ((io.h_queries || (io.h_bytes && !slow_ctx)) && two_bufs && ensure(ctx, ctx->q_rm2, (size_t)QB * qrow)) return -1;
     if (!matrix) {
         if (ensure(ctx, ctx->q_rm, (size_t)QB * qrow)) return -1;
         if (sel_kind == SEL_NUC && ensure(ctx, ctx->q_wm, (size_t)3 * ctx->Wp * QB * 4)) return -1;
@@ -565,8 +566,10 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
     bool used[2] = {false, false};
     int sbi = 0;
     // host input: a short first sub-batch, so that the compute stream waits for a small copy only; the copies of all later
-    // sub-batches hide behind the one before (2.2 ms of exposed PCIe time per 125k-query batch otherwise)
-    const int ramp = (!matrix && (io.h_queries || io.h_bytes) && n > QB) ? std::min(QB, 4096) : QB;
+    // sub-batches hide behind the one before (2.2 ms of exposed PCIe time per 125k-query batch otherwise).  8192 queries: long
+    // enough to cover the copy + packing of the full-size sub-batch that follows (0.36 us of compute against 0.1 us of copy per
+    // query at config 5 shapes)
+    const int ramp = (!matrix && (io.h_queries || io.h_bytes) && n > QB) ? std::min(QB, 8192) : QB;
     for (int sb0 = 0, nb = 0; sb0 < n; sb0 += nb, ++sbi) {
         nb = std::min(sbi == 0 ? ramp : QB, n - sb0);
         const void* d_q = nullptr;
@@ -598,17 +601,21 @@ int run_macro(apples_ctx* ctx, int64_t base0, int n, const BatchIO& io, const ap
                                        (size_t)nb * io.byte_stride, cudaMemcpyHostToDevice, cs));
                 }
             }
+            if (io.h_bytes && !slow_ctx) {
+                // packed on the COPY stream, into the buffer that goes with the staging buffer: the packer of sub-batch b + 1
+                // runs beside the count kernel of sub-batch b instead of in front of its own (1.1 ms per 125k-query batch)
+                void* pk = buf ? ctx->q_rm2.p : ctx->q_rm.p;
+                CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, pk, (int*)ctx->bad_flag.p, cs,
+                               nuc ? (int*)ctx->q_rowflag.p + sb0 : nullptr));
+                ctx->n_launch += 1;
+                d_q = pk;
+            }
             CK(cudaEventRecord(ctx->ev_ready[buf], cs));
             CK(cudaStreamWaitEvent(s, ctx->ev_ready[buf], 0));
             if (io.h_bytes && slow_ctx) {
                 CK(launch_repitch_bytes((const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->Lp, (uint8_t*)ctx->q_bytes_p.p, s));
                 ctx->n_launch += 1;
-            } else if (io.h_bytes) {
-                CK(launch_pack(ctx->kind, (const uint8_t*)stage, io.byte_stride, nb, ctx->L, ctx->q_rm.p,
-                               (int*)ctx->bad_flag.p, s, (nuc && !slow_ctx) ? (int*)ctx->q_rowflag.p + sb0 : nullptr));
-                ctx->n_launch += 1;
-                d_q = ctx->q_rm.p;
-            } else {
+            } else if (!io.h_bytes) {
                 d_q = stage;
             }
             used[buf] = true;
