@@ -353,6 +353,12 @@ class MultiGpuPlacer:
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         return self._sharded('place_rows', rows, self_node, params)
 
+    def timings(self, reset=False):
+        """Stage timers of the contexts: times are the maximum over the GPUs (they run side by side), counters the sum."""
+        ts = [p.timings(reset) for p in self.placers]
+        return {k: (max if k.endswith('_ms') or k.startswith('max_') or k.endswith('_mhz') else sum)(t[k] for t in ts)
+                for k in ts[0]}
+
 
 def visible_devices(first=0, count=0):
     """Device ordinals for `--device first --gpus count` (count 0 = every visible device from `first` on)."""
@@ -398,6 +404,7 @@ def place_arrays(reference, options, name_to_node_map, queries, tree=None, place
         else:
             placer = GpuPlacer(tree, reference, name_to_node_map, device=devs[0])
     try:
+        t_before = placer.timings()
         in_backbone = [n in placer.name_to_node for n in names]
         # upstream decides per query (`if obs_dist` in runquery, PoolQueryWorker.py:40); one batch is one mode here
         matrix = bool(queries[0][2])
@@ -431,6 +438,7 @@ def place_arrays(reference, options, name_to_node_map, queries, tree=None, place
             params = placer.params_from_options(options, reference)
             mat = _fasta.as_byte_matrix([q[1] for q in mine], placer.L)
             out = placer.place_bytes(mat, self_node, params) if mine else placer._outputs(0)
+        log_stage_times(placer, len(mine), t_before)
         if world > 1:
             from .parallel import gather_placements
             out = gather_placements(out, len(queries))
@@ -438,6 +446,21 @@ def place_arrays(reference, options, name_to_node_map, queries, tree=None, place
     finally:
         if own:
             placer.close()
+
+
+def log_stage_times(placer, n_queries, before=None):
+    """The reference logs two lines per query (PoolQueryWorker.py:134-139: time of the distance stage, time of the dynamic
+    programming).  A batch has no per-query times; the same two lines are logged once per batch from the device stage
+    timers (distances = packing + count kernels + selection, dynamic programming = placement kernels)."""
+    import logging
+    import time
+    t = placer.timings()
+    if before:   # a caller-owned placer accumulates over its calls: this call's share
+        t = {k: t[k] - before.get(k, 0.0) for k in t}
+    logging.info('[%s] Distances are computed for %d queries in %.3f seconds.\n'
+                 '[%s] Dynamic programming is completed for %d queries in %.3f seconds.'
+                 % (time.strftime('%H:%M:%S'), n_queries, 1e-3 * (t['transpose_ms'] + t['rep_distance_ms'] + t['selection_ms']),
+                    time.strftime('%H:%M:%S'), n_queries, 1e-3 * t['placement_ms']))
 
 
 def log_messages(names, in_backbone, out, exclude_intplace=False):
@@ -488,6 +511,7 @@ def place_alignment(reference, options, name_to_node_map, names, mat, tree=None,
         else:
             placer = GpuPlacer(tree, reference, name_to_node_map, device=devs[0])
     try:
+        t_before = placer.timings()
         n2n = placer.name_to_node
         in_backbone = np.fromiter((nm in n2n for nm in names), dtype=bool, count=n)
         self_node = np.full(hi - lo, -1, np.int32)
@@ -497,6 +521,7 @@ def place_alignment(reference, options, name_to_node_map, names, mat, tree=None,
         if mat.shape[1] != placer.L:
             raise ValueError('query alignment has %d columns, reference has %d' % (mat.shape[1], placer.L))
         out = placer.place_bytes(mat[lo:hi], self_node, params) if hi > lo else placer._outputs(0)
+        log_stage_times(placer, hi - lo, t_before)
         if world > 1:
             from .parallel import gather_placements
             out = gather_placements(out, n)
