@@ -746,8 +746,18 @@ __global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
 // Reference.py:146) go through the same queue one at a time, in ascending order.  The observed SET, the counts and the
 // zero tie-break (by unit key and position) do not depend on the order of expansion, so the results are those of the
 // generic kernel bit for bit.
+// one warp (query) per block: a block's registers and shared memory stay allocated until its slowest query is done, and
+// the queries of a block differ by 10x in work.  Measured 4 / 2 / 1 warps per block: 45.3 / 44.7 / 44.6 ms per step for the
+// first pass, 43.8-44.2 with the rerun launch at 1 as well (tools/ab_variants.sh, same box)
+#ifndef SEL_NUC_WARPS
+#define SEL_NUC_WARPS 1
+#endif
+#ifndef SEL_HEAVY_WARPS
+#define SEL_HEAVY_WARPS 1
+#endif
 template <bool HEAVY>
-__global__ void __launch_bounds__(128, HEAVY ? 4 : SEL_MINBLOCKS) select_nuc_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(32 * (HEAVY ? SEL_HEAVY_WARPS : SEL_NUC_WARPS), (HEAVY ? 16 : 32) / (HEAVY ? SEL_HEAVY_WARPS : SEL_NUC_WARPS))
+select_nuc_kernel(const SelectArgs a) {
     constexpr int KIND = SEL_NUC;
     constexpr int NR = HEAVY ? 8 : SEL_NR;
     constexpr int WORDS = HEAVY ? 4096 : 1024;  // shared 32-bit words per warp (also the sort buffer of the tail)
@@ -1055,10 +1065,13 @@ void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
     if (a.n <= 0) return;
     const size_t sm_nuc = (size_t)warps * 1024 * 4, sm_heavy = (size_t)warps * 4096 * 4;   // select_nuc_kernel: WORDS
     if (kind == SEL_NUC && a.out_map) {  // overflow rerun
-        cudaFuncSetAttribute(select_nuc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_heavy);
-        select_nuc_kernel<true><<<grid, block, sm_heavy, s>>>(a);
-    } else if (kind == SEL_NUC)
-        select_nuc_kernel<false><<<grid, block, sm_nuc, s>>>(a);
+        const int w = SEL_HEAVY_WARPS;
+        cudaFuncSetAttribute(select_nuc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm_heavy / warps * w));
+        select_nuc_kernel<true><<<(a.n + w - 1) / w, w * 32, sm_heavy / warps * w, s>>>(a);
+    } else if (kind == SEL_NUC) {
+        const int w = SEL_NUC_WARPS;
+        select_nuc_kernel<false><<<(a.n + w - 1) / w, w * 32, sm_nuc / warps * w, s>>>(a);
+    }
     else if (kind == SEL_NUCW)
         select_kernel<SEL_NUCW><<<grid, block, 0, s>>>(a);
     else if (kind == SEL_AA)
