@@ -763,7 +763,10 @@ select_nuc_kernel(const SelectArgs a) {
     constexpr int WORDS = HEAVY ? 4096 : 1024;  // shared 32-bit words per warp (also the sort buffer of the tail)
     constexpr int QCAP = 320;                   // pending units: fewer than 32 left over + one chunk of 256 keys
     constexpr int LCAP = (WORDS - QCAP) / 2;    // member list entries
-    constexpr int PF = HEAVY ? 16 : 8;          // rows prefetched ahead of the one being counted
+#ifndef SEL_PF
+#define SEL_PF 8
+#endif
+    constexpr int PF = HEAVY ? 16 : SEL_PF;     // rows prefetched ahead of the one being counted
     constexpr int POS_BITS = 27;
     extern __shared__ uint32_t s_sortbuf[];
     uint32_t* wbuf = s_sortbuf + (threadIdx.x >> 5) * WORDS;
@@ -788,7 +791,10 @@ select_nuc_kernel(const SelectArgs a) {
     st.znode = -1;
     st.zkey.idx = 0;
 
-    constexpr int U = 8;
+#ifndef SEL_U
+#define SEL_U 8
+#endif
+    constexpr int U = SEL_U;   // keys per lane and chunk (independent loads in flight)
     Key<KIND> l1 = key_none<KIND>(), l2 = key_none<KIND>();
     uint32_t bm = 1u, bv = 0u;
     int u0 = 0, np = 0, qhead = 0;
