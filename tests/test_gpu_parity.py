@@ -752,6 +752,13 @@ def test_config5_parity_including_overflow_reruns(workdir):
         if _check_p('c5', q[0], got, p, False, octx, q) == 'tie':
             ties += 1
     assert ties <= 2
+    # the same batch in three sub-batches (a short first one: the copy stream runs ahead of the compute stream with the
+    # device packer, api.cu run_macro), from bytes and from packed rows: byte-identical to the single-sub-batch result
+    pl.set_limits(max_subbatch=10240)
+    for other in (pl.place_bytes(q_host, None, params), pl.place_packed(packed_host, None, params)):
+        for x, y in zip((edge, error, distal, pendant, status), other):
+            assert x.tobytes() == y.tobytes()
+    assert pl.timings()['rep_distance_launches'] >= 1 + 3 + 3
     pl.close()
 
 
