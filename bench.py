@@ -511,6 +511,7 @@ def main():
         nominal = 4500.0
         img_bytes = (q_per_launch + n_rep) * n_w * 128.0 + 4.0 * q_per_launch * n_rep
         fill_bytes = -(-q_per_launch // 256) * -(-n_rep // 256) * n_w * 65536.0
+        read_bytes = fill_bytes * 1.5
         tc_traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'dense_tc_traffic_r02.json')
         if os.path.isfile(tpath):
@@ -527,13 +528,17 @@ def main():
                                    'sustained (2 x %.0f)' % (peak_src, tops / (2 * bf16_burst), bf16_burst,
                                                              tops / (2 * bf16_sust), bf16_sust),
                     'algorithmic_ops_per_launch': ops,
-                    # second resource of the same kernel: every 256 x 256 tile pulls 64 KB of operand images per 32-site
-                    # word from L2 into shared memory; an SM's fill port takes 64 B per clock
-                    'l2_to_smem': {'achieved': fill_bytes / (dense_ms * 1e-3) / 1e9, 'peak': 148 * 64 * sm_max * 1e6 / 1e9,
-                                   'unit': 'GB/s', 'frac': fill_bytes / (dense_ms * 1e-3) / (148 * 64 * sm_max * 1e6),
-                                   'bytes_per_launch': fill_bytes,
-                                   'peak_source': '148 SMs x 64 B/clk x max SM clock (B300_MICROARCH.md; ncu of the kernel '
-                                                  'reads 84 GB per 24 320-query launch, profiles/dense_tc_traffic_r02.json)'},
+                    # the resource that actually runs out: shared-memory bandwidth.  Per 32-site word a 256 x 256 tile writes
+                    # 64 KB of operand images into shared memory (TMA) and its 8 MMAs (M = 128, N = 256, K = 32 bytes) read
+                    # 4 KB of A and 8 KB of B each = 96 KB; the crossbar moves 128 B per clock and SM
+                    'smem': {'achieved': (fill_bytes + read_bytes) / (dense_ms * 1e-3) / 1e9, 'peak': 148 * 128 * sm_max * 1e6 / 1e9,
+                             'unit': 'GB/s', 'frac': (fill_bytes + read_bytes) / (dense_ms * 1e-3) / (148 * 128 * sm_max * 1e6),
+                             'fill_bytes_per_launch': fill_bytes, 'operand_read_bytes_per_launch': read_bytes,
+                             'peak_source': 'shared-memory crossbar 128 B/clk/SM (B300_MICROARCH.md) x 148 SMs x max SM clock; '
+                                            'fills checked against ncu l1tex__m_xbar2l1tex_read_bytes (84.06 GB per 24 320-query '
+                                            'launch, profiles/dense_tc_traffic_r02.json); at the full tensor rate the kernel '
+                                            'would need 159 B/clk/SM, so 0.80 of the tensor peak is this design point\'s ceiling '
+                                            'if no operand byte is reused inside the tensor core'},
                     'cell_sites_per_s': cs_rate, 'vs_int_pipe_balanced_peak': cs_rate / bal_peak,
                     'hbm': {'achieved': img_bytes / (dense_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                             'frac': img_bytes / (dense_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': peak_src,
