@@ -86,9 +86,20 @@ def gather_placements(local, n_total, device=None):
         return tuple(np.asarray(a.cpu() if hasattr(a, 'cpu') else a) for a in local)
     if device is None:
         device = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    import os
+    import time
+    trace = torch.device(device).type == 'cuda' and os.environ.get('APPLES_B200_GATHER_TRACE')
+    t0 = time.time()
     ts = [(a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))).to(device, non_blocking=True)
           for a in local]
-    full = gather_records(pack_records(*ts), n_total)
+    rec = pack_records(*ts)
+    if trace:
+        torch.cuda.synchronize(device)
+        t1 = time.time()
+    full = gather_records(rec, n_total)
+    if trace:
+        torch.cuda.synchronize(device)
+        t2 = time.time()
     parts = unpack_records(full)
     if torch.device(device).type != 'cuda':
         return tuple(t.numpy() for t in parts)
@@ -101,6 +112,10 @@ def gather_placements(local, n_total, device=None):
         dst.copy_(src)
     hbuf.copy_(dbuf, non_blocking=True)
     torch.cuda.current_stream(device).synchronize()
+    if trace:
+        import sys
+        sys.stderr.write('[apples_b200] gather rank %d: upload + pack %.2f ms, all-gather %.2f ms, split + download %.2f ms\n'
+                         % (dist.get_rank(), 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (time.time() - t2)))
     return tuple(v.numpy() for v in _soa_views(hbuf, n_total))
 
 

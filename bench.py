@@ -395,7 +395,9 @@ def main():
         bytes_host.copy_(q_bytes)
         bytes_np = bytes_host.numpy()
         for _ in range(min(args.warmup, 1)):
-            pl.place_bytes(bytes_np, self_node, params)
+            out = pl.place_bytes(bytes_np, self_node, params)
+            if world > 1:   # the gather's pinned buffer and first-use costs belong to the warm-up as well
+                parallel.gather_placements(out, nq * world, device=device)
         pl.timings(reset=True)   # stage timers of the timed steps only
         barrier()
         e0.record(stream)
@@ -413,17 +415,24 @@ def main():
         e1.record(stream)
         barrier()
         ems = e0.elapsed_time(e1)
+        place_ms_per_rank = None
         if world > 1:
             t = torch.tensor([ems], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
+            # the gather is a synchronisation point: a rank whose host->device copies are slower (PCIe / NUMA position)
+            # makes every other rank wait there
+            tp = torch.tensor([1e3 * t_place / args.steps], dtype=torch.float64, device=device)
+            tps = [torch.zeros_like(tp) for _ in range(world)]
+            dist.all_gather(tps, tp)
+            place_ms_per_rank = [round(float(x.item()), 2) for x in tps]
         e2e = {'value': nq * world * args.steps / (ems / 1e3), 'unit': 'queries/s',
                'h2d_bytes_per_step': (int(bytes_host.numel()) + (32 * nq if world > 1 else 0)) * world,
                'd2h_bytes_per_step': (32 * nq + (32 * nq * world if world > 1 else 0)) * world,
                'input': 'alignment bytes (uint8 per site) in pinned host memory, packed on the device',
                'wall_ms_per_step': 1e3 * (time.time() - t0) / args.steps,
                'rank0_place_call_ms_per_step': 1e3 * t_place / args.steps,
-               'rank0_gather_ms_per_step': 1e3 * t_gather / args.steps}
+               'rank0_gather_ms_per_step': 1e3 * t_gather / args.steps, 'place_call_ms_per_rank': place_ms_per_rank}
         tme = pl.timings(reset=True)
         e2e['stage_ms_per_step'] = {k: tme[k] / args.steps for k in ('h2d_ms', 'transpose_ms', 'rep_distance_ms', 'selection_ms',
                                                                       'placement_ms', 'd2h_ms')}
