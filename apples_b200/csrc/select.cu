@@ -500,8 +500,11 @@ __device__ __forceinline__ int chain_lengths(const SelectArgs& a, const int* nod
 #ifndef SEL_NR
 #define SEL_NR 2
 #endif
+#ifndef SEL_GEN_WARPS
+#define SEL_GEN_WARPS 1   // warps (queries) per block of the generic kernel (protein bench: 11.6 / 11.1 / 10.85 ms at 4 / 2 / 1)
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128, 4) select_kernel(const SelectArgs a) {
+__global__ void __launch_bounds__(32 * SEL_GEN_WARPS, 16 / SEL_GEN_WARPS) select_kernel(const SelectArgs a) {
     static_assert(KIND != SEL_NUC, "packed nucleotide counts go through select_nuc_kernel");
     constexpr int NR = SEL_NR;
     const int lane = threadIdx.x & 31;
@@ -1066,22 +1069,20 @@ select_nuc_kernel(const SelectArgs a) {
 }
 
 void launch_select(int kind, const SelectArgs& a, cudaStream_t s) {
-    const int warps = 4;
-    dim3 grid((a.n + warps - 1) / warps), block(warps * 32);
     if (a.n <= 0) return;
-    const size_t sm_nuc = (size_t)warps * 1024 * 4, sm_heavy = (size_t)warps * 4096 * 4;   // select_nuc_kernel: WORDS
     if (kind == SEL_NUC && a.out_map) {  // overflow rerun
         const int w = SEL_HEAVY_WARPS;
-        cudaFuncSetAttribute(select_nuc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm_heavy / warps * w));
-        select_nuc_kernel<true><<<(a.n + w - 1) / w, w * 32, sm_heavy / warps * w, s>>>(a);
+        const size_t sm = (size_t)w * 4096 * 4;   // select_nuc_kernel<true>: WORDS per warp
+        cudaFuncSetAttribute(select_nuc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        select_nuc_kernel<true><<<(a.n + w - 1) / w, w * 32, sm, s>>>(a);
     } else if (kind == SEL_NUC) {
         const int w = SEL_NUC_WARPS;
-        select_nuc_kernel<false><<<(a.n + w - 1) / w, w * 32, sm_nuc / warps * w, s>>>(a);
+        select_nuc_kernel<false><<<(a.n + w - 1) / w, w * 32, (size_t)w * 1024 * 4, s>>>(a);
+    } else {
+        const int w = SEL_GEN_WARPS;
+        const dim3 g((a.n + w - 1) / w), b(w * 32);
+        if (kind == SEL_NUCW) select_kernel<SEL_NUCW><<<g, b, 0, s>>>(a);
+        else if (kind == SEL_AA) select_kernel<SEL_AA><<<g, b, 0, s>>>(a);
+        else select_kernel<SEL_MATRIX><<<g, b, 0, s>>>(a);
     }
-    else if (kind == SEL_NUCW)
-        select_kernel<SEL_NUCW><<<grid, block, 0, s>>>(a);
-    else if (kind == SEL_AA)
-        select_kernel<SEL_AA><<<grid, block, 0, s>>>(a);
-    else
-        select_kernel<SEL_MATRIX><<<grid, block, 0, s>>>(a);
 }
