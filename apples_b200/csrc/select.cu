@@ -817,7 +817,10 @@ select_nuc_kernel(const SelectArgs a) {
                 // larger of the band's upper edge P_hi / 65536 and the ratio of l2 (l2.m << 16 and P_hi * v fit 32 bits:
                 // counts <= 65535, P_hi < 49154) ----
                 {
-                    const int u = u0 + 2 * 32 * U + lane * 32;
+#ifndef SEL_KPF
+#define SEL_KPF 2   // key chunks prefetched ahead of the one being scanned
+#endif
+                    const int u = u0 + SEL_KPF * 32 * U + lane * 32;
                     if (lane < U && u < a.n_units) prefetch_l2(krow + u);
                 }
                 uint32_t raw[U];
