@@ -18,6 +18,7 @@ STATUS_CODE_MASK = 0xff
 PLACED, ZERO_DIST_LEAF, TOO_FEW_DISTANCES, PLACED_MISPLACEMENT_FLAG = 0, 1, 2, 3
 FLAG_PENDANT_INT0 = 0x100
 FLAG_DEGENERATE = 0x200
+NEWICK_UNSUPPORTED = 1   # apples_newick_*: text outside the native parser's language, use the Python twin
 
 # every symbol the header declares (tests/test_cabi.py checks the library exports exactly these)
 SYMBOLS = [
@@ -28,6 +29,10 @@ SYMBOLS = [
     'apples_fasta_open', 'apples_fasta_close', 'apples_fasta_count', 'apples_fasta_max_len', 'apples_fasta_stride',
     'apples_fasta_uniform', 'apples_fasta_pinned', 'apples_fasta_matrix', 'apples_fasta_lengths', 'apples_fasta_names',
     'apples_fasta_name_offsets', 'apples_jplace_write',
+    'apples_newick_parse', 'apples_newick_free', 'apples_newick_nodes', 'apples_newick_rooted', 'apples_newick_parent',
+    'apples_newick_level', 'apples_newick_first', 'apples_newick_edge_length', 'apples_newick_has_length',
+    'apples_newick_has_label', 'apples_newick_labels', 'apples_newick_label_offsets', 'apples_newick_extended',
+    'apples_free_text',
 ]
 
 
@@ -94,6 +99,18 @@ def load():
         getattr(lib, 'apples_fasta_' + fn).restype = vp
     lib.apples_jplace_write.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i64, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
                                         C.c_int, C.POINTER(i64), C.c_char_p, C.c_int]
+    lib.apples_newick_parse.argtypes = [vp, i64, C.POINTER(vp), C.c_char_p, C.c_int]
+    lib.apples_newick_free.argtypes = [vp]
+    lib.apples_newick_free.restype = None
+    lib.apples_newick_nodes.argtypes = [vp]
+    lib.apples_newick_nodes.restype = i64
+    lib.apples_newick_rooted.argtypes = [vp]
+    for fn in ('parent', 'level', 'first', 'edge_length', 'has_length', 'has_label', 'labels', 'label_offsets'):
+        getattr(lib, 'apples_newick_' + fn).argtypes = [vp]
+        getattr(lib, 'apples_newick_' + fn).restype = vp
+    lib.apples_newick_extended.argtypes = [i64, vp, vp, vp, vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(i64), C.c_char_p, C.c_int]
+    lib.apples_free_text.argtypes = [vp]
+    lib.apples_free_text.restype = None
     _lib = lib
     return lib
 

@@ -25,7 +25,7 @@ class BackboneTree:
     nchild[M] int32, label[M] list[str|None], is_rooted bool.
     """
 
-    def __init__(self, parent, edge_length, has_length, label, is_rooted, length_text=None):
+    def __init__(self, parent, edge_length, has_length, label, is_rooted, length_text=None, level=None, first=None):
         self.parent = np.ascontiguousarray(parent, dtype=np.int32)
         self.edge_length = np.ascontiguousarray(edge_length, dtype=np.float64)
         self.has_length = np.ascontiguousarray(has_length, dtype=bool)
@@ -37,20 +37,22 @@ class BackboneTree:
         nchild = np.zeros(M, dtype=np.int32)
         np.add.at(nchild, par[par >= 0], 1)
         self.nchild = nchild
-        # level: parents have larger ids than children, so one descending sweep suffices
-        level = np.zeros(M, dtype=np.int32)
-        first = np.arange(M, dtype=np.int32)
-        pl = par.tolist()
-        lv = level.tolist()
-        for u in range(M - 2, -1, -1):
-            lv[u] = lv[pl[u]] + 1
-        self.level = np.asarray(lv, dtype=np.int32)
-        fl = first.tolist()
-        for u in range(M - 1):
-            p = pl[u]
-            if fl[u] < fl[p]:
-                fl[p] = fl[u]
-        self.first = np.asarray(fl, dtype=np.int32)
+        if level is not None and first is not None:   # the native parser computes them with the arrays
+            self.level = np.ascontiguousarray(level, dtype=np.int32)
+            self.first = np.ascontiguousarray(first, dtype=np.int32)
+        else:
+            # level: parents have larger ids than children, so one descending sweep suffices
+            pl = par.tolist()
+            lv = [0] * M
+            for u in range(M - 2, -1, -1):
+                lv[u] = lv[pl[u]] + 1
+            self.level = np.asarray(lv, dtype=np.int32)
+            fl = list(range(M))
+            for u in range(M - 1):
+                p = pl[u]
+                if fl[u] < fl[p]:
+                    fl[p] = fl[u]
+            self.first = np.asarray(fl, dtype=np.int32)
         self.is_leaf = nchild == 0
         self.leaf_ids = np.nonzero(self.is_leaf)[0].astype(np.int32)
         # name -> edge_index of the leaf (prepareTree.py:32-34; later duplicates overwrite, like a dict)
@@ -60,8 +62,10 @@ class BackboneTree:
 
     # ------------------------------------------------------------------ construction
     @classmethod
-    def from_newick(cls, newick):
-        """Parse a newick string or file path (prepareTree.py:24)."""
+    def from_newick(cls, newick, native=None):
+        """Parse a newick string or file path (prepareTree.py:24).  The native parser of libapples_b200
+        (apples_newick_parse, hostio.cpp) does the work when the library is there and the text is inside its language;
+        this function's Python body is the definition of that language and the fallback.  native=True / False force one."""
         if isinstance(newick, (bytes, bytearray)):
             newick = newick.decode()
         if os.path.isfile(os.path.expanduser(newick)):
@@ -69,6 +73,12 @@ class BackboneTree:
                 s = f.read()
         else:
             s = newick
+        if native is not False:
+            t = cls._from_newick_native(s)
+            if t is not None:
+                return t
+            if native is True:
+                raise ValueError('the native newick parser does not take this text')
         s = s.strip()
         is_rooted = s.startswith('[&R]')
         if s.startswith('['):
@@ -138,6 +148,46 @@ class BackboneTree:
             label[r] = c_label[v]
         return cls(parent, elen, has, label, is_rooted)
 
+    @classmethod
+    def _from_newick_native(cls, s):
+        """BackboneTree through apples_newick_parse, or None when the library is missing or declines the text."""
+        import ctypes as C
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except (RuntimeError, OSError):
+            return None
+        raw = s.encode('utf-8', 'surrogateescape') if isinstance(s, str) else bytes(s)
+        h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        rc = lib.apples_newick_parse(raw, len(raw), C.byref(h), err, 256)
+        if rc == _lib.NEWICK_UNSUPPORTED:
+            return None
+        if rc != 0:
+            raise ValueError(err.value.decode())
+        try:
+            n = int(lib.apples_newick_nodes(h))
+
+            def arr(fn, dtype, count):
+                p = getattr(lib, 'apples_newick_' + fn)(h)
+                return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(count,)).copy()
+            parent, level, first = arr('parent', np.int32, n), arr('level', np.int32, n), arr('first', np.int32, n)
+            elen, has = arr('edge_length', np.float64, n), arr('has_length', np.uint8, n).astype(bool)
+            has_label = arr('has_label', np.uint8, n)
+            off = arr('label_offsets', np.int64, n + 1)
+            text = C.string_at(lib.apples_newick_labels(h), int(off[-1])).decode('utf-8', 'surrogateescape')
+            if len(text) == int(off[-1]):      # ASCII labels: byte offsets are character offsets
+                o = off.tolist()
+                label = [text[o[i]:o[i + 1]] if f else None for i, f in enumerate(has_label.tolist())]
+            else:
+                b = text.encode('utf-8', 'surrogateescape')
+                o = off.tolist()
+                label = [b[o[i]:o[i + 1]].decode('utf-8', 'surrogateescape') if f else None for i, f in enumerate(has_label.tolist())]
+            rooted = bool(lib.apples_newick_rooted(h))
+        finally:
+            lib.apples_newick_free(h)
+        return cls(parent, elen, has, label, rooted, level=level, first=first)
+
     # ------------------------------------------------------------------ queries
     def children_of(self, u):
         """Children of u, left to right (increasing id)."""
@@ -150,8 +200,15 @@ class BackboneTree:
         out.reverse()
         return out
 
-    def extended_newick(self):
-        """Newick with `{edge_index}` after every non-root node (jutil.py:22-96), same number formatting."""
+    def extended_newick(self, native=None):
+        """Newick with `{edge_index}` after every non-root node (jutil.py:22-96), same number formatting.  Written by
+        apples_newick_extended (hostio.cpp) when the library is there; the Python body below is the definition."""
+        if native is not False:
+            s = self._extended_newick_native()
+            if s is not None:
+                return s
+            if native is True:
+                raise ValueError('the native extended-newick writer declined this tree')
         M = self.num_nodes
         strs = [None] * M
         pend = [[] for _ in range(M)]
@@ -181,6 +238,38 @@ class BackboneTree:
         if self.is_rooted:
             return '[&R] %s;' % root
         return '%s;' % root
+
+
+def _extended_newick_native(self):
+    import ctypes as C
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except (RuntimeError, OSError):
+        return None
+    M = self.num_nodes
+    enc = [None if l is None else str(l).encode('utf-8', 'surrogateescape') for l in self.label]
+    has_label = np.fromiter((l is not None for l in enc), dtype=np.uint8, count=M)
+    off = np.zeros(M + 1, dtype=np.int64)
+    np.cumsum(np.fromiter((0 if l is None else len(l) for l in enc), dtype=np.int64, count=M), out=off[1:])
+    blob = b''.join(l for l in enc if l is not None)
+    has_len = np.ascontiguousarray(self.has_length, dtype=np.uint8)
+    out, n = C.c_void_p(), C.c_int64(0)
+    err = C.create_string_buffer(256)
+    rc = lib.apples_newick_extended(M, _lib.ptr(self.parent), _lib.ptr(self.edge_length), _lib.ptr(has_len), blob,
+                                    _lib.ptr(off), _lib.ptr(has_label), 1 if self.is_rooted else 0, C.byref(out), C.byref(n),
+                                    err, 256)
+    if rc == _lib.NEWICK_UNSUPPORTED:
+        return None
+    if rc != 0:
+        raise ValueError(err.value.decode())
+    try:
+        return C.string_at(out, n.value).decode('utf-8', 'surrogateescape')
+    finally:
+        lib.apples_free_text(out)
+
+
+BackboneTree._extended_newick_native = _extended_newick_native
 
 
 def prepare_tree(tree_fp):

@@ -204,6 +204,36 @@ int apples_jplace_write(const char* path, const char* prefix, const char* suffix
                         const double* distal, const double* pendant, const int32_t* status, int exclude_intplace,
                         int n_threads, int64_t* n_written, char* err, int errlen);
 
+/* Newick text -> flat post-order arrays, replacing treeswift.read_tree_newick + index_edges + set_levels
+ * (apples/prepareTree.py:24, apples/util.py:57-88): node id = edge_index = post-order rank (children left to right, root
+ * last); parent (-1 for the root), edge_length (0 where the text has none) + has_length, level (root 0), first (smallest
+ * id of the subtree), labels (bytes of the text, concatenated; label_offsets n + 1; has_label tells "" from none).
+ * Returns 0, a negative value on bad arguments, or APPLES_NEWICK_UNSUPPORTED for text this parser does not take
+ * (unbalanced brackets or quotes, branch lengths that are not plain decimals, exotic blanks): the caller then uses its
+ * own parser (apples_b200/tree.py, the definition of the accepted language). */
+#define APPLES_NEWICK_UNSUPPORTED 1
+typedef struct apples_newick apples_newick;
+int apples_newick_parse(const char* text, int64_t len, apples_newick** out, char* err, int errlen);
+void apples_newick_free(apples_newick* t);
+int64_t apples_newick_nodes(const apples_newick* t);
+int apples_newick_rooted(const apples_newick* t);             /* text starts with [&R] */
+const int32_t* apples_newick_parent(const apples_newick* t);
+const int32_t* apples_newick_level(const apples_newick* t);
+const int32_t* apples_newick_first(const apples_newick* t);
+const double* apples_newick_edge_length(const apples_newick* t);
+const uint8_t* apples_newick_has_length(const apples_newick* t);
+const uint8_t* apples_newick_has_label(const apples_newick* t);
+const char* apples_newick_labels(const apples_newick* t);
+const int64_t* apples_newick_label_offsets(const apples_newick* t);
+
+/* Flat arrays -> the newick string with `{edge_index}` after every non-root node, replacing jutil.extended_newick
+ * (apples/jutil.py:22-96): lengths as str(int(x)) when integral, else Python's float repr; "[&R] " in front when rooted.
+ * *out_text is malloc'ed (apples_free_text).  APPLES_NEWICK_UNSUPPORTED: an integral length beyond 9e18. */
+int apples_newick_extended(int64_t n, const int32_t* parent, const double* edge_length, const uint8_t* has_length,
+                           const char* labels, const int64_t* label_offsets, const uint8_t* has_label, int rooted,
+                           char** out_text, int64_t* out_len, char* err, int errlen);
+void apples_free_text(char* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -304,3 +304,65 @@ def test_native_jplace_writer_equals_python_writer(tmp_path):
             nw = jplace.write_arrays(fp, names, inb, out, '((a,b),c);', ex, argv=['run_apples.py', '-x'], threads=th)
             assert open(fp, encoding='utf-8').read() == ref, (n, fb, ex, th)
             assert nw == len(doc['placements'])
+
+
+def _same_tree(a, b):
+    assert (a.parent == b.parent).all() and (a.level == b.level).all() and (a.first == b.first).all()
+    assert a.edge_length.tobytes() == b.edge_length.tobytes() and (a.has_length == b.has_length).all()
+    assert a.label == b.label and a.is_rooted == b.is_rooted and a.name_to_node == b.name_to_node
+    assert (a.nchild == b.nchild).all() and (a.leaf_ids == b.leaf_ids).all()
+
+
+def test_native_newick_equals_python_twin(workdir):
+    """apples_newick_parse / apples_newick_extended (hostio.cpp) against BackboneTree's Python parser and writer, which
+    define the accepted language: the golden backbones, random trees with polytomies, and hand-written corner cases;
+    text outside the native parser's language must come back as 'unsupported' and then parse through the Python twin."""
+    from apples_b200.tree import BackboneTree
+    texts = []
+    for f in ('backbone.nwk', 'small_backbone.nwk', 'syn300.nwk', 'prot_backbone.nwk'):
+        texts.append(open(util.gunzip_to(f, workdir)).read())
+    for seed in range(5):
+        texts.append(synth.random_tree(50 + 37 * seed, seed=seed, polytomy_frac=0.3 if seed % 2 else 0.0))
+    texts += [
+        '(a:1,b:2.5,(c:1e-3,d:0.0)x:3)root;',
+        "[&R] ((a:1,b:2)90:0.5,('c d':1.25e+2,e:-0.5)'in ner':7);",
+        '((a,b),(c,d));',                                   # no lengths
+        '  (a:0.1[comment],b[&x=1]:2,(c:3,d:4)[c]:5);\n\n',  # comments, surrounding blanks
+        '(a:1,\n b:2,\r\n\t(c:3 , d:4) : 5 ) ;',           # blanks everywhere
+        '(a:10,b:3.0,(c:100000000000000000000,d:1e22):0.30000000000000004);',   # integral and shortest-repr lengths
+        '(a:+1.5,b:.5,(c:5.,d:1E3):2)lab:9;',               # root with a length (not written: the root has no edge)
+        'a;',                                               # a single node
+        '(a:1,b:2)',                                        # no terminator
+        "(a:1,'':2,(b:1,c:1)'':3);",                        # empty quoted labels are labels
+        '(äö:1,中文:2,(x:1,y:1)ß:3);',      # non-ASCII labels
+    ]
+    n_native = 0
+    for t in texts:
+        py = BackboneTree.from_newick(t, native=False)
+        auto = BackboneTree.from_newick(t)
+        _same_tree(py, auto)
+        nat = BackboneTree._from_newick_native(t)
+        if nat is not None:
+            n_native += 1
+            _same_tree(py, nat)
+        ext_py = py.extended_newick(native=False)
+        assert auto.extended_newick() == ext_py
+        ext_nat = auto._extended_newick_native()
+        assert ext_nat is None or ext_nat == ext_py
+    assert n_native >= len(texts) - 2     # the CJK label case and nothing much else may be declined
+    # outside the native language: declined, and the public entry point still equals the Python twin (or raises like it)
+    for t in ['(a:inf,b:nan);', '(a:1_0,b:2);', "(a:1,b:2]x);", "(a:1,'b:2);", '(a:0x10,b:1);', '(a:1,b:2));']:
+        assert BackboneTree._from_newick_native(t) is None, t
+        try:
+            py = BackboneTree.from_newick(t, native=False)
+        except Exception as e:   # the Python twin's own error (e.g. float('0x10')): the public entry point raises the same
+            with pytest.raises(type(e)):
+                BackboneTree.from_newick(t)
+            continue
+        _same_tree(py, BackboneTree.from_newick(t))
+        assert BackboneTree.from_newick(t).extended_newick() == py.extended_newick(native=False)
+    # integral lengths beyond 9e18 and non-finite lengths in the writer
+    big = BackboneTree.from_newick('(a:1e30,b:2);', native=False)
+    assert big._extended_newick_native() is None and big.extended_newick() == big.extended_newick(native=False)
+    nf = BackboneTree.from_newick('(a:inf,b:nan,c:-inf);', native=False)
+    assert nf.extended_newick() == nf.extended_newick(native=False) == '(a:inf{0},b:nan{1},c:-inf{2});'
