@@ -62,7 +62,7 @@ def gather_records(rec, n_total=None, out=None):
     return full[:n_total]
 
 
-_GATHER_BUFFERS = {}   # (n_total, per, device) -> (device SoA buffer, pinned host twin)
+_GATHER_BUFFERS = {}   # device -> (capacity in records, device SoA buffer, pinned host twin); grown, never one per batch size
 
 
 def _soa_views(buf, n):
@@ -103,11 +103,12 @@ def gather_placements(local, n_total, device=None):
     parts = unpack_records(full)
     if torch.device(device).type != 'cuda':
         return tuple(t.numpy() for t in parts)
-    key = (int(n_total), str(device))
-    if key not in _GATHER_BUFFERS:
-        _GATHER_BUFFERS[key] = (torch.empty(32 * n_total, dtype=torch.uint8, device=device),
+    key = str(device)
+    if key not in _GATHER_BUFFERS or _GATHER_BUFFERS[key][0] < n_total:
+        _GATHER_BUFFERS[key] = (int(n_total), torch.empty(32 * n_total, dtype=torch.uint8, device=device),
                                 torch.empty(32 * n_total, dtype=torch.uint8).pin_memory())
-    dbuf, hbuf = _GATHER_BUFFERS[key]
+    _, dbuf, hbuf = _GATHER_BUFFERS[key]
+    dbuf, hbuf = dbuf[:32 * n_total], hbuf[:32 * n_total]
     for dst, src in zip(_soa_views(dbuf, n_total), parts):
         dst.copy_(src)
     hbuf.copy_(dbuf, non_blocking=True)
