@@ -87,9 +87,12 @@ class GpuPlacer:
             d = reference.device_arrays_bytes(self.name_to_node)
             self.kind, self.L, self.ref_names = d['kind'], int(d['L']), d['ref_names']
             rb, rn, go, gm = d['ref_bytes'], d['ref_node'], d['group_offsets'], d['group_members']
-            self._check(self.lib.apples_set_reference_bytes(self.h, self.kind, self.L, rb.shape[0], _lib.ptr(rb),
-                                                            rb.shape[1], _lib.ptr(rn), len(go) - 1, _lib.ptr(go),
-                                                            _lib.ptr(gm)))
+            if not (rb.dtype == np.uint8 and rb.ndim == 2 and rb.strides[1] == 1 and rb.strides[0] >= rb.shape[1]):
+                rb = np.ascontiguousarray(rb, dtype=np.uint8)
+            # rows may be padded (the native reader's matrix): the stride is passed on, no gigabyte-sized copy
+            self._check(self.lib.apples_set_reference_bytes(self.h, self.kind, self.L, rb.shape[0], rb.ctypes.data,
+                                                            rb.strides[0] if rb.shape[0] else self.L, _lib.ptr(rn),
+                                                            len(go) - 1, _lib.ptr(go), _lib.ptr(gm)))
         else:
             self.set_reference_arrays(**reference.device_arrays(self.name_to_node))
         self.reference = reference
