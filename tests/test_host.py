@@ -366,3 +366,24 @@ def test_native_newick_equals_python_twin(workdir):
     assert big._extended_newick_native() is None and big.extended_newick() == big.extended_newick(native=False)
     nf = BackboneTree.from_newick('(a:inf,b:nan,c:-inf);', native=False)
     assert nf.extended_newick() == nf.extended_newick(native=False) == '(a:inf{0},b:nan{1},c:-inf{2});'
+
+
+def test_native_newick_fuzz_against_python_twin():
+    """30 000 random strings over the newick punctuation: whatever the native parser accepts must give the arrays and
+    the extended newick of the Python twin (it may decline anything; it must never differ or raise on its own)."""
+    import random
+    from apples_b200.tree import BackboneTree
+    rnd = random.Random(20260117)
+    alpha = "(((()))),,,,::;[]' ab1.e-+5 \n\t"
+    accepted = 0
+    for _ in range(30000):
+        t = ''.join(rnd.choice(alpha) for _ in range(rnd.randint(1, 24)))
+        nat = BackboneTree._from_newick_native(t)
+        if nat is None:
+            continue
+        accepted += 1
+        py = BackboneTree.from_newick(t, native=False)
+        _same_tree(py, nat)
+        ext = nat._extended_newick_native()
+        assert ext is None or ext == py.extended_newick(native=False), t
+    assert accepted > 3000
